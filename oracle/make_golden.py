@@ -1,0 +1,74 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (imported from
+/root/reference through oracle/ref_shims) on the seeded fixture weights.
+
+Run here (CPU container, has /root/reference):   python oracle/make_golden.py
+The GPU box has no /root/reference; it only reads the committed .npz files.
+TEST INFRASTRUCTURE ONLY.
+"""
+import copy
+import json
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = "/root/reference"
+sys.path[:0] = [REF, os.path.join(HERE, "ref_shims"), HERE]
+
+from fixture import make_state_dict, param_shapes  # noqa: E402
+
+CASES = [
+    # name, config, seed, (B,H,W), resolution_level
+    ("vits_120x160", "config_v2_vits14.json", 0, (1, 120, 160), None),
+    ("vits_pad_96x288_rl3", "config_v2_vits14.json", 1, (2, 96, 288), 3),
+]
+
+
+def seeded_rgb(shape, seed):
+    g = torch.Generator().manual_seed(1234 + seed)
+    b, h, w = shape
+    return torch.randint(0, 256, (b, 3, h, w), dtype=torch.uint8, generator=g)
+
+
+def main():
+    warnings.simplefilter("ignore")
+    from unidepth.models import UniDepthV2
+    out_dir = os.path.join(HERE, "..", "tests", "golden")
+    os.makedirs(out_dir, exist_ok=True)
+    for name, cfg_name, seed, shape, level in CASES:
+        cfg = json.load(open(os.path.join(REF, "configs", cfg_name)))
+        model = UniDepthV2(copy.deepcopy(cfg)).eval()
+        ref_sd = model.state_dict()
+        shapes = param_shapes(cfg)
+        assert list(shapes.keys()) == list(ref_sd.keys()) or set(shapes) == set(ref_sd), \
+            (set(shapes) ^ set(ref_sd))
+        for k, v in ref_sd.items():
+            assert tuple(v.shape) == tuple(shapes[k]), (k, v.shape, shapes[k])
+        sd = make_state_dict(cfg, seed)
+        info = model.load_state_dict(sd, strict=True)
+        if level is not None:
+            model.resolution_level = level
+        rgb = seeded_rgb(shape, seed)
+        out = model.infer(rgb)
+        arrays = {k: v.detach().cpu().numpy() for k, v in out.items()}
+        # depth_features is large; keep every 4th channel (the restatement is checked on those)
+        arrays["depth_features"] = arrays["depth_features"][:, ::4]
+        meta = dict(config=cfg_name, seed=seed, shape=list(shape), resolution_level=level)
+        np.savez_compressed(os.path.join(out_dir, name + ".npz"), __meta__=json.dumps(meta), **arrays)
+        d = arrays["depth"]
+        print(name, "depth range", float(d.min()), float(d.max()), "conf", float(arrays["confidence"].min()),
+              float(arrays["confidence"].max()), "K", arrays["intrinsics"][0].tolist())
+    # also copy the configs the tests need (JSON input format, not code)
+    for cfg_name in ("config_v2_vits14.json", "config_v2_vitl14.json", "config_v2_vitb14.json"):
+        cfg = json.load(open(os.path.join(REF, "configs", cfg_name)))
+        keep = {"model": cfg["model"],
+                "data": {"augmentations": {"shape_constraints": cfg["data"]["augmentations"]["shape_constraints"]}},
+                "training": {"losses": {}}}
+        json.dump(keep, open(os.path.join(out_dir, cfg_name), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,59 @@
+"""Pin the oracle: the torch-fp32 restatement (oracle/unidepth_oracle.py) must reproduce the
+outputs of the unmodified reference stored in tests/golden/*.npz (made by oracle/make_golden.py).
+Both are fp32 on CPU, so the tolerance is only summation-order noise."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import unidepth_oracle as O
+from fixture import make_state_dict
+
+CASES = ["vits_120x160", "vits_pad_96x288_rl3"]
+
+
+def _rgb(shape, seed):
+    g = torch.Generator().manual_seed(1234 + seed)
+    b, h, w = shape
+    return torch.randint(0, 256, (b, 3, h, w), dtype=torch.uint8, generator=g)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_matches_reference_golden(name, golden_dir):
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    meta = json.loads(str(z["__meta__"]))
+    cfg = json.load(open(os.path.join(golden_dir, meta["config"])))
+    sd = make_state_dict(cfg, meta["seed"])
+    out = O.infer_v2(sd, cfg, _rgb(meta["shape"], meta["seed"]), resolution_level=meta["resolution_level"])
+    assert set(out) == {"confidence", "intrinsics", "radius", "depth", "points", "rays", "depth_features"}
+    for k, v in out.items():
+        ref = torch.from_numpy(z[k])
+        got = v[:, ::4] if k == "depth_features" else v
+        assert got.shape == ref.shape, (k, got.shape, ref.shape)
+        # error relative to |ref|, floored at 10% of the tensor's mean magnitude so that
+        # zero-crossings of signed tensors (points.x, depth_features) do not blow it up
+        floor = 0.1 * ref.abs().mean().item()
+        err = ((got - ref).abs() / ref.abs().clamp(min=floor)).max().item()
+        print(k, "max rel err", err)
+        assert err < 3e-4, (k, err)
+    rel_depth = ((out["depth"] - torch.from_numpy(z["depth"])).abs() / torch.from_numpy(z["depth"])).max().item()
+    assert rel_depth < 5e-5, rel_depth
+    kk = out["intrinsics"]
+    kr = torch.from_numpy(z["intrinsics"])
+    for (i, j) in ((0, 0), (1, 1), (0, 2), (1, 2)):
+        assert ((kk[:, i, j] - kr[:, i, j]).abs() / kr[:, i, j].abs()).max().item() < 1e-5
+
+
+def test_shape_arithmetic_examples():
+    # SURVEY.md section 8 a1 (values produced by the reference functions)
+    assert O.get_resize_factor((480, 640), (2e5, 6e5))[1] == (490, 644)
+    assert O.get_resize_factor((1024, 1536), (2e5, 6e5))[1] == (644, 952)
+    pads, shp = O.get_paddings((480, 1600), (0.5, 2.5))
+    assert pads == (0, 0, 80, 80) and shp == (640, 1600)
+    pads, shp = O.get_paddings((1000, 400), (0.5, 2.5))
+    assert pads == (50, 50, 0, 0) and shp == (1000, 500)
+    levels = {0: (434, 574), 2: (490, 644), 5: (560, 742), 9: (658, 868)}
+    for lvl, hw in levels.items():
+        assert O.get_resize_factor((480, 640), O.resolve_pixel_bounds((2e5, 6e5), lvl))[1] == hw

@@ -1,0 +1,241 @@
+/* udb.h -- C ABI of libudb.so: the sm_100a kernels behind unidepth_b200's UniDepthV2.infer().
+ *
+ * The reference (lpiccinelli-eth/UniDepth) has no FFI on its inference path: every op below
+ * replaces a PyTorch library call made by the reference's Python (file:line cited per entry,
+ * relative to the reference repo root).  The Python host (unidepth_b200/) binds these with ctypes;
+ * INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; the caller (PyTorch's
+ *     caching allocator) owns all memory, the library never allocates, frees, copies to the host
+ *     or synchronises the device;
+ *   - every launch goes to the `stream` argument (a cudaStream_t passed as void*), so calls are
+ *     CUDA-graph capturable;
+ *   - return value 0 = OK; non-zero = error, message via udb_last_error() (thread-local);
+ *   - "f16" tensors are IEEE half, "f32" are float; activations that feed tensor-core GEMMs are
+ *     f16, residual streams / LayerNorm statistics / softmax / epilogue math are f32.
+ */
+#ifndef UDB_H_
+#define UDB_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UDB_VERSION 1
+
+int udb_version(void);
+const char* udb_last_error(void);
+/* Number of kernels launched by this library on the calling process since load (bench evidence). */
+int64_t udb_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Tensor-core GEMM  D = epilogue(A . W^T)  (tcgen05.mma kind::f16, fp32 accumulation in TMEM, TMA
+ * operand loads, persistent warp-specialised kernel).
+ * Replaces nn.Linear / nn.Conv2d(k=s=14) / nn.Conv2d(1x1, 3x3) / nn.ConvTranspose2d(k=s) calls:
+ *   unidepth/models/backbones/metadinov2/{patch_embed.py:82, attention.py:55-61, mlp.py:36-40},
+ *   unidepth/layers/{attention.py:119-138, mlp.py:29-34, upsample.py:171-180,218-222},
+ *   unidepth/models/unidepthv2/decoder.py:43,264,279,288-303.
+ * ------------------------------------------------------------------------------------------- */
+enum { UDB_A_MATRIX = 0, UDB_A_CONV3X3 = 1 };
+enum { UDB_ACT_NONE = 0, UDB_ACT_GELU = 1, UDB_ACT_LEAKY = 2 };
+enum { UDB_STORE_ROWS = 0, UDB_STORE_CONVT = 1, UDB_STORE_CONVTILE = 2, UDB_STORE_HEAD = 3 };
+
+typedef struct udb_gemm_t {
+  /* operands: A f16 [M,K] row-major (lda elements) or NHWC f16 image for UDB_A_CONV3X3;
+   * W f16 [N,K] row-major (ldw elements).  K-extent is zero-extended to a multiple of 64. */
+  const void* a;
+  const void* w;
+  int32_t M, N, K;
+  int32_t lda, ldw;
+  int32_t a_mode;
+  /* UDB_A_CONV3X3: input [B, H(+2), W(+2), C] f16 NHWC; K = 9*C ordered (dy,dx,c); the output
+   * pixel (y,x) reads input (y+dy+off, x+dx+off), off = -1 for zero padding (out-of-range taps
+   * read 0 through TMA out-of-bounds fill) or 0 when the input was padded by the caller
+   * (reflect padding, in_H = H+2, in_W = W+2). */
+  int32_t conv_B, conv_H, conv_W, conv_C, conv_inH, conv_inW, conv_off, conv_TH, conv_TW;
+  /* epilogue: v = acc + bias[n]; v = act(v); v *= gamma[n]; v += resid[...]; out = v;
+   * out2 = f16(leaky(v)) (optional second copy for the next conv's input) */
+  const float* bias;
+  const float* gamma;
+  const void* resid;
+  int32_t resid_f32; /* 1: f32, 0: f16 */
+  void* out;
+  int32_t out_f32;
+  void* out2;
+  int32_t act;
+  int32_t store_mode;
+  int64_t ldc; /* elements between consecutive output rows / pixels */
+  /* UDB_STORE_ROWS: out_row = (m / rows_per_group)*group_stride + m % rows_per_group + row_offset
+   * (rows_per_group <= 0: identity).  resid row = resid_mod > 0 ? m % resid_mod + resid_row_offset
+   * : out_row, with leading dimension ldr. */
+  int32_t rows_per_group, group_stride, row_offset;
+  int32_t resid_mod, resid_row_offset;
+  int64_t ldr;
+  /* UDB_STORE_CONVT: row m = (b, y, x) of a [B,h,w] grid; column n = (dy*k+dx)*Cout + co;
+   * writes NHWC pixel (b, y*k+dy, x*k+dx, co) of a [B, h*k, w*k, Cout] map. */
+  int32_t ct_k, ct_cout, ct_h, ct_w;
+  /* UDB_STORE_HEAD (N == 32): out_pixel = exp(clamp(sum_n head_w[n]*leaky(acc+bias)[n] + head_b,
+   * -8, 8) + head_add) written as f32 to out[b*H*W + y*W + x]. */
+  const float* head_w;
+  float head_b, head_add;
+} udb_gemm_t;
+
+int udb_gemm_f16(const udb_gemm_t* g, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused softmax(Q K^T / sqrt(d)) V  (flash-style, tcgen05 QK^T and PV, S/O accumulators in TMEM).
+ * Replaces F.scaled_dot_product_attention: metadinov2/attention.py:58, layers/attention.py:136.
+ * q/k/v are f16 matrices with row stride ld* (elements); head h occupies columns
+ * [col0 + h*head_dim, +head_dim).  Row of (batch b, position s) = b*seq + s.  out f16 [B*Sq, ldo].
+ * ------------------------------------------------------------------------------------------- */
+typedef struct udb_attn_t {
+  const void* q;
+  const void* k;
+  const void* v;
+  void* out;
+  int32_t B, heads, seq_q, seq_k, head_dim;
+  int32_t ldq, ldk, ldv, ldo;
+  int32_t q_col0, k_col0, v_col0, o_col0;
+  float scale; /* 1/sqrt(head_dim) */
+} udb_attn_t;
+
+int udb_attention_f16(const udb_attn_t* a, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * LayerNorm over the last dim (F.layer_norm): metadinov2/block.py:86,89 (eps 1e-6),
+ * dinov2.py:336-345 (final norm, eps 1e-5), layers/attention.py:116-117, layers/mlp.py:30,
+ * unidepthv2/decoder.py:190-199.  Input row r is read from in + in_row(r)*ld_in with
+ * in_row(r) = (r / rows_per_group)*group_stride + r % rows_per_group + row_offset (identity if
+ * rows_per_group <= 0) -- used to drop / pick the cls token of each image.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct udb_layernorm_t {
+  const void* in;
+  int32_t in_f32;
+  void* out;
+  int32_t out_f32;
+  const float* weight;
+  const float* bias;
+  int32_t rows, dim;
+  int64_t ld_in, ld_out;
+  int32_t rows_per_group, group_stride, row_offset;
+  float eps;
+} udb_layernorm_t;
+
+int udb_layernorm(const udb_layernorm_t* p, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Pre-processing + patch extraction (unidepthv2.py:288-297 + patch_embed.py:82's im2col):
+ * uint8 (or f32 0..255) NCHW -> /255 -> (x-mean)/std -> zero pad -> bilinear (align_corners=False)
+ * to (net_h, net_w) -> f16 patch matrix [B*gh*gw, ldp] with column c*196 + py*14 + px
+ * (columns >= 588 zero).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct udb_preprocess_t {
+  const void* rgb;
+  int32_t rgb_is_u8; /* 1: uint8, 0: float32 */
+  int32_t normalize;
+  int32_t B, H, W;
+  int32_t pad_l, pad_r, pad_t, pad_b;
+  int32_t net_h, net_w;
+  void* patches;
+  int32_t ldp;
+} udb_preprocess_t;
+
+int udb_preprocess_patchify(const udb_preprocess_t* p, void* stream);
+
+/* Bicubic (A=-0.75, align_corners=False, no antialias) resize of the [1,M,M,D] position grid to
+ * [gh,gw,D] (dinov2.py:267-304, interpolate_offset == 0).  f32 -> f32. */
+int udb_posembed_bicubic(const float* grid, int32_t m, int32_t dim, float* out, int32_t gh,
+                         int32_t gw, void* stream);
+
+/* x[b, 0, :] = cls_token + pos_embed[0]   (dinov2.py:314-315); x f32 [B, T, D]. */
+int udb_set_cls_rows(float* x, const float* cls_token, const float* pos0, int32_t B, int32_t T,
+                     int32_t D, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Small fp32 dense layer for the 4-token camera head (unidepthv2/decoder.py:101-111), kept in
+ * fp32 on CUDA cores to protect the 1e-4 intrinsics bar:
+ *   y[m, n] = resid[m,n] + gamma[n] * act(sum_k x[m,k] * w[n,k] + bias[n])      M <= 64
+ * ------------------------------------------------------------------------------------------- */
+typedef struct udb_small_linear_t {
+  const float* x;
+  const float* w;
+  const float* bias;
+  const float* gamma;
+  const float* resid;
+  float* y;
+  int32_t M, N, K;
+  int32_t act;
+} udb_small_linear_t;
+int udb_small_linear_f32(const udb_small_linear_t* p, void* stream);
+
+/* Self-attention over the 4 camera tokens, fp32 (layers/attention.py:110-138 with pos_embed added
+ * to q only).  q [B,4,C], kv [B,4,2C] (k then v), pos [4,C] -> out [B,4,C]. */
+int udb_camera_attn4_f32(const float* q, const float* kv, const float* pos, float* out, int32_t B,
+                         int32_t C, int32_t heads, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Camera tail + rays (unidepthv2/decoder.py:85-99, 361-403; utils/coordinate.py:4-20):
+ *   x[B,4] -> (fx,fy,cx,cy) = (exp,exp,sigmoid,sigmoid) * (0.7*diag, 0.7*diag, W, H)
+ *   K_net[B,3,3]; K_out[B,3,3] = post-processed (unidepthv2.py:92-108); intr4[B,4].
+ * ------------------------------------------------------------------------------------------- */
+int udb_camera_intrinsics(const float* x, int32_t B, int32_t net_h, int32_t net_w, float factor,
+                          int32_t pad_l, int32_t pad_t, float* intr4, float* k_net, float* k_out,
+                          void* stream);
+
+/* Ray embedding (unidepthv2/decoder.py:234-253; utils/geometric.py:227-252;
+ * utils/positional_embedding.py:218-256): unit rays from intr4 (or from rays_in [B,net_h*net_w,3]
+ * when not NULL) -> antialiased bilinear down-sample by `net/grid` -> renormalise -> polar,
+ * azimuth -> sin(angle * pi * scales[j]); out f32/f16 [B*gh*gw, 2*bands]. */
+typedef struct udb_ray_embed_t {
+  const float* intr4;
+  const float* rays_in;
+  const float* scales; /* [bands] */
+  int32_t B, net_h, net_w, gh, gw, bands;
+  void* out;
+  int32_t out_f32;
+} udb_ray_embed_t;
+int udb_ray_embed(const udb_ray_embed_t* p, void* stream);
+
+/* x2 bilinear up-sample, align_corners=False (layers/upsample.py:215), NHWC f16 -> f16.
+ * Optionally fused: out = up(x) is followed by nothing; see udb_gemm for the convT add. */
+int udb_upsample2x_nhwc_f16(const void* in, void* out, int32_t B, int32_t H, int32_t W, int32_t C,
+                            void* stream);
+
+/* Bilinear align_corners=True resize NHWC f16 [B,H,W,C] -> [B,oh,ow,C] written into a buffer
+ * reflect-padded by `pad` pixels on each side ([B,oh+2*pad,ow+2*pad,C]); pad = 0 gives the plain
+ * resize (unidepthv2/decoder.py:299-301 + the reflect pad of the following conv :207-219). */
+int udb_resize_ac_pad_nhwc_f16(const void* in, void* out, int32_t B, int32_t H, int32_t W,
+                               int32_t C, int32_t oh, int32_t ow, int32_t pad, void* stream);
+
+/* Reflect-pad by 1 pixel: NHWC f16 [B,H,W,C] -> [B,H+2,W+2,C] (nn.Conv2d padding_mode="reflect",
+ * unidepthv2/decoder.py:200-213). */
+int udb_reflect_pad1_nhwc_f16(const void* in, void* out, int32_t B, int32_t H, int32_t W, int32_t C,
+                              void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Output assembly (unidepthv2.py:80-89, 311-339, 375-377; unidepthv2/decoder.py:456-462):
+ * radius/confidence f32 [B,net_h,net_w] (already exp'ed), rays from intr4 (or rays_in) ->
+ * points = rays*radius -> bilinear (align_corners=False) to (padded_h, padded_w) -> crop pads ->
+ * confidence[B,1,H,W], radius[B,1,H,W]=|points|, depth[B,1,H,W]=points.z, points[B,3,H,W],
+ * rays[B,3,H,W] renormalised.  All f32.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct udb_postprocess_t {
+  const float* radius;
+  const float* confidence;
+  const float* intr4;
+  const float* rays_in; /* optional [B, net_h*net_w, 3] */
+  int32_t B, net_h, net_w, padded_h, padded_w, pad_l, pad_t, H, W;
+  float* out_confidence;
+  float* out_radius;
+  float* out_depth;
+  float* out_points;
+  float* out_rays;
+} udb_postprocess_t;
+int udb_postprocess(const udb_postprocess_t* p, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UDB_H_ */

@@ -1,0 +1,39 @@
+"""Fused attention kernel vs torch softmax(QK^T/sqrt(d))V in fp32 on the same f16 inputs."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(q, k, v):
+    q, k, v = q.float(), k.float(), v.float()
+    a = torch.softmax(q @ k.transpose(-1, -2) * q.shape[-1] ** -0.5, dim=-1)
+    return a @ v
+
+
+@pytest.mark.parametrize("B,H,Sq,Sk", [(1, 1, 128, 128), (1, 2, 128, 256), (2, 3, 200, 200), (2, 16, 1611, 1611),
+                                       (1, 8, 1610, 1610), (1, 4, 77, 300)])
+def test_attention_fused_qkv_layout(B, H, Sq, Sk):
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from unidepth_b200 import ops
+    dev = torch.device("cuda:0")
+    torch.manual_seed(Sq + H)
+    d = 64
+    D = H * d
+    if Sq == Sk:
+        qkv = torch.randn(B * Sq, 3 * D, device=dev).half()      # [3][H][d] column layout (ViT qkv)
+        out = torch.empty(B * Sq, D, device=dev, dtype=torch.float16)
+        ops.attention(qkv, qkv, qkv, out, B=B, heads=H, seq_q=Sq, seq_k=Sk, head_dim=d, q_col0=0, k_col0=D, v_col0=2 * D)
+        q, k, v = qkv.view(B, Sq, 3, H, d).permute(2, 0, 3, 1, 4)
+    else:
+        qm = torch.randn(B * Sq, D, device=dev).half()
+        kv = torch.randn(B * Sk, 2 * D, device=dev).half()       # [k(H d); v(H d)] (decoder kv)
+        out = torch.empty(B * Sq, D, device=dev, dtype=torch.float16)
+        ops.attention(qm, kv, kv, out, B=B, heads=H, seq_q=Sq, seq_k=Sk, head_dim=d, k_col0=0, v_col0=D)
+        q = qm.view(B, Sq, H, d).permute(0, 2, 1, 3)
+        k, v = kv.view(B, Sk, 2, H, d).permute(2, 0, 3, 1, 4)
+    ref = _ref(q, k, v).permute(0, 2, 1, 3).reshape(B * Sq, D)
+    err = (out.float() - ref).abs().max().item()
+    print(f"attention B{B} H{H} Sq{Sq} Sk{Sk}: max abs err {err:.3e} (ref max {ref.abs().max().item():.3e})")
+    assert err < 4e-3

@@ -1,0 +1,142 @@
+"""tcgen05 GEMM / conv / convT kernel vs a plain PyTorch fp32 reference of the same op (operands
+rounded to f16 exactly as the kernel sees them, fp32 math).  Tolerances: fp32 accumulation-order
+noise for f32 outputs, one f16 ulp for f16 outputs."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    return torch.device("cuda:0")
+
+
+def _close(got, ref, tol, name):
+    got, ref = got.float(), ref.float()
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    print(f"{name}: max abs err {err:.3e} (ref max {scale:.3e})")
+    assert err <= tol * max(scale, 1.0), (name, err, scale)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 128, 128), (1000, 1024, 1024), (12888, 3072, 1024),
+                                   (1611, 384, 1536), (300, 64, 640), (130, 32, 192), (256, 64, 200)])
+def test_gemm_plain(M, N, K):
+    from unidepth_b200 import ops
+    dev = _dev()
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N)
+    a = torch.randn(M, K, generator=g).to(dev).half()
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(dev).half()
+    bias = torch.randn(N, generator=g).to(dev)
+    ref = a.float() @ w.float().t() + bias
+    out32 = ops.gemm(a, w, bias=bias, out_dtype=torch.float32)
+    _close(out32, ref, 2e-5, f"gemm f32 {M}x{N}x{K}")
+    out16 = ops.gemm(a, w, bias=bias, out_dtype=torch.float16)
+    _close(out16, ref, 1e-3, f"gemm f16 {M}x{N}x{K}")
+
+
+def test_gemm_epilogues():
+    from unidepth_b200 import ops
+    dev = _dev()
+    torch.manual_seed(0)
+    M, N, K = 777, 512, 256
+    a = torch.randn(M, K, device=dev).half()
+    w = (torch.randn(N, K, device=dev) / K ** 0.5).half()
+    bias = torch.randn(N, device=dev)
+    gamma = torch.rand(N, device=dev) + 0.5
+    resid = torch.randn(M, N, device=dev)
+    lin = a.float() @ w.float().t() + bias
+    _close(ops.gemm(a, w, bias=bias, act=ops.ACT_GELU, out_dtype=torch.float32), F.gelu(lin), 2e-5, "gelu")
+    _close(ops.gemm(a, w, bias=bias, act=ops.ACT_LEAKY, out_dtype=torch.float32), F.leaky_relu(lin, 0.01), 2e-5, "leaky")
+    _close(ops.gemm(a, w, bias=bias, gamma=gamma, resid=resid, out_dtype=torch.float32), resid + gamma * lin, 2e-5, "gamma+resid f32")
+    r16 = resid.half()
+    _close(ops.gemm(a, w, bias=bias, resid=r16, out_dtype=torch.float32), r16.float() + lin, 2e-5, "resid f16")
+    # in-place residual stream (out aliases resid)
+    x = resid.clone()
+    ops.gemm(a, w, bias=bias, gamma=gamma, resid=x, out=x)
+    _close(x, resid + gamma * lin, 2e-5, "in-place residual")
+    # second output = leaky(out) in f16
+    out2 = torch.empty(M, N, device=dev, dtype=torch.float16)
+    o = ops.gemm(a, w, bias=bias, out_dtype=torch.float32, out2=out2)
+    _close(out2, F.leaky_relu(o, 0.01), 1e-3, "out2 leaky")
+    # row mapping: tokens of B images -> rows b*T + 1 + n, residual = pos[1 + n]
+    Bn, Np = 3, 259
+    T = Np + 1
+    a2 = torch.randn(Bn * Np, K, device=dev).half()
+    pos = torch.randn(T, N, device=dev)
+    x = torch.zeros(Bn * T, N, device=dev)
+    ops.gemm(a2, w, bias=bias, resid=pos, out=x, rows_per_group=Np, group_stride=T, row_offset=1,
+             resid_mod=Np, resid_row_offset=1)
+    ref = (a2.float() @ w.float().t() + bias).view(Bn, Np, N) + pos[1:]
+    _close(x.view(Bn, T, N)[:, 1:], ref, 2e-5, "token row mapping")
+    assert x.view(Bn, T, N)[:, 0].abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("B,H,W,C,N,tile", [(1, 16, 32, 64, 64, (8, 16)), (2, 35, 46, 128, 256, (8, 16)),
+                                            (1, 70, 92, 256, 128, (8, 16)), (1, 20, 33, 64, 32, (4, 32))])
+def test_conv3x3_zero_pad(B, H, W, C, N, tile):
+    from unidepth_b200 import ops
+    dev = _dev()
+    torch.manual_seed(1)
+    x = torch.randn(B, C, H, W, device=dev).half()
+    w = (torch.randn(N, C, 3, 3, device=dev) / (9 * C) ** 0.5).half()
+    bias = torch.randn(N, device=dev)
+    ref = F.conv2d(x.float(), w.float(), bias, padding=1).permute(0, 2, 3, 1)
+    xn = x.permute(0, 2, 3, 1).contiguous()
+    wp = w.permute(0, 2, 3, 1).reshape(N, 9 * C).contiguous()
+    out = ops.conv3x3(xn, wp, bias=bias, out_dtype=torch.float32, tile=tile)
+    _close(out, ref, 3e-5, f"conv3x3 {B}x{H}x{W}x{C}->{N}")
+    # RCU-style epilogue: gamma*conv + x, plus leaky copy
+    if N == C:
+        gamma = torch.rand(N, device=dev) + 0.5
+        out2 = torch.empty(B, H, W, N, device=dev, dtype=torch.float16)
+        o = ops.conv3x3(xn, wp, bias=bias, gamma=gamma, resid=xn, out_dtype=torch.float16, out2=out2)
+        r = gamma * ref + xn.float()
+        _close(o, r, 1.5e-3, "conv3x3 rcu epilogue")
+        _close(out2, F.leaky_relu(r, 0.01), 1.5e-3, "conv3x3 rcu out2")
+
+
+def test_conv3x3_reflect_and_head():
+    from unidepth_b200 import ops
+    dev = _dev()
+    torch.manual_seed(2)
+    B, H, W, C, N = 2, 37, 50, 64, 32
+    x = torch.randn(B, C, H, W, device=dev).half()
+    w = (torch.randn(N, C, 3, 3, device=dev) / (9 * C) ** 0.5).half()
+    bias = torch.randn(N, device=dev)
+    xp = F.pad(x.float(), (1, 1, 1, 1), mode="reflect")
+    ref = F.conv2d(xp, w.float(), bias)
+    xn = x.permute(0, 2, 3, 1).contiguous()
+    wp = w.permute(0, 2, 3, 1).reshape(N, 9 * C).contiguous()
+    xpad = ops.reflect_pad1(xn)
+    assert torch.equal(xpad.float(), xp.permute(0, 2, 3, 1))
+    out = ops.conv3x3(xpad, wp, bias=bias, out_dtype=torch.float32, prepadded=True)
+    _close(out, ref.permute(0, 2, 3, 1), 3e-5, "conv3x3 reflect")
+    hw = torch.randn(32, device=dev) * 0.3
+    hb = 0.1
+    head = ops.conv3x3(xpad, wp, bias=bias, prepadded=True, act=ops.ACT_LEAKY, head_w=hw, head_b=hb, head_add=2.0)
+    hr = torch.exp((F.leaky_relu(ref, 0.01) * hw.view(1, -1, 1, 1)).sum(1).add(hb).clip(-8, 8) + 2.0)
+    _close(head, hr, 3e-5, "conv3x3 head")
+
+
+@pytest.mark.parametrize("k,cout", [(1, 128), (2, 64), (4, 32)])
+def test_conv_transpose(k, cout):
+    from unidepth_b200 import ops
+    dev = _dev()
+    torch.manual_seed(3)
+    B, h, w_, cin = 2, 9, 13, 128
+    x = torch.randn(B, cin, h, w_, device=dev).half()
+    wt = (torch.randn(cin, cout, k, k, device=dev) / cin ** 0.5).half()
+    bias = torch.randn(cout, device=dev)
+    lat = torch.randn(B, h * k, w_ * k, cout, device=dev).half()
+    ref = F.conv_transpose2d(x.float(), wt.float(), bias, stride=k).permute(0, 2, 3, 1) + lat.float()
+    xm = x.permute(0, 2, 3, 1).reshape(B * h * w_, cin).contiguous()
+    wp = wt.permute(2, 3, 1, 0).reshape(k * k * cout, cin).contiguous()
+    bp = bias.repeat(k * k).contiguous()
+    out2 = torch.empty_like(lat)
+    out = ops.conv_transpose_ks(xm, wp, k, cout, (h, w_), bias=bp, resid=lat, out=lat.clone(), out2=out2)
+    _close(out, ref, 1.5e-3, f"convT k={k}")
+    _close(out2, F.leaky_relu(ref, 0.01), 1.5e-3, f"convT k={k} out2")

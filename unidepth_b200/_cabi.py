@@ -1,0 +1,129 @@
+"""ctypes binding of libudb.so (include/udb.h).  Thin: structures mirror the C structs field for
+field; every call raises RuntimeError with udb_last_error() on a non-zero return.  There is no
+fallback: if the library is missing the import fails loudly."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libudb.so")
+
+A_MATRIX, A_CONV3X3 = 0, 1
+ACT_NONE, ACT_GELU, ACT_LEAKY = 0, 1, 2
+STORE_ROWS, STORE_CONVT, STORE_CONVTILE, STORE_HEAD = 0, 1, 2, 3
+
+vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+
+
+class Gemm(C.Structure):
+    _fields_ = [
+        ("a", vp), ("w", vp), ("M", i32), ("N", i32), ("K", i32), ("lda", i32), ("ldw", i32),
+        ("a_mode", i32),
+        ("conv_B", i32), ("conv_H", i32), ("conv_W", i32), ("conv_C", i32), ("conv_inH", i32),
+        ("conv_inW", i32), ("conv_off", i32), ("conv_TH", i32), ("conv_TW", i32),
+        ("bias", vp), ("gamma", vp), ("resid", vp), ("resid_f32", i32), ("out", vp), ("out_f32", i32),
+        ("out2", vp), ("act", i32), ("store_mode", i32), ("ldc", i64),
+        ("rows_per_group", i32), ("group_stride", i32), ("row_offset", i32),
+        ("resid_mod", i32), ("resid_row_offset", i32), ("ldr", i64),
+        ("ct_k", i32), ("ct_cout", i32), ("ct_h", i32), ("ct_w", i32),
+        ("head_w", vp), ("head_b", f32), ("head_add", f32),
+    ]
+
+
+class Attn(C.Structure):
+    _fields_ = [
+        ("q", vp), ("k", vp), ("v", vp), ("out", vp),
+        ("B", i32), ("heads", i32), ("seq_q", i32), ("seq_k", i32), ("head_dim", i32),
+        ("ldq", i32), ("ldk", i32), ("ldv", i32), ("ldo", i32),
+        ("q_col0", i32), ("k_col0", i32), ("v_col0", i32), ("o_col0", i32), ("scale", f32),
+    ]
+
+
+class LayerNorm(C.Structure):
+    _fields_ = [
+        ("inp", vp), ("in_f32", i32), ("out", vp), ("out_f32", i32), ("weight", vp), ("bias", vp),
+        ("rows", i32), ("dim", i32), ("ld_in", i64), ("ld_out", i64),
+        ("rows_per_group", i32), ("group_stride", i32), ("row_offset", i32), ("eps", f32),
+    ]
+
+
+class Preprocess(C.Structure):
+    _fields_ = [
+        ("rgb", vp), ("rgb_is_u8", i32), ("normalize", i32), ("B", i32), ("H", i32), ("W", i32),
+        ("pad_l", i32), ("pad_r", i32), ("pad_t", i32), ("pad_b", i32), ("net_h", i32), ("net_w", i32),
+        ("patches", vp), ("ldp", i32),
+    ]
+
+
+class SmallLinear(C.Structure):
+    _fields_ = [
+        ("x", vp), ("w", vp), ("bias", vp), ("gamma", vp), ("resid", vp), ("y", vp),
+        ("M", i32), ("N", i32), ("K", i32), ("act", i32),
+    ]
+
+
+class RayEmbed(C.Structure):
+    _fields_ = [
+        ("intr4", vp), ("rays_in", vp), ("scales", vp),
+        ("B", i32), ("net_h", i32), ("net_w", i32), ("gh", i32), ("gw", i32), ("bands", i32),
+        ("out", vp), ("out_f32", i32),
+    ]
+
+
+class Postprocess(C.Structure):
+    _fields_ = [
+        ("radius", vp), ("confidence", vp), ("intr4", vp), ("rays_in", vp),
+        ("B", i32), ("net_h", i32), ("net_w", i32), ("padded_h", i32), ("padded_w", i32),
+        ("pad_l", i32), ("pad_t", i32), ("H", i32), ("W", i32),
+        ("out_confidence", vp), ("out_radius", vp), ("out_depth", vp), ("out_points", vp), ("out_rays", vp),
+    ]
+
+
+EXPORTS = {
+    "udb_version": (i32, []),
+    "udb_last_error": (C.c_char_p, []),
+    "udb_launch_count": (i64, []),
+    "udb_gemm_f16": (i32, [C.POINTER(Gemm), vp]),
+    "udb_attention_f16": (i32, [C.POINTER(Attn), vp]),
+    "udb_layernorm": (i32, [C.POINTER(LayerNorm), vp]),
+    "udb_preprocess_patchify": (i32, [C.POINTER(Preprocess), vp]),
+    "udb_posembed_bicubic": (i32, [vp, i32, i32, vp, i32, i32, vp]),
+    "udb_set_cls_rows": (i32, [vp, vp, vp, i32, i32, i32, vp]),
+    "udb_small_linear_f32": (i32, [C.POINTER(SmallLinear), vp]),
+    "udb_camera_attn4_f32": (i32, [vp, vp, vp, vp, i32, i32, i32, vp]),
+    "udb_camera_intrinsics": (i32, [vp, i32, i32, i32, f32, i32, i32, vp, vp, vp, vp]),
+    "udb_ray_embed": (i32, [C.POINTER(RayEmbed), vp]),
+    "udb_upsample2x_nhwc_f16": (i32, [vp, vp, i32, i32, i32, i32, vp]),
+    "udb_resize_ac_pad_nhwc_f16": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]),
+    "udb_reflect_pad1_nhwc_f16": (i32, [vp, vp, i32, i32, i32, i32, vp]),
+    "udb_postprocess": (i32, [C.POINTER(Postprocess), vp]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load libudb.so (built by unidepth_b200.build).  Raises if it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build the CUDA extension first (python -m unidepth_b200.build). "
+                "unidepth_b200 has no CPU / PyTorch fallback.")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in EXPORTS.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed: {lib().udb_last_error().decode()}")
+
+
+def launch_count() -> int:
+    return int(lib().udb_launch_count())

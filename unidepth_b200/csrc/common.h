@@ -1,0 +1,34 @@
+// Host-side helpers shared by the .cu files: error reporting, launch counting, TMA tensor maps.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+
+#include "../../include/udb.h"
+
+namespace udb {
+
+void set_error(const char* fmt, ...);
+extern std::atomic<int64_t> g_launches;
+
+inline int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return 1;
+  }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+int num_sms();
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda).
+// dims/strides innermost first; strides_bytes has rank-1 entries (stride of dim 1..rank-1).
+int make_tmap_f16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                  const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128);
+
+}  // namespace udb

@@ -1,0 +1,547 @@
+// HBM-bound / latency-bound kernels of the UniDepthV2.infer() path: LayerNorm, preprocessing +
+// patch extraction, position-embedding resize, the fp32 camera head, ray embedding, bilinear
+// resamplers and the output assembly.  Reference call sites are cited in include/udb.h.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace udb {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ------------------------------------------------------------------------------------ LayerNorm
+// one warp per row; dim % 128 == 0, dim <= 1024; lane owns float4 #(lane + 32*i)
+template <bool IN_F32, bool OUT_F32>
+__global__ void __launch_bounds__(256) layernorm_kernel(const udb_layernorm_t p) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= p.rows) return;
+  long long irow = row;
+  if (p.rows_per_group > 0)
+    irow = (long long)(row / p.rows_per_group) * p.group_stride + (row % p.rows_per_group) + p.row_offset;
+  const int nvec = p.dim >> 7;  // float4 per lane
+  float4 x[8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (i < nvec) {
+      const int e = (lane + 32 * i) * 4;
+      if (IN_F32) {
+        x[i] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.in) + irow * p.ld_in + e);
+      } else {
+        const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(p.in) + irow * p.ld_in + e);
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+        x[i] = make_float4(a.x, a.y, b.x, b.y);
+      }
+      s += (x[i].x + x[i].y) + (x[i].z + x[i].w);
+    }
+  }
+  const float mean = warp_sum(s) / (float)p.dim;
+  float v = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (i < nvec) {
+      const float a = x[i].x - mean, b = x[i].y - mean, c = x[i].z - mean, d = x[i].w - mean;
+      v += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(v) / (float)p.dim + p.eps);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (i < nvec) {
+      const int e = (lane + 32 * i) * 4;
+      const float4 w = __ldg(reinterpret_cast<const float4*>(p.weight + e));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + e));
+      const float y0 = (x[i].x - mean) * rstd * w.x + b.x;
+      const float y1 = (x[i].y - mean) * rstd * w.y + b.y;
+      const float y2 = (x[i].z - mean) * rstd * w.z + b.z;
+      const float y3 = (x[i].w - mean) * rstd * w.w + b.w;
+      if (OUT_F32) {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (long long)row * p.ld_out + e) =
+            make_float4(y0, y1, y2, y3);
+      } else {
+        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out) + (long long)row * p.ld_out + e) =
+            make_uint2(pack_half2(y0, y1), pack_half2(y2, y3));
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ preprocess
+__device__ __forceinline__ void bilinear_src(float scale, int dst, int in_size, int& i0, int& i1, float& l0, float& l1) {
+  // ATen area_pixel_compute_source_index (align_corners=False): fp32 index arithmetic
+  float src = scale * ((float)dst + 0.5f) - 0.5f;
+  if (src < 0.f) src = 0.f;
+  i0 = (int)src;
+  if (i0 > in_size - 1) i0 = in_size - 1;
+  i1 = i0 + ((i0 < in_size - 1) ? 1 : 0);
+  l1 = src - (float)i0;
+  l0 = 1.f - l1;
+}
+
+__global__ void __launch_bounds__(256) preprocess_patchify_kernel(const udb_preprocess_t p, int gh, int gw, float sh, float sw) {
+  const long long total = (long long)p.B * gh * gw * p.ldp;
+  const float mean[3] = {0.485f, 0.456f, 0.406f};
+  const float stdv[3] = {0.229f, 0.224f, 0.225f};
+  const int padded_h = p.H + p.pad_t + p.pad_b, padded_w = p.W + p.pad_l + p.pad_r;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int col = (int)(idx % p.ldp);
+    const long long rowi = idx / p.ldp;
+    float val = 0.f;
+    if (col < 588) {
+      const int c = col / 196, py = (col % 196) / 14, px = col % 14;
+      const int gx = (int)(rowi % gw), gy = (int)((rowi / gw) % gh), b = (int)(rowi / ((long long)gw * gh));
+      const int Y = gy * 14 + py, X = gx * 14 + px;
+      int y0, y1, x0, x1;
+      float ly0, ly1, lx0, lx1;
+      bilinear_src(sh, Y, padded_h, y0, y1, ly0, ly1);
+      bilinear_src(sw, X, padded_w, x0, x1, lx0, lx1);
+      auto fetch = [&](int yy, int xx) -> float {
+        const int oy = yy - p.pad_t, ox = xx - p.pad_l;
+        if (oy < 0 || oy >= p.H || ox < 0 || ox >= p.W) return 0.f;
+        const long long o = (((long long)b * 3 + c) * p.H + oy) * p.W + ox;
+        float v = p.rgb_is_u8 ? (float)reinterpret_cast<const uint8_t*>(p.rgb)[o]
+                              : reinterpret_cast<const float*>(p.rgb)[o];
+        if (p.normalize) v = (v / 255.0f - mean[c]) / stdv[c];
+        return v;
+      };
+      val = ly0 * (lx0 * fetch(y0, x0) + lx1 * fetch(y0, x1)) + ly1 * (lx0 * fetch(y1, x0) + lx1 * fetch(y1, x1));
+    }
+    reinterpret_cast<__half*>(p.patches)[idx] = __float2half_rn(val);
+  }
+}
+
+// ------------------------------------------------------------------------------------ pos-embed bicubic
+__device__ __forceinline__ float cubic1(float x, float A) { return ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f; }
+__device__ __forceinline__ float cubic2(float x, float A) { return ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A; }
+
+__global__ void __launch_bounds__(256) posembed_bicubic_kernel(const float* __restrict__ grid, int m, int dim,
+                                                               float* __restrict__ out, int gh, int gw) {
+  const float A = -0.75f;
+  const float sy = (float)m / (float)gh, sx = (float)m / (float)gw;
+  const long long total = (long long)gh * gw * dim;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int d = (int)(idx % dim);
+    const int j = (int)((idx / dim) % gw);
+    const int i = (int)(idx / ((long long)dim * gw));
+    const float ry = sy * ((float)i + 0.5f) - 0.5f, rx = sx * ((float)j + 0.5f) - 0.5f;
+    const float fy = floorf(ry), fx = floorf(rx);
+    const int iy = (int)fy, ix = (int)fx;
+    const float ty = ry - fy, tx = rx - fx;
+    const float wy[4] = {cubic2(ty + 1.f, A), cubic1(ty, A), cubic1(1.f - ty, A), cubic2(2.f - ty, A)};
+    const float wx[4] = {cubic2(tx + 1.f, A), cubic1(tx, A), cubic1(1.f - tx, A), cubic2(2.f - tx, A)};
+    float acc = 0.f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int yy = min(max(iy - 1 + a, 0), m - 1);
+      float r = 0.f;
+#pragma unroll
+      for (int bq = 0; bq < 4; ++bq) {
+        const int xx = min(max(ix - 1 + bq, 0), m - 1);
+        r += wx[bq] * grid[((long long)yy * m + xx) * dim + d];
+      }
+      acc += wy[a] * r;
+    }
+    out[idx] = acc;
+  }
+}
+
+__global__ void set_cls_rows_kernel(float* x, const float* cls, const float* pos0, int B, int T, int D) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * D) return;
+  const int b = idx / D, d = idx % D;
+  x[(long long)b * T * D + d] = cls[d] + pos0[d];
+}
+
+// ------------------------------------------------------------------------------------ camera head (fp32)
+// one warp per 4 output features, 8 rows per pass
+__global__ void __launch_bounds__(128) small_linear_kernel(const udb_small_linear_t p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = (blockIdx.x * 4 + warp) * 4;
+  const int m0 = blockIdx.y * 8;
+  if (n0 >= p.N) return;
+  float acc[4][8];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int m = 0; m < 8; ++m) acc[a][m] = 0.f;
+  for (int k = lane; k < p.K; k += 32) {
+    float xv[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) xv[m] = (m0 + m < p.M) ? p.x[(long long)(m0 + m) * p.K + k] : 0.f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const float wv = (n0 + a < p.N) ? p.w[(long long)(n0 + a) * p.K + k] : 0.f;
+#pragma unroll
+      for (int m = 0; m < 8; ++m) acc[a][m] = fmaf(wv, xv[m], acc[a][m]);
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int m = 0; m < 8; ++m) acc[a][m] = warp_sum(acc[a][m]);
+  if (lane == 0) {
+    for (int a = 0; a < 4; ++a) {
+      const int n = n0 + a;
+      if (n >= p.N) break;
+      for (int m = 0; m < 8; ++m) {
+        if (m0 + m >= p.M) break;
+        float v = acc[a][m] + (p.bias ? p.bias[n] : 0.f);
+        if (p.act == UDB_ACT_GELU) v = gelu_erf(v);
+        if (p.gamma) v *= p.gamma[n];
+        if (p.resid) v += p.resid[(long long)(m0 + m) * p.N + n];
+        p.y[(long long)(m0 + m) * p.N + n] = v;
+      }
+    }
+  }
+}
+
+// one warp per (b, head, query token); 4 tokens
+__global__ void camera_attn4_kernel(const float* q, const float* kv, const float* pos, float* out, int B, int C, int heads) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (gw >= B * heads * 4) return;
+  const int t = gw % 4, h = (gw / 4) % heads, b = gw / (4 * heads);
+  const int d = C / heads;
+  const float scale = rsqrtf((float)d);
+  float s[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float a = 0.f;
+    for (int e = lane; e < d; e += 32) {
+      const float qv = q[((long long)b * 4 + t) * C + h * d + e] + pos[t * C + h * d + e];
+      a += qv * kv[((long long)b * 4 + j) * 2 * C + h * d + e];
+    }
+    s[j] = warp_sum(a) * scale;
+  }
+  const float mx = fmaxf(fmaxf(s[0], s[1]), fmaxf(s[2], s[3]));
+  float den = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { s[j] = expf(s[j] - mx); den += s[j]; }
+  for (int e = lane; e < d; e += 32) {
+    float a = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) a += s[j] * kv[((long long)b * 4 + j) * 2 * C + C + h * d + e];
+    out[((long long)b * 4 + t) * C + h * d + e] = a / den;
+  }
+}
+
+__global__ void camera_intrinsics_kernel(const float* x, int B, int net_h, int net_w, float factor, int pad_l,
+                                         int pad_t, float* intr4, float* k_net, float* k_out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float diag = sqrtf((float)(net_h * net_h + net_w * net_w));
+  const float fx = expf(x[b * 4 + 0]) * (0.7f * diag);
+  const float fy = expf(x[b * 4 + 1]) * (0.7f * diag);
+  const float cx = (1.f / (1.f + expf(-x[b * 4 + 2]))) * (float)net_w;
+  const float cy = (1.f / (1.f + expf(-x[b * 4 + 3]))) * (float)net_h;
+  intr4[b * 4 + 0] = fx; intr4[b * 4 + 1] = fy; intr4[b * 4 + 2] = cx; intr4[b * 4 + 3] = cy;
+  float* k = k_net + b * 9;
+  k[0] = fx; k[1] = 0.f; k[2] = cx; k[3] = 0.f; k[4] = fy; k[5] = cy; k[6] = 0.f; k[7] = 0.f; k[8] = 1.f;
+  float* o = k_out + b * 9;
+  o[0] = fx / factor; o[1] = 0.f; o[2] = cx / factor - (float)pad_l;
+  o[3] = 0.f; o[4] = fy / factor; o[5] = cy / factor - (float)pad_t;
+  o[6] = 0.f; o[7] = 0.f; o[8] = 1.f;
+}
+
+// ------------------------------------------------------------------------------------ rays
+__device__ __forceinline__ float3 unit_ray(const float4 k /*fx,fy,cx,cy*/, int y, int x) {
+  // K^-1 [u, v, 1]^T with u = x + 0.5, v = y + 0.5 (coords_grid), then L2-normalise (clamp 1e-5)
+  const float rx = (1.0f / k.x) * ((float)x + 0.5f) + (-k.z / k.x);
+  const float ry = (1.0f / k.y) * ((float)y + 0.5f) + (-k.w / k.y);
+  const float n = fmaxf(sqrtf(rx * rx + ry * ry + 1.0f), 1e-5f);
+  return make_float3(rx / n, ry / n, 1.0f / n);
+}
+
+// antialiased-bilinear tap range along one axis (ATen _upsample_bilinear2d_aa weights)
+__device__ __forceinline__ void aa_range(float scale, int o, int in_size, int& lo, int& cnt, float& center) {
+  const float support = (scale >= 1.f) ? scale : 1.f;
+  center = scale * ((float)o + 0.5f);
+  lo = max((int)(center - support + 0.5f), 0);
+  cnt = min((int)(center + support + 0.5f), in_size) - lo;
+}
+__device__ __forceinline__ float aa_w(float scale, int k, float center) {
+  const float inv = (scale >= 1.f) ? 1.f / scale : 1.f;
+  return fmaxf(0.f, 1.f - fabsf(((float)k - center + 0.5f) * inv));
+}
+
+// one warp per output token
+__global__ void __launch_bounds__(256) ray_embed_kernel(const udb_ray_embed_t p) {
+  const int tok = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const int n = p.gh * p.gw;
+  if (tok >= p.B * n) return;
+  const int b = tok / n, i = (tok % n) / p.gw, j = tok % p.gw;
+  const float sy = (float)p.net_h / (float)p.gh, sx = (float)p.net_w / (float)p.gw;
+  int ylo, ycnt, xlo, xcnt;
+  float yc, xc;
+  aa_range(sy, i, p.net_h, ylo, ycnt, yc);
+  aa_range(sx, j, p.net_w, xlo, xcnt, xc);
+  float4 k = make_float4(1.f, 1.f, 0.f, 0.f);
+  if (!p.rays_in) k = *reinterpret_cast<const float4*>(p.intr4 + b * 4);
+  float ax = 0.f, ay = 0.f, az = 0.f, wsum_y = 0.f, wsum_x = 0.f;
+  for (int a = 0; a < ycnt; ++a) wsum_y += aa_w(sy, ylo + a, yc);
+  for (int a = 0; a < xcnt; ++a) wsum_x += aa_w(sx, xlo + a, xc);
+  const int taps = ycnt * xcnt;
+  for (int t = lane; t < taps; t += 32) {
+    const int yy = ylo + t / xcnt, xx = xlo + t % xcnt;
+    const float w = (aa_w(sy, yy, yc) / wsum_y) * (aa_w(sx, xx, xc) / wsum_x);
+    float3 r;
+    if (p.rays_in) {
+      const float* rp = p.rays_in + ((long long)b * p.net_h * p.net_w + (long long)yy * p.net_w + xx) * 3;
+      r = make_float3(rp[0], rp[1], rp[2]);
+    } else {
+      r = unit_ray(k, yy, xx);
+    }
+    ax = fmaf(w, r.x, ax); ay = fmaf(w, r.y, ay); az = fmaf(w, r.z, az);
+  }
+  ax = warp_sum(ax); ay = warp_sum(ay); az = warp_sum(az);
+  const float nrm = fmaxf(sqrtf(ax * ax + ay * ay + az * az), 1e-4f);
+  ax /= nrm; ay /= nrm; az /= nrm;
+  const float polar = acosf(az);
+  const float xcl = fmaxf(fabsf(ax), 1e-3f) * ((ax >= 0.f) ? 1.f : -1.f);
+  const float azim = atan2f(ay, xcl);
+  const float pi = 3.14159265358979323846f;
+  for (int f = lane; f < 2 * p.bands; f += 32) {
+    const float ang = (f < p.bands) ? polar : azim;
+    const float sc = __ldg(p.scales + (f % p.bands));
+    const float v = sinf(ang * sc * pi);
+    if (p.out_f32) reinterpret_cast<float*>(p.out)[(long long)tok * 2 * p.bands + f] = v;
+    else reinterpret_cast<__half*>(p.out)[(long long)tok * 2 * p.bands + f] = __float2half_rn(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------ resamplers (NHWC f16, 8 ch / thread)
+__device__ __forceinline__ void lerp8(const uint4& a, const uint4& b, float wa, float wb, float (&acc)[8], float scale) {
+  const __half2* ha = reinterpret_cast<const __half2*>(&a);
+  const __half2* hb = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float2 fa = __half22float2(ha[q]), fb = __half22float2(hb[q]);
+    acc[2 * q] += scale * (wa * fa.x + wb * fb.x);
+    acc[2 * q + 1] += scale * (wa * fa.y + wb * fb.y);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+  return make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
+}
+
+__global__ void __launch_bounds__(256) upsample2x_kernel(const __half* __restrict__ in, __half* __restrict__ out, int B, int H, int W, int C) {
+  const int cv = C >> 3;
+  const long long total = (long long)B * (2 * H) * (2 * W) * cv;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(idx % cv);
+    const int X = (int)((idx / cv) % (2 * W));
+    const int Y = (int)((idx / ((long long)cv * 2 * W)) % (2 * H));
+    const int b = (int)(idx / ((long long)cv * 2 * W * 2 * H));
+    int y0, y1, x0, x1;
+    float ly0, ly1, lx0, lx1;
+    bilinear_src(0.5f, Y, H, y0, y1, ly0, ly1);
+    bilinear_src(0.5f, X, W, x0, x1, lx0, lx1);
+    const uint4* base = reinterpret_cast<const uint4*>(in) + (long long)b * H * W * cv + c8;
+    const uint4 v00 = base[((long long)y0 * W + x0) * cv], v01 = base[((long long)y0 * W + x1) * cv];
+    const uint4 v10 = base[((long long)y1 * W + x0) * cv], v11 = base[((long long)y1 * W + x1) * cv];
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    lerp8(v00, v01, lx0, lx1, acc, ly0);
+    lerp8(v10, v11, lx0, lx1, acc, ly1);
+    reinterpret_cast<uint4*>(out)[idx] = pack8(acc);
+  }
+}
+
+__device__ __forceinline__ int reflect_idx(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * (n - 1) - i : i); }
+
+__global__ void __launch_bounds__(256) resize_ac_pad_kernel(const __half* __restrict__ in, __half* __restrict__ out, int B, int H, int W,
+                                                            int C, int oh, int ow, int pad) {
+  const int cv = C >> 3;
+  const int ph = oh + 2 * pad, pw = ow + 2 * pad;
+  const float sh = (oh > 1) ? (float)(H - 1) / (float)(oh - 1) : 0.f;
+  const float sw = (ow > 1) ? (float)(W - 1) / (float)(ow - 1) : 0.f;
+  const long long total = (long long)B * ph * pw * cv;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(idx % cv);
+    const int PX = (int)((idx / cv) % pw);
+    const int PY = (int)((idx / ((long long)cv * pw)) % ph);
+    const int b = (int)(idx / ((long long)cv * pw * ph));
+    const int Y = reflect_idx(PY - pad, oh), X = reflect_idx(PX - pad, ow);
+    const float fy = sh * (float)Y, fx = sw * (float)X;
+    const int y0 = min((int)fy, H - 1), x0 = min((int)fx, W - 1);
+    const int y1 = y0 + ((y0 < H - 1) ? 1 : 0), x1 = x0 + ((x0 < W - 1) ? 1 : 0);
+    const float ly1 = fy - (float)y0, lx1 = fx - (float)x0;
+    const float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+    const uint4* base = reinterpret_cast<const uint4*>(in) + (long long)b * H * W * cv + c8;
+    const uint4 v00 = base[((long long)y0 * W + x0) * cv], v01 = base[((long long)y0 * W + x1) * cv];
+    const uint4 v10 = base[((long long)y1 * W + x0) * cv], v11 = base[((long long)y1 * W + x1) * cv];
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    lerp8(v00, v01, lx0, lx1, acc, ly0);
+    lerp8(v10, v11, lx0, lx1, acc, ly1);
+    reinterpret_cast<uint4*>(out)[idx] = pack8(acc);
+  }
+}
+
+__global__ void __launch_bounds__(256) reflect_pad1_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H, int W, int cv) {
+  const int ph = H + 2, pw = W + 2;
+  const long long total = (long long)B * ph * pw * cv;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(idx % cv);
+    const int PX = (int)((idx / cv) % pw);
+    const int PY = (int)((idx / ((long long)cv * pw)) % ph);
+    const int b = (int)(idx / ((long long)cv * pw * ph));
+    const int Y = reflect_idx(PY - 1, H), X = reflect_idx(PX - 1, W);
+    out[idx] = in[(((long long)b * H + Y) * W + X) * cv + c8];
+  }
+}
+
+// ------------------------------------------------------------------------------------ output assembly
+__global__ void __launch_bounds__(256) postprocess_kernel(const udb_postprocess_t p) {
+  const long long total = (long long)p.B * p.H * p.W;
+  const float sh = (float)p.net_h / (float)p.padded_h, sw = (float)p.net_w / (float)p.padded_w;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(idx % p.W), y = (int)((idx / p.W) % p.H), b = (int)(idx / ((long long)p.W * p.H));
+    int y0, y1, x0, x1;
+    float ly0, ly1, lx0, lx1;
+    bilinear_src(sh, y + p.pad_t, p.net_h, y0, y1, ly0, ly1);
+    bilinear_src(sw, x + p.pad_l, p.net_w, x0, x1, lx0, lx1);
+    float4 k = make_float4(1.f, 1.f, 0.f, 0.f);
+    if (!p.rays_in) k = *reinterpret_cast<const float4*>(p.intr4 + b * 4);
+    const int ys[2] = {y0, y1}, xs[2] = {x0, x1};
+    const float wy[2] = {ly0, ly1}, wx[2] = {lx0, lx1};
+    float conf = 0.f, px = 0.f, py = 0.f, pz = 0.f, rx = 0.f, ry = 0.f, rz = 0.f;
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      float c_r = 0.f, px_r = 0.f, py_r = 0.f, pz_r = 0.f, rx_r = 0.f, ry_r = 0.f, rz_r = 0.f;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const long long o = ((long long)b * p.net_h + ys[a]) * p.net_w + xs[c];
+        float3 r;
+        if (p.rays_in) { const float* rp = p.rays_in + o * 3; r = make_float3(rp[0], rp[1], rp[2]); }
+        else r = unit_ray(k, ys[a], xs[c]);
+        const float rad = p.radius[o];
+        c_r += wx[c] * p.confidence[o];
+        px_r += wx[c] * (r.x * rad); py_r += wx[c] * (r.y * rad); pz_r += wx[c] * (r.z * rad);
+        rx_r += wx[c] * r.x; ry_r += wx[c] * r.y; rz_r += wx[c] * r.z;
+      }
+      conf += wy[a] * c_r; px += wy[a] * px_r; py += wy[a] * py_r; pz += wy[a] * pz_r;
+      rx += wy[a] * rx_r; ry += wy[a] * ry_r; rz += wy[a] * rz_r;
+    }
+    const long long plane = (long long)p.H * p.W;
+    const long long pix = (long long)y * p.W + x;
+    p.out_confidence[b * plane + pix] = conf;
+    p.out_radius[b * plane + pix] = sqrtf(px * px + py * py + pz * pz);
+    p.out_depth[b * plane + pix] = pz;
+    p.out_points[(b * 3 + 0) * plane + pix] = px;
+    p.out_points[(b * 3 + 1) * plane + pix] = py;
+    p.out_points[(b * 3 + 2) * plane + pix] = pz;
+    const float rn = fmaxf(sqrtf(rx * rx + ry * ry + rz * rz), 1e-5f);
+    p.out_rays[(b * 3 + 0) * plane + pix] = rx / rn;
+    p.out_rays[(b * 3 + 1) * plane + pix] = ry / rn;
+    p.out_rays[(b * 3 + 2) * plane + pix] = rz / rn;
+  }
+}
+
+static inline int grid_for(long long total, int block = 256) {
+  long long g = (total + block - 1) / block;
+  const long long cap = (long long)num_sms() * 16;
+  return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+}  // namespace udb
+
+using namespace udb;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" int udb_layernorm(const udb_layernorm_t* p, void* stream) {
+  if (p->dim % 128 != 0 || p->dim > 1024) { set_error("udb_layernorm: dim %d unsupported (multiple of 128, <= 1024)", p->dim); return 1; }
+  const int grid = (p->rows + 7) / 8;
+  if (grid == 0) return 0;
+  if (p->in_f32 && p->out_f32) layernorm_kernel<true, true><<<grid, 256, 0, ST(stream)>>>(*p);
+  else if (p->in_f32) layernorm_kernel<true, false><<<grid, 256, 0, ST(stream)>>>(*p);
+  else if (p->out_f32) layernorm_kernel<false, true><<<grid, 256, 0, ST(stream)>>>(*p);
+  else layernorm_kernel<false, false><<<grid, 256, 0, ST(stream)>>>(*p);
+  return check_launch("layernorm_kernel");
+}
+
+extern "C" int udb_preprocess_patchify(const udb_preprocess_t* p, void* stream) {
+  if (p->net_h % 14 || p->net_w % 14 || p->ldp < 588) { set_error("udb_preprocess_patchify: bad shape"); return 1; }
+  const int gh = p->net_h / 14, gw = p->net_w / 14;
+  const int padded_h = p->H + p->pad_t + p->pad_b, padded_w = p->W + p->pad_l + p->pad_r;
+  const float sh = (float)padded_h / (float)p->net_h, sw = (float)padded_w / (float)p->net_w;
+  const long long total = (long long)p->B * gh * gw * p->ldp;
+  preprocess_patchify_kernel<<<grid_for(total), 256, 0, ST(stream)>>>(*p, gh, gw, sh, sw);
+  return check_launch("preprocess_patchify_kernel");
+}
+
+extern "C" int udb_posembed_bicubic(const float* grid, int32_t m, int32_t dim, float* out, int32_t gh, int32_t gw, void* stream) {
+  posembed_bicubic_kernel<<<grid_for((long long)gh * gw * dim), 256, 0, ST(stream)>>>(grid, m, dim, out, gh, gw);
+  return check_launch("posembed_bicubic_kernel");
+}
+
+extern "C" int udb_set_cls_rows(float* x, const float* cls_token, const float* pos0, int32_t B, int32_t T, int32_t D, void* stream) {
+  set_cls_rows_kernel<<<(B * D + 255) / 256, 256, 0, ST(stream)>>>(x, cls_token, pos0, B, T, D);
+  return check_launch("set_cls_rows_kernel");
+}
+
+extern "C" int udb_small_linear_f32(const udb_small_linear_t* p, void* stream) {
+  dim3 grid((p->N + 15) / 16, (p->M + 7) / 8);
+  small_linear_kernel<<<grid, 128, 0, ST(stream)>>>(*p);
+  return check_launch("small_linear_kernel");
+}
+
+extern "C" int udb_camera_attn4_f32(const float* q, const float* kv, const float* pos, float* out, int32_t B, int32_t C, int32_t heads, void* stream) {
+  const int warps = B * heads * 4;
+  camera_attn4_kernel<<<(warps * 32 + 127) / 128, 128, 0, ST(stream)>>>(q, kv, pos, out, B, C, heads);
+  return check_launch("camera_attn4_kernel");
+}
+
+extern "C" int udb_camera_intrinsics(const float* x, int32_t B, int32_t net_h, int32_t net_w, float factor, int32_t pad_l,
+                                     int32_t pad_t, float* intr4, float* k_net, float* k_out, void* stream) {
+  camera_intrinsics_kernel<<<(B + 63) / 64, 64, 0, ST(stream)>>>(x, B, net_h, net_w, factor, pad_l, pad_t, intr4, k_net, k_out);
+  return check_launch("camera_intrinsics_kernel");
+}
+
+extern "C" int udb_ray_embed(const udb_ray_embed_t* p, void* stream) {
+  const int toks = p->B * p->gh * p->gw;
+  ray_embed_kernel<<<(toks + 7) / 8, 256, 0, ST(stream)>>>(*p);
+  return check_launch("ray_embed_kernel");
+}
+
+extern "C" int udb_upsample2x_nhwc_f16(const void* in, void* out, int32_t B, int32_t H, int32_t W, int32_t C, void* stream) {
+  if (C % 8) { set_error("udb_upsample2x_nhwc_f16: C %% 8 != 0"); return 1; }
+  const long long total = (long long)B * 4 * H * W * (C / 8);
+  upsample2x_kernel<<<grid_for(total), 256, 0, ST(stream)>>>(reinterpret_cast<const __half*>(in), reinterpret_cast<__half*>(out), B, H, W, C);
+  return check_launch("upsample2x_kernel");
+}
+
+extern "C" int udb_resize_ac_pad_nhwc_f16(const void* in, void* out, int32_t B, int32_t H, int32_t W, int32_t C, int32_t oh,
+                                          int32_t ow, int32_t pad, void* stream) {
+  if (C % 8) { set_error("udb_resize_ac_pad_nhwc_f16: C %% 8 != 0"); return 1; }
+  const long long total = (long long)B * (oh + 2 * pad) * (ow + 2 * pad) * (C / 8);
+  resize_ac_pad_kernel<<<grid_for(total), 256, 0, ST(stream)>>>(reinterpret_cast<const __half*>(in), reinterpret_cast<__half*>(out), B, H, W, C, oh, ow, pad);
+  return check_launch("resize_ac_pad_kernel");
+}
+
+extern "C" int udb_reflect_pad1_nhwc_f16(const void* in, void* out, int32_t B, int32_t H, int32_t W, int32_t C, void* stream) {
+  if (C % 8) { set_error("udb_reflect_pad1_nhwc_f16: C %% 8 != 0"); return 1; }
+  const long long total = (long long)B * (H + 2) * (W + 2) * (C / 8);
+  reflect_pad1_kernel<<<grid_for(total), 256, 0, ST(stream)>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), B, H, W, C / 8);
+  return check_launch("reflect_pad1_kernel");
+}
+
+extern "C" int udb_postprocess(const udb_postprocess_t* p, void* stream) {
+  postprocess_kernel<<<grid_for((long long)p->B * p->H * p->W), 256, 0, ST(stream)>>>(*p);
+  return check_launch("postprocess_kernel");
+}

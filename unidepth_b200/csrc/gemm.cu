@@ -1,0 +1,419 @@
+// Persistent warp-specialised tcgen05 GEMM for sm_100a:   D = epilogue(A . W^T)
+//
+//   warp 0      : TMA producer  (A tile 128x64 f16, W tile BNx64 f16, 128B swizzle, mbarrier ring)
+//   warp 1      : MMA issuer    (one elected thread, tcgen05.mma.cta_group::1.kind::f16, M=128,N=BN,K=16)
+//   warp 2      : TMEM allocator (2 accumulator stages of BN fp32 columns)
+//   warps 4..11 : epilogue      (tcgen05.ld 32x32b -> registers -> bias/act/gamma/residual -> global)
+//
+// The A operand is either a row-major matrix (2-D tensor map) or a 3x3 convolution window over an
+// NHWC image (4-D tensor map, one (dy,dx,64-channel) slab per k-block; zero padding comes from TMA
+// out-of-bounds fill), so linear layers, 1x1 / 3x3 convolutions and k=s transposed convolutions all
+// run through this one kernel.  See include/udb.h (udb_gemm) for the reference call sites.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace udb {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = (4 + kEpiWarps) * 32;
+
+struct GemmArgs {
+  int M, N, K, num_kb;
+  int tiles_m, tiles_n;
+  int a_mode;
+  int conv_H, conv_W, conv_cpb /*64-ch blocks per tap*/, conv_off, conv_TH, conv_TW, conv_tx, conv_ty;
+  const float* bias;
+  const float* gamma;
+  const void* resid;
+  int resid_f32;
+  void* out;
+  int out_f32;
+  __half* out2;
+  int act;
+  int store_mode;
+  long long ldc, ldr;
+  int rpg, gstride, roff;
+  int resid_mod, resid_roff;
+  int ct_k, ct_cout, ct_h, ct_w;
+  const float* head_w;
+  float head_b, head_add;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStages = BN >= 256 ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = (2 * BN) < 32 ? 32 : (2 * BN);
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const GemmArgs p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kStages * Cfg::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kStages;
+  uint64_t* tmem_full = bars + 2 * kStages;
+  uint64_t* tmem_empty = bars + 2 * kStages + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], kEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_ptr);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int num_tiles = p.tiles_m * p.tiles_n;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int mt = tile / p.tiles_n;
+        const int nt = tile % p.tiles_n;
+        int cb = 0, cy = 0, cx = 0;
+        if (p.a_mode == UDB_A_CONV3X3) {
+          const int per_img = p.conv_tx * p.conv_ty;
+          cb = mt / per_img;
+          const int r = mt % per_img;
+          cy = (r / p.conv_tx) * p.conv_TH + p.conv_off;
+          cx = (r % p.conv_tx) * p.conv_TW + p.conv_off;
+        }
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          if (p.a_mode == UDB_A_CONV3X3) {
+            const int tap = kb / p.conv_cpb;
+            const int c0 = (kb % p.conv_cpb) * BK;
+            tma_load_4d(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], c0, cx + tap % 3,
+                        cy + tap / 3, cb);
+          } else {
+            tma_load_2d(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * BK, mt * BM);
+          }
+          tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * BK, nt * BN);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(BM, BN, false, false);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[as], aphase ^ 1);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          const uint64_t da = umma_desc_sw128(smem_u32(sA + stage * Cfg::kABytes), 16, 1024);
+          const uint64_t db = umma_desc_sw128(smem_u32(sB + stage * Cfg::kBBytes), 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 elements (32 B) along K inside the 128 B swizzle atom: +2 in 16-byte units
+            umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[as]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue
+    const int ew = warp - 4;
+    const int quad = warp & 3;            // TMEM lane quadrant this warp may access
+    constexpr int kGroups = BN >= 64 ? 2 : 1;
+    const int grp = ew >> 2;              // column half
+    constexpr int kColsPerGrp = BN / kGroups;
+    const int r_in_tile = quad * 32 + lane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int mt = tile / p.tiles_n;
+      const int nt = tile % p.tiles_n;
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after_sync();
+      if (grp < kGroups) {
+        // ---- per-row addressing
+        bool valid;
+        long long out_off = 0, res_off = 0;
+        const int m = mt * BM + r_in_tile;
+        if (p.store_mode == UDB_STORE_CONVTILE || p.store_mode == UDB_STORE_HEAD) {
+          const int per_img = p.conv_tx * p.conv_ty;
+          const int b = mt / per_img;
+          const int r = mt % per_img;
+          const int y = (r / p.conv_tx) * p.conv_TH + r_in_tile / p.conv_TW;
+          const int x = (r % p.conv_tx) * p.conv_TW + r_in_tile % p.conv_TW;
+          valid = (y < p.conv_H) && (x < p.conv_W);
+          out_off = (((long long)b * p.conv_H + y) * p.conv_W + x) * p.ldc;
+          res_off = (((long long)b * p.conv_H + y) * p.conv_W + x) * p.ldr;
+        } else if (p.store_mode == UDB_STORE_CONVT) {
+          valid = m < p.M;
+          const int hw = p.ct_h * p.ct_w;
+          const int b = m / hw;
+          const int r = m % hw;
+          const int y = r / p.ct_w, x = r % p.ct_w;
+          const long long W2 = (long long)p.ct_w * p.ct_k;
+          const long long H2 = (long long)p.ct_h * p.ct_k;
+          out_off = ((b * H2 + (long long)y * p.ct_k) * W2 + (long long)x * p.ct_k) * p.ct_cout;
+          res_off = out_off;
+        } else {
+          valid = m < p.M;
+          long long orow = m;
+          if (p.rpg > 0) orow = (long long)(m / p.rpg) * p.gstride + (m % p.rpg) + p.roff;
+          out_off = orow * p.ldc;
+          res_off = (p.resid_mod > 0) ? ((long long)(m % p.resid_mod) + p.resid_roff) * p.ldr
+                                      : orow * p.ldr;
+        }
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
+#pragma unroll 1
+        for (int c = 0; c < kColsPerGrp; c += 32) {
+          const int col = grp * kColsPerGrp + c;   // column inside the tile
+          const int n0 = nt * BN + col;            // global column
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(t_row + col, r);
+          tmem_ld_wait();
+          if (!valid || n0 >= p.N) continue;
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.bias) {
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + n0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b4 = __ldg(bp + j);
+              v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+            }
+          }
+          if (p.act == UDB_ACT_GELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          } else if (p.act == UDB_ACT_LEAKY) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = leaky(v[j]);
+          }
+          if (p.store_mode == UDB_STORE_HEAD) {
+            float acc = p.head_b;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc = fmaf(v[j], __ldg(p.head_w + j), acc);
+            acc = fminf(fmaxf(acc, -8.0f), 8.0f) + p.head_add;
+            reinterpret_cast<float*>(p.out)[out_off] = expf(acc);
+            continue;
+          }
+          if (p.gamma) {
+            const float4* gp = reinterpret_cast<const float4*>(p.gamma + n0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 g4 = __ldg(gp + j);
+              v[4 * j] *= g4.x; v[4 * j + 1] *= g4.y; v[4 * j + 2] *= g4.z; v[4 * j + 3] *= g4.w;
+            }
+          }
+          long long coff = n0;
+          if (p.store_mode == UDB_STORE_CONVT) {
+            const int tap = n0 / p.ct_cout;
+            const int co = n0 % p.ct_cout;
+            const long long W2 = (long long)p.ct_w * p.ct_k;
+            coff = ((long long)(tap / p.ct_k) * W2 + (tap % p.ct_k)) * p.ct_cout + co;
+          }
+          if (p.resid) {
+            if (p.resid_f32) {
+              const float4* rp = reinterpret_cast<const float4*>(
+                  reinterpret_cast<const float*>(p.resid) + res_off + coff);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 r4 = rp[j];
+                v[4 * j] += r4.x; v[4 * j + 1] += r4.y; v[4 * j + 2] += r4.z; v[4 * j + 3] += r4.w;
+              }
+            } else {
+              const uint4* rp = reinterpret_cast<const uint4*>(
+                  reinterpret_cast<const __half*>(p.resid) + res_off + coff);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint4 u = rp[j];
+                const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float2 f = __half22float2(h[q]);
+                  v[8 * j + 2 * q] += f.x;
+                  v[8 * j + 2 * q + 1] += f.y;
+                }
+              }
+            }
+          }
+          if (p.out) {
+            if (p.out_f32) {
+              float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + out_off + coff);
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            } else {
+              uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + out_off + coff);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                op[j] = make_uint4(pack_half2(v[8 * j], v[8 * j + 1]), pack_half2(v[8 * j + 2], v[8 * j + 3]),
+                                   pack_half2(v[8 * j + 4], v[8 * j + 5]), pack_half2(v[8 * j + 6], v[8 * j + 7]));
+            }
+          }
+          if (p.out2) {
+            uint4* op = reinterpret_cast<uint4*>(p.out2 + out_off + coff);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              op[j] = make_uint4(pack_half2(leaky(v[8 * j]), leaky(v[8 * j + 1])),
+                                 pack_half2(leaky(v[8 * j + 2]), leaky(v[8 * j + 3])),
+                                 pack_half2(leaky(v[8 * j + 4]), leaky(v[8 * j + 5])),
+                                 pack_half2(leaky(v[8 * j + 6]), leaky(v[8 * j + 7])));
+          }
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after_sync();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+template <int BN>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, cudaStream_t st) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_f16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes);
+    if (e != cudaSuccess) {
+      set_error("gemm: cudaFuncSetAttribute(%d B smem): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
+      return 1;
+    }
+    attr_set = true;
+  }
+  const int tiles = a.tiles_m * a.tiles_n;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  gemm_f16_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, a);
+  return check_launch("gemm_f16_kernel");
+}
+
+}  // namespace udb
+
+extern "C" int udb_gemm_f16(const udb_gemm_t* g, void* stream) {
+  using namespace udb;
+  if (!g || !g->a || !g->w) { set_error("udb_gemm_f16: null operand"); return 1; }
+  if (g->N % 32 != 0) { set_error("udb_gemm_f16: N=%d must be a multiple of 32", g->N); return 1; }
+  GemmArgs a{};
+  a.M = g->M; a.N = g->N; a.K = g->K;
+  a.num_kb = (g->K + BK - 1) / BK;
+  a.a_mode = g->a_mode;
+  a.bias = g->bias; a.gamma = g->gamma; a.resid = g->resid; a.resid_f32 = g->resid_f32;
+  a.out = g->out; a.out_f32 = g->out_f32; a.out2 = reinterpret_cast<__half*>(g->out2);
+  a.act = g->act; a.store_mode = g->store_mode;
+  a.ldc = g->ldc; a.ldr = g->ldr > 0 ? g->ldr : g->ldc;
+  a.rpg = g->rows_per_group; a.gstride = g->group_stride; a.roff = g->row_offset;
+  a.resid_mod = g->resid_mod; a.resid_roff = g->resid_row_offset;
+  a.ct_k = g->ct_k; a.ct_cout = g->ct_cout; a.ct_h = g->ct_h; a.ct_w = g->ct_w;
+  a.head_w = g->head_w; a.head_b = g->head_b; a.head_add = g->head_add;
+
+  // tile width: widest that divides the work sensibly
+  int bn;
+  if (g->store_mode == UDB_STORE_HEAD) {
+    if (g->N != 32) { set_error("udb_gemm_f16: HEAD store needs N == 32"); return 1; }
+    bn = 32;
+  } else if (g->N % 256 == 0) bn = 256;
+  else if (g->N % 128 == 0) bn = 128;
+  else if (g->N % 64 == 0) bn = 64;
+  else bn = 32;
+  if (g->store_mode == UDB_STORE_CONVT && (g->ct_cout % 32) != 0) {
+    set_error("udb_gemm_f16: CONVT needs Cout %% 32 == 0"); return 1;
+  }
+  a.tiles_n = (g->N + bn - 1) / bn;
+
+  CUtensorMap tmA, tmB;
+  if (g->a_mode == UDB_A_CONV3X3) {
+    if (g->conv_C % BK != 0 || g->K != 9 * g->conv_C) {
+      set_error("udb_gemm_f16: conv3x3 needs C %% 64 == 0 and K == 9*C (C=%d K=%d)", g->conv_C, g->K);
+      return 1;
+    }
+    const int TH = g->conv_TH > 0 ? g->conv_TH : 8, TW = g->conv_TW > 0 ? g->conv_TW : 16;
+    if (TH * TW != BM) { set_error("udb_gemm_f16: conv tile %dx%d != 128 pixels", TH, TW); return 1; }
+    a.conv_H = g->conv_H; a.conv_W = g->conv_W; a.conv_cpb = g->conv_C / BK; a.conv_off = g->conv_off;
+    a.conv_TH = TH; a.conv_TW = TW;
+    a.conv_tx = (g->conv_W + TW - 1) / TW; a.conv_ty = (g->conv_H + TH - 1) / TH;
+    a.tiles_m = g->conv_B * a.conv_tx * a.conv_ty;
+    a.M = a.tiles_m * BM;
+    const uint64_t dims[4] = {(uint64_t)g->conv_C, (uint64_t)g->conv_inW, (uint64_t)g->conv_inH, (uint64_t)g->conv_B};
+    const uint64_t str[3] = {(uint64_t)g->conv_C * 2, (uint64_t)g->conv_inW * g->conv_C * 2,
+                             (uint64_t)g->conv_inH * g->conv_inW * g->conv_C * 2};
+    const uint32_t box[4] = {(uint32_t)BK, (uint32_t)TW, (uint32_t)TH, 1};
+    if (make_tmap_f16(&tmA, g->a, 4, dims, str, box, true)) return 1;
+  } else {
+    a.tiles_m = (g->M + BM - 1) / BM;
+    if (g->store_mode == UDB_STORE_CONVTILE || g->store_mode == UDB_STORE_HEAD) {
+      set_error("udb_gemm_f16: tile store modes need a_mode == CONV3X3"); return 1;
+    }
+    const uint64_t dims[2] = {(uint64_t)g->K, (uint64_t)g->M};
+    const uint64_t str[1] = {(uint64_t)g->lda * 2};
+    const uint32_t box[2] = {(uint32_t)BK, (uint32_t)BM};
+    if (make_tmap_f16(&tmA, g->a, 2, dims, str, box, true)) return 1;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)g->K, (uint64_t)g->N};
+    const uint64_t str[1] = {(uint64_t)g->ldw * 2};
+    const uint32_t box[2] = {(uint32_t)BK, (uint32_t)bn};
+    if (make_tmap_f16(&tmB, g->w, 2, dims, str, box, true)) return 1;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (bn) {
+    case 256: return launch_gemm<256>(tmA, tmB, a, st);
+    case 128: return launch_gemm<128>(tmA, tmB, a, st);
+    case 64: return launch_gemm<64>(tmA, tmB, a, st);
+    default: return launch_gemm<32>(tmA, tmB, a, st);
+  }
+}

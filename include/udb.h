@@ -56,7 +56,7 @@ typedef struct udb_gemm_t {
    * (reflect padding, in_H = H+2, in_W = W+2). */
   int32_t conv_B, conv_H, conv_W, conv_C, conv_inH, conv_inW, conv_off, conv_TH, conv_TW;
   /* epilogue: v = acc + bias[n]; v = act(v); v *= gamma[n]; v += resid[...]; out = v;
-   * out2 = f16(leaky(v)) (optional second copy for the next conv's input) */
+   * out2 = f16(v) or f16(leaky(v)) (optional second f16 copy, e.g. the next conv's input) */
   const float* bias;
   const float* gamma;
   const void* resid;
@@ -64,6 +64,7 @@ typedef struct udb_gemm_t {
   void* out;
   int32_t out_f32;
   void* out2;
+  int32_t out2_leaky; /* 1: out2 = f16(leaky(v)); 0: out2 = f16(v) */
   int32_t act;
   int32_t store_mode;
   int64_t ldc; /* elements between consecutive output rows / pixels */
@@ -167,6 +168,7 @@ typedef struct udb_small_linear_t {
   float* y;
   int32_t M, N, K;
   int32_t act;
+  int32_t ldx, ldy, ldr; /* row strides (elements) of x, y, resid; 0 = dense (K, N, N) */
 } udb_small_linear_t;
 int udb_small_linear_f32(const udb_small_linear_t* p, void* stream);
 

@@ -23,7 +23,7 @@ class Gemm(C.Structure):
         ("conv_B", i32), ("conv_H", i32), ("conv_W", i32), ("conv_C", i32), ("conv_inH", i32),
         ("conv_inW", i32), ("conv_off", i32), ("conv_TH", i32), ("conv_TW", i32),
         ("bias", vp), ("gamma", vp), ("resid", vp), ("resid_f32", i32), ("out", vp), ("out_f32", i32),
-        ("out2", vp), ("act", i32), ("store_mode", i32), ("ldc", i64),
+        ("out2", vp), ("out2_leaky", i32), ("act", i32), ("store_mode", i32), ("ldc", i64),
         ("rows_per_group", i32), ("group_stride", i32), ("row_offset", i32),
         ("resid_mod", i32), ("resid_row_offset", i32), ("ldr", i64),
         ("ct_k", i32), ("ct_cout", i32), ("ct_h", i32), ("ct_w", i32),
@@ -59,7 +59,7 @@ class Preprocess(C.Structure):
 class SmallLinear(C.Structure):
     _fields_ = [
         ("x", vp), ("w", vp), ("bias", vp), ("gamma", vp), ("resid", vp), ("y", vp),
-        ("M", i32), ("N", i32), ("K", i32), ("act", i32),
+        ("M", i32), ("N", i32), ("K", i32), ("act", i32), ("ldx", i32), ("ldy", i32), ("ldr", i32),
     ]
 
 

@@ -171,6 +171,7 @@ __global__ void __launch_bounds__(128) small_linear_kernel(const udb_small_linea
   const int n0 = (blockIdx.x * 4 + warp) * 4;
   const int m0 = blockIdx.y * 8;
   if (n0 >= p.N) return;
+  const long long ldx = p.ldx > 0 ? p.ldx : p.K, ldy = p.ldy > 0 ? p.ldy : p.N, ldr = p.ldr > 0 ? p.ldr : p.N;
   float acc[4][8];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(128) small_linear_kernel(const udb_small_linea
   for (int k = lane; k < p.K; k += 32) {
     float xv[8];
 #pragma unroll
-    for (int m = 0; m < 8; ++m) xv[m] = (m0 + m < p.M) ? p.x[(long long)(m0 + m) * p.K + k] : 0.f;
+    for (int m = 0; m < 8; ++m) xv[m] = (m0 + m < p.M) ? p.x[(long long)(m0 + m) * ldx + k] : 0.f;
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
       const float wv = (n0 + a < p.N) ? p.w[(long long)(n0 + a) * p.K + k] : 0.f;
@@ -200,8 +201,8 @@ __global__ void __launch_bounds__(128) small_linear_kernel(const udb_small_linea
         float v = acc[a][m] + (p.bias ? p.bias[n] : 0.f);
         if (p.act == UDB_ACT_GELU) v = gelu_erf(v);
         if (p.gamma) v *= p.gamma[n];
-        if (p.resid) v += p.resid[(long long)(m0 + m) * p.N + n];
-        p.y[(long long)(m0 + m) * p.N + n] = v;
+        if (p.resid) v += p.resid[(long long)(m0 + m) * ldr + n];
+        p.y[(long long)(m0 + m) * ldy + n] = v;
       }
     }
   }

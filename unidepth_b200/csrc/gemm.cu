@@ -31,6 +31,7 @@ struct GemmArgs {
   void* out;
   int out_f32;
   __half* out2;
+  int out2_leaky;
   int act;
   int store_mode;
   long long ldc, ldr;
@@ -300,6 +301,12 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
           if (p.out2) {
             uint4* op = reinterpret_cast<uint4*>(p.out2 + out_off + coff);
+            if (!p.out2_leaky) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                op[j] = make_uint4(pack_half2(v[8 * j], v[8 * j + 1]), pack_half2(v[8 * j + 2], v[8 * j + 3]),
+                                   pack_half2(v[8 * j + 4], v[8 * j + 5]), pack_half2(v[8 * j + 6], v[8 * j + 7]));
+            } else
 #pragma unroll
             for (int j = 0; j < 4; ++j)
               op[j] = make_uint4(pack_half2(leaky(v[8 * j]), leaky(v[8 * j + 1])),
@@ -353,7 +360,7 @@ extern "C" int udb_gemm_f16(const udb_gemm_t* g, void* stream) {
   a.num_kb = (g->K + BK - 1) / BK;
   a.a_mode = g->a_mode;
   a.bias = g->bias; a.gamma = g->gamma; a.resid = g->resid; a.resid_f32 = g->resid_f32;
-  a.out = g->out; a.out_f32 = g->out_f32; a.out2 = reinterpret_cast<__half*>(g->out2);
+  a.out = g->out; a.out_f32 = g->out_f32; a.out2 = reinterpret_cast<__half*>(g->out2); a.out2_leaky = g->out2_leaky;
   a.act = g->act; a.store_mode = g->store_mode;
   a.ldc = g->ldc; a.ldr = g->ldr > 0 ? g->ldr : g->ldc;
   a.rpg = g->rows_per_group; a.gstride = g->group_stride; a.roff = g->row_offset;
@@ -380,6 +387,9 @@ extern "C" int udb_gemm_f16(const udb_gemm_t* g, void* stream) {
     if (g->conv_C % BK != 0 || g->K != 9 * g->conv_C) {
       set_error("udb_gemm_f16: conv3x3 needs C %% 64 == 0 and K == 9*C (C=%d K=%d)", g->conv_C, g->K);
       return 1;
+    }
+    if (g->store_mode != UDB_STORE_CONVTILE && g->store_mode != UDB_STORE_HEAD) {
+      set_error("udb_gemm_f16: conv3x3 operand needs a CONVTILE or HEAD store"); return 1;
     }
     const int TH = g->conv_TH > 0 ? g->conv_TH : 8, TW = g->conv_TW > 0 ? g->conv_TW : 16;
     if (TH * TW != BM) { set_error("udb_gemm_f16: conv tile %dx%d != 128 pixels", TH, TW); return 1; }

@@ -14,6 +14,21 @@ from ._cabi import (A_CONV3X3, A_MATRIX, ACT_GELU, ACT_LEAKY, ACT_NONE, STORE_CO
 
 f16, f32 = torch.float16, torch.float32
 
+# When set to a list, the tensor-core ops append (kernel, algorithmic flops, start_event, end_event)
+# for every launch (bench.py's per-kernel roofline); None in normal operation.
+PROFILE = None
+
+
+def _launch(kernel: str, flops: float, fn):
+    if PROFILE is None:
+        return fn()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    rc = fn()
+    e.record()
+    PROFILE.append((kernel, flops, s, e))
+    return rc
+
 
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -34,7 +49,7 @@ def _is32(t):
 
 
 def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, act=ACT_NONE, gamma=None, resid=None,
-         out: Optional[torch.Tensor] = None, out_dtype=f16, out2: Optional[torch.Tensor] = None,
+         out: Optional[torch.Tensor] = None, out_dtype=f16, out2: Optional[torch.Tensor] = None, out2_leaky=True,
          rows_per_group=0, group_stride=0, row_offset=0, resid_mod=0, resid_row_offset=0,
          out_rows: Optional[int] = None):
     """out[row(m), :] = resid + gamma * act(a @ w.T + bias).  a f16 [M,K], w f16 [N,K]."""
@@ -53,16 +68,17 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, act=ACT_NONE, gamma=Non
     if resid is not None:
         g.resid, g.resid_f32, g.ldr = _ptr(resid), _is32(resid), resid.stride(0)
     g.out, g.out_f32, g.ldc = _ptr(out), _is32(out), out.stride(0)
-    g.out2 = _ptr(out2)
+    g.out2, g.out2_leaky = _ptr(out2), int(out2_leaky)
     g.act, g.store_mode = act, STORE_ROWS
     g.rows_per_group, g.group_stride, g.row_offset = rows_per_group, group_stride, row_offset
     g.resid_mod, g.resid_row_offset = resid_mod, resid_row_offset
-    cabi.check(cabi.lib().udb_gemm_f16(C.byref(g), _stream()), "udb_gemm_f16")
+    cabi.check(_launch("gemm_f16_kernel", 2.0 * M * N * K, lambda: cabi.lib().udb_gemm_f16(C.byref(g), _stream())),
+               "udb_gemm_f16")
     return out
 
 
 def conv3x3(x: torch.Tensor, w: torch.Tensor, *, bias=None, act=ACT_NONE, gamma=None, resid=None,
-            out: Optional[torch.Tensor] = None, out_dtype=f16, out2=None, prepadded=False,
+            out: Optional[torch.Tensor] = None, out_dtype=f16, out2=None, out2_leaky=True, prepadded=False,
             head_w=None, head_b=0.0, head_add=0.0, tile=(8, 16)):
     """3x3 convolution over an NHWC f16 image x [B,H,W,C] (or [B,H+2,W+2,C] if prepadded) with
     packed weights w [Cout, 9*C] ordered (dy,dx,c).  Zero padding unless prepadded.
@@ -96,13 +112,14 @@ def conv3x3(x: torch.Tensor, w: torch.Tensor, *, bias=None, act=ACT_NONE, gamma=
         g.out, g.out_f32, g.ldc = _ptr(out), _is32(out), out.stride(2)
         if resid is not None:
             g.resid, g.resid_f32, g.ldr = _ptr(resid), _is32(resid), resid.stride(2)
-        g.out2 = _ptr(out2)
-    cabi.check(cabi.lib().udb_gemm_f16(C.byref(g), _stream()), "udb_gemm_f16(conv3x3)")
+        g.out2, g.out2_leaky = _ptr(out2), int(out2_leaky)
+    cabi.check(_launch("gemm_f16_kernel", 2.0 * B * H * W * N * 9 * Cin,
+                       lambda: cabi.lib().udb_gemm_f16(C.byref(g), _stream())), "udb_gemm_f16(conv3x3)")
     return out
 
 
 def conv_transpose_ks(x: torch.Tensor, w: torch.Tensor, k: int, cout: int, grid_hw, *, bias=None,
-                      resid=None, out: Optional[torch.Tensor] = None, out_dtype=f16, out2=None):
+                      resid=None, out: Optional[torch.Tensor] = None, out_dtype=f16, out2=None, out2_leaky=True):
     """ConvTranspose2d with kernel == stride == k as a GEMM with a pixel-shuffle store.
     x f16 [B*h*w, Cin]; w f16 [k*k*cout, Cin] ordered (dy,dx,co); bias f32 [k*k*cout].
     out NHWC [B, h*k, w*k, cout] (+ resid of the same shape, may alias out)."""
@@ -120,10 +137,11 @@ def conv_transpose_ks(x: torch.Tensor, w: torch.Tensor, k: int, cout: int, grid_
     if resid is not None:
         g.resid, g.resid_f32 = _ptr(resid), _is32(resid)
     g.out, g.out_f32, g.ldc = _ptr(out), _is32(out), cout
-    g.out2 = _ptr(out2)
+    g.out2, g.out2_leaky = _ptr(out2), int(out2_leaky)
     g.store_mode = STORE_CONVT
     g.ct_k, g.ct_cout, g.ct_h, g.ct_w = k, cout, h, ww
-    cabi.check(cabi.lib().udb_gemm_f16(C.byref(g), _stream()), "udb_gemm_f16(convT)")
+    cabi.check(_launch("gemm_f16_kernel", 2.0 * M * k * k * cout * K,
+                       lambda: cabi.lib().udb_gemm_f16(C.byref(g), _stream())), "udb_gemm_f16(convT)")
     return out
 
 
@@ -134,7 +152,8 @@ def attention(q, k, v, out, *, B, heads, seq_q, seq_k, head_dim, q_col0=0, k_col
     a.ldq, a.ldk, a.ldv, a.ldo = q.stride(0), k.stride(0), v.stride(0), out.stride(0)
     a.q_col0, a.k_col0, a.v_col0, a.o_col0 = q_col0, k_col0, v_col0, o_col0
     a.scale = head_dim ** -0.5
-    cabi.check(cabi.lib().udb_attention_f16(C.byref(a), _stream()), "udb_attention_f16")
+    cabi.check(_launch("attn_fwd_kernel", 4.0 * B * heads * seq_q * seq_k * head_dim,
+                       lambda: cabi.lib().udb_attention_f16(C.byref(a), _stream())), "udb_attention_f16")
     return out
 
 
@@ -181,14 +200,17 @@ def set_cls_rows(x, cls_token, pos0, B, T, D):
 
 
 def small_linear(x, w, bias=None, act=ACT_NONE, gamma=None, resid=None, out=None):
+    """fp32 y = resid + gamma * act(x @ w.T + bias); x / out / resid may be row-strided 2-D views."""
     M, K = x.shape
     N = w.shape[0]
-    assert x.dtype == f32 and w.dtype == f32 and x.is_contiguous() and w.is_contiguous()
+    assert x.dtype == f32 and w.dtype == f32 and x.stride(1) == 1 and w.is_contiguous()
     if out is None:
         out = torch.empty((M, N), device=x.device, dtype=f32)
+    assert out.stride(1) == 1 and (resid is None or resid.stride(1) == 1)
     p = cabi.SmallLinear()
     p.x, p.w, p.bias, p.gamma, p.resid, p.y = _ptr(x), _ptr(w), _ptr(bias), _ptr(gamma), _ptr(resid), _ptr(out)
     p.M, p.N, p.K, p.act = M, N, K, act
+    p.ldx, p.ldy, p.ldr = x.stride(0), out.stride(0), (resid.stride(0) if resid is not None else 0)
     cabi.check(cabi.lib().udb_small_linear_f32(C.byref(p), _stream()), "udb_small_linear_f32")
     return out
 

@@ -1,0 +1,471 @@
+"""UniDepthV2 -- drop-in for the reference's inference API, running on libudb.so (sm_100a).
+
+Mirrors `unidepth.models.UniDepthV2` for the inference path only
+(reference: unidepth/models/unidepthv2/unidepthv2.py:111-127 constructor, :239-339 `infer`,
+:414-416 `device`, :381-394 `load_pretrained`; HF-hub mixin `from_pretrained`):
+
+    model = UniDepthV2.from_pretrained(dir_with_config_json_and_safetensors)   # or UniDepthV2(config)
+    model = model.to("cuda").eval()
+    out = model.infer(rgb_uint8)        # dict: confidence intrinsics radius depth points rays depth_features
+
+The module owns `nn.Parameter`s under exactly the reference's state-dict names, so reference
+checkpoints (`model.safetensors` / `pytorch_model.bin`) load unchanged.  The forward itself is not
+PyTorch: `infer` packs the weights once (f16 GEMM operands, f32 epilogue vectors) and drives the
+hand-written kernels through the C ABI (include/udb.h) on torch's current stream, optionally as a
+captured CUDA graph.  There is no CPU / eager fallback: a missing library or a CPU-resident model
+raises.
+"""
+from __future__ import annotations
+
+import json
+import math
+import os
+import warnings
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .spec import ModelSpec, PATCH, get_paddings, get_resize_factor, param_shapes, pixel_bounds
+
+try:  # same mixin as the reference (unidepthv2.py:111-117)
+    from huggingface_hub import PyTorchModelHubMixin
+    _HAS_HF = True
+except Exception:  # pragma: no cover
+    _HAS_HF = False
+
+    class PyTorchModelHubMixin:  # minimal stand-in: local directories only
+        def __init_subclass__(cls, **kwargs):
+            super().__init_subclass__()
+
+f16, f32 = torch.float16, torch.float32
+
+
+class _Node(nn.Module):
+    """Anonymous container used to reproduce the reference's dotted parameter names."""
+
+
+def _register(root: nn.Module, dotted: str, tensor: torch.Tensor):
+    parts = dotted.split(".")
+    mod = root
+    for p in parts[:-1]:
+        if p not in mod._modules:
+            mod.add_module(p, _Node())
+        mod = mod._modules[p]
+    mod.register_parameter(parts[-1], nn.Parameter(tensor, requires_grad=False))
+
+
+class UniDepthV2(nn.Module, PyTorchModelHubMixin,
+                 **(dict(library_name="UniDepth", repo_url="https://github.com/lpiccinelli-eth/UniDepth",
+                         tags=["monocular-metric-depth-estimation"]) if _HAS_HF else {})):
+    def __init__(self, config: dict, eps: float = 1e-6, **kwargs):
+        super().__init__()
+        self.config = config
+        self.eps = eps
+        self.spec = ModelSpec(config)
+        s = self.spec
+        if not s.use_norm:
+            raise NotImplementedError("pixel_encoder.use_norm=false is not used by any shipped UniDepthV2 config")
+        for key, shape in param_shapes(config).items():
+            _register(self, key, torch.zeros(shape, dtype=f32))
+        self.shape_constraints = dict(s.shape_constraints)   # mutable, read by infer (unidepthv2.py:459)
+        self.interpolation_mode = "bilinear"                 # unidepthv2.py:460
+        self.use_cuda_graph = True
+        self._packed: Optional[dict] = None
+        self._packed_key = None
+        self._graphs: Dict[tuple, dict] = {}
+        self._posembed_cache: Dict[tuple, torch.Tensor] = {}
+
+    # ------------------------------------------------------------------ reference-compatible API
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    def load_pretrained(self, model_file: str):
+        """unidepthv2.py:381-394: torch checkpoint, optional 'model' key, strip 'module.'."""
+        sd = torch.load(model_file, map_location="cpu", weights_only=False)
+        if "model" in sd:
+            sd = sd["model"]
+        sd = {k.replace("module.", ""): v for k, v in sd.items()}
+        info = self.load_state_dict(sd, strict=False)
+        print(f"Loaded from {model_file} for {self.__class__.__name__} results in:", info)
+
+    if not _HAS_HF:
+        @classmethod
+        def from_pretrained(cls, path: str, **kwargs):
+            config = json.load(open(os.path.join(path, "config.json")))
+            model = cls(config=config.get("config", config))
+            st = os.path.join(path, "model.safetensors")
+            if os.path.exists(st):
+                from safetensors.torch import load_file
+                model.load_state_dict(load_file(st), strict=False)
+            else:
+                model.load_state_dict(torch.load(os.path.join(path, "pytorch_model.bin"), map_location="cpu"),
+                                      strict=False)
+            return model
+
+    def forward(self, *args, **kwargs):
+        raise NotImplementedError("training/validation forward is out of scope; use .infer()")
+
+    # ------------------------------------------------------------------ weight packing
+    def _fingerprint(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def _pack(self):
+        """One-time (per weight version) repack into kernel operand layouts."""
+        dev = self.device
+        if dev.type != "cuda":
+            raise RuntimeError("unidepth_b200.UniDepthV2.infer needs the model on a CUDA device "
+                               "(model.to('cuda')); there is no CPU fallback")
+        s = self.spec
+        sd = {k: v.detach() for k, v in self.state_dict().items()}
+        h16 = lambda t: t.to(f16).contiguous()
+        c32 = lambda t: t.to(f32).contiguous()
+        P: dict = {}
+        d, hid = s.embed_dim, s.hidden
+        if hid // s.dec_heads != 64 or d // s.enc_heads != 64:
+            raise NotImplementedError("attention kernel supports head_dim 64 only (ViT-L/B encoders with a "
+                                      "512-wide decoder); ViT-S decoder heads (32) are a later round")
+        pe = "pixel_encoder."
+        wpe = torch.zeros((d, 640), device=dev, dtype=f16)
+        wpe[:, :588] = sd[pe + "patch_embed.proj.weight"].reshape(d, 588).to(f16)
+        P["patch_w"], P["patch_b"] = wpe, c32(sd[pe + "patch_embed.proj.bias"])
+        P["cls"] = c32(sd[pe + "cls_token"].reshape(d))
+        P["pos"] = c32(sd[pe + "pos_embed"].reshape(-1, d))
+        P["blocks"] = []
+        for i in range(s.depth):
+            b = f"{pe}blocks.{i}."
+            P["blocks"].append(dict(
+                n1w=c32(sd[b + "norm1.weight"]), n1b=c32(sd[b + "norm1.bias"]),
+                qkv_w=h16(sd[b + "attn.qkv.weight"]), qkv_b=c32(sd[b + "attn.qkv.bias"]),
+                proj_w=h16(sd[b + "attn.proj.weight"]), proj_b=c32(sd[b + "attn.proj.bias"]),
+                ls1=c32(sd[b + "ls1.gamma"]),
+                n2w=c32(sd[b + "norm2.weight"]), n2b=c32(sd[b + "norm2.bias"]),
+                fc1_w=h16(sd[b + "mlp.fc1.weight"]), fc1_b=c32(sd[b + "mlp.fc1.bias"]),
+                fc2_w=h16(sd[b + "mlp.fc2.weight"]), fc2_b=c32(sd[b + "mlp.fc2.bias"]),
+                ls2=c32(sd[b + "ls2.gamma"])))
+        P["norm_w"], P["norm_b"] = c32(sd[pe + "norm.weight"]), c32(sd[pe + "norm.bias"])
+
+        pd = "pixel_decoder."
+        P["adapt"] = [(h16(sd[f"{pd}input_adapter.input_adapters.{i}.weight"]),
+                       c32(sd[f"{pd}input_adapter.input_adapters.{i}.bias"])) for i in range(4)]
+        P["cam_adapt"] = [(c32(sd[f"{pd}camera_token_adapter.input_adapters.{i}.weight"]),
+                           c32(sd[f"{pd}camera_token_adapter.input_adapters.{i}.bias"])) for i in range(4)]
+        cl = pd + "camera_layer."
+
+        def mlp32(prefix):
+            return dict(nw=c32(sd[prefix + ".norm.weight"]), nb=c32(sd[prefix + ".norm.bias"]),
+                        w1=c32(sd[prefix + ".proj1.weight"]), b1=c32(sd[prefix + ".proj1.bias"]),
+                        w2=c32(sd[prefix + ".proj2.weight"]), b2=c32(sd[prefix + ".proj2.bias"]))
+
+        def agg32(prefix):
+            return dict(mlp=mlp32(prefix + ".mlp"), kv=c32(sd[prefix + ".kv.weight"]), q=c32(sd[prefix + ".q.weight"]),
+                        nxw=c32(sd[prefix + ".norm_attnx.weight"]), nxb=c32(sd[prefix + ".norm_attnx.bias"]),
+                        ncw=c32(sd[prefix + ".norm_attnctx.weight"]), ncb=c32(sd[prefix + ".norm_attnctx.bias"]),
+                        out=c32(sd[prefix + ".out.weight"]), ls1=c32(sd[prefix + ".ls1.gamma"]),
+                        ls2=c32(sd[prefix + ".ls2.gamma"]))
+
+        P["cam"] = dict(pos=c32(sd[cl + "latents_pos"].reshape(4, hid)), agg1=agg32(cl + "aggregate1"),
+                        agg2=agg32(cl + "aggregate2"), project=mlp32(cl + "project"),
+                        pinhole=mlp32(cl + "out_pinhole"))
+        dl = pd + "depth_layer."
+        P["prompt"] = []
+        for i in range(4):
+            p = f"{dl}prompt_camera.{i}.layers.0"
+            P["prompt"].append(dict(
+                nxw=c32(sd[p + ".norm_attnx.weight"]), nxb=c32(sd[p + ".norm_attnx.bias"]),
+                ncw=c32(sd[p + ".norm_attnctx.weight"]), ncb=c32(sd[p + ".norm_attnctx.bias"]),
+                q=h16(sd[p + ".q.weight"]), kv=h16(sd[p + ".kv.weight"]), out=h16(sd[p + ".out.weight"]),
+                mnw=c32(sd[p + ".mlp.norm.weight"]), mnb=c32(sd[p + ".mlp.norm.bias"]),
+                w1=h16(sd[p + ".mlp.proj1.weight"]), b1=c32(sd[p + ".mlp.proj1.bias"]),
+                w2=h16(sd[p + ".mlp.proj2.weight"]), b2=c32(sd[p + ".mlp.proj2.bias"])))
+        P["lat_w"], P["lat_b"] = h16(sd[dl + "to_latents.weight"]), c32(sd[dl + "to_latents.bias"])
+        conv_pack = lambda w: h16(w.permute(0, 2, 3, 1).reshape(w.shape[0], -1))   # [Cout,(dy,dx,ci)]
+        P["ups"] = []
+        for i in range(len(s.dec_depths)):
+            k = max(1, 2 * i)
+            wt = sd[f"{dl}process_features.{i}.weight"]                            # [Cin,Cout,k,k]
+            cout = wt.shape[1]
+            st = dict(k=k, cout=cout,
+                      ct_w=h16(wt.permute(2, 3, 1, 0).reshape(k * k * cout, wt.shape[0])),
+                      ct_b=c32(sd[f"{dl}process_features.{i}.bias"].repeat(k * k)), rcus=[])
+            for j in range(s.dec_depths[i]):
+                u = f"{dl}ups.{i}.convs.{j}."
+                st["rcus"].append(dict(w1=conv_pack(sd[u + "conv1.weight"]), b1=c32(sd[u + "conv1.bias"]),
+                                       w2=conv_pack(sd[u + "conv2.weight"]), b2=c32(sd[u + "conv2.bias"]),
+                                       gamma=c32(sd[u + "gamma"].reshape(-1))))
+            uw = sd[f"{dl}ups.{i}.up.0.weight"]
+            st["up_w"], st["up_b"] = h16(uw.reshape(uw.shape[0], uw.shape[1])), c32(sd[f"{dl}ups.{i}.up.0.bias"])
+            P["ups"].append(st)
+        last = len(s.dec_depths) - 1
+        P["heads"] = []
+        for mlp_p, lr, hr, add in ((f"{dl}depth_mlp.{last}", "to_depth_lr", "to_depth_hr", 2.0),
+                                   (f"{dl}confidence_mlp", "to_confidence_lr", "to_confidence_hr", 0.0)):
+            P["heads"].append(dict(
+                lnw=c32(sd[mlp_p + ".0.weight"]), lnb=c32(sd[mlp_p + ".0.bias"]),
+                w=h16(sd[mlp_p + ".1.weight"]), b=c32(sd[mlp_p + ".1.bias"]),
+                lr_w=conv_pack(sd[f"{dl}{lr}.weight"]), lr_b=c32(sd[f"{dl}{lr}.bias"]),
+                hr_w=conv_pack(sd[f"{dl}{hr}.0.weight"]), hr_b=c32(sd[f"{dl}{hr}.0.bias"]),
+                head_w=c32(sd[f"{dl}{hr}.2.weight"].reshape(32)), head_b=float(sd[f"{dl}{hr}.2.bias"].item()),
+                add=add))
+        self._packed = P
+        self._packed_key = self._fingerprint()
+        self._graphs.clear()
+        self._posembed_cache.clear()
+
+    def _weights(self):
+        if self._packed is None or self._packed_key != self._fingerprint():
+            self._pack()
+        return self._packed
+
+    def _pos_embed(self, gh: int, gw: int) -> torch.Tensor:
+        """[1+gh*gw, D] f32: row 0 = cls position, rest = bicubic-resized grid (cached per shape)."""
+        key = (gh, gw)
+        if key not in self._posembed_cache:
+            P = self._weights()
+            pos = P["pos"]
+            m = int(math.isqrt(pos.shape[0] - 1))
+            d = pos.shape[1]
+            if (gh, gw) == (m, m):
+                full = pos.clone()
+            else:
+                grid = ops.posembed_bicubic(pos[1:].contiguous(), m, d, gh, gw)
+                full = torch.cat([pos[:1], grid], dim=0).contiguous()
+            self._posembed_cache[key] = full
+        return self._posembed_cache[key]
+
+    # ------------------------------------------------------------------ the forward (kernel launches only)
+    def _forward(self, rgb: torch.Tensor, geom: dict, normalize: bool, gt_intr4=None, taps: Optional[dict] = None):
+        P = self._weights()
+        s = self.spec
+        dev = rgb.device
+        B = rgb.shape[0]
+        nh, nw = geom["net_hw"]
+        gh, gw = nh // PATCH, nw // PATCH
+        N, T, D, hid = gh * gw, gh * gw + 1, s.embed_dim, s.hidden
+        E = lambda *shape, dtype=f16: torch.empty(shape, device=dev, dtype=dtype)
+
+        # a2/a3/a4: preprocess + patch embed + cls/pos
+        patches = E(B * N, 640)
+        ops.preprocess_patchify(rgb, geom["paddings"], (nh, nw), patches, normalize)
+        pos = self._pos_embed(gh, gw)
+        x = E(B * T, D, dtype=f32)
+        ops.gemm(patches, P["patch_w"], bias=P["patch_b"], resid=pos, out=x, rows_per_group=N, group_stride=T,
+                 row_offset=1, resid_mod=N, resid_row_offset=1)
+        ops.set_cls_rows(x, P["cls"], pos, B, T, D)
+        if taps is not None:
+            taps["tokens0"] = x.clone().view(B, T, D)
+
+        # a5-a8: transformer blocks
+        h = E(B * T, D)
+        qkv = E(B * T, 3 * D)
+        att = E(B * T, D)
+        mid = E(B * T, 4 * D)
+        feats, clss = [], []
+        for i, blk in enumerate(P["blocks"]):
+            ops.layernorm(x, blk["n1w"], blk["n1b"], 1e-6, out=h)
+            ops.gemm(h, blk["qkv_w"], bias=blk["qkv_b"], out=qkv)
+            ops.attention(qkv, qkv, qkv, att, B=B, heads=s.enc_heads, seq_q=T, seq_k=T, head_dim=64,
+                          q_col0=0, k_col0=D, v_col0=2 * D)
+            ops.gemm(att, blk["proj_w"], bias=blk["proj_b"], gamma=blk["ls1"], resid=x, out=x)
+            ops.layernorm(x, blk["n2w"], blk["n2b"], 1e-6, out=h)
+            ops.gemm(h, blk["fc1_w"], bias=blk["fc1_b"], act=ops.ACT_GELU, out=mid)
+            ops.gemm(mid, blk["fc2_w"], bias=blk["fc2_b"], gamma=blk["ls2"], resid=x, out=x)
+            if taps is not None and i == 0:
+                taps["block0"] = x.clone().view(B, T, D)
+            if (i + 1) in s.taps:
+                feats.append(ops.layernorm(x, P["norm_w"], P["norm_b"], 1e-5, out=E(B * N, D), rows=B * N,
+                                           rows_per_group=N, group_stride=T, row_offset=1))
+                clss.append(ops.layernorm(x, P["norm_w"], P["norm_b"], 1e-5, out=E(B, D, dtype=f32), rows=B,
+                                          rows_per_group=1, group_stride=T, row_offset=0))
+        if taps is not None:
+            taps["feat3"] = feats[-1].clone().view(B, gh, gw, D)
+            taps["cls3"] = clss[-1].clone().view(B, 1, D)
+
+        # a9: adapters
+        F = [ops.gemm(feats[l], P["adapt"][l][0], bias=P["adapt"][l][1], out_dtype=f32) for l in range(4)]
+        tokens = E(B, 4, hid, dtype=f32)
+        tok2 = tokens.view(B, 4 * hid)
+        for l in range(4):
+            ops.small_linear(clss[l], P["cam_adapt"][l][0], P["cam_adapt"][l][1], out=tok2[:, l * hid:(l + 1) * hid])
+
+        # a10: camera head (fp32)
+        cam = P["cam"]
+        t = tokens.view(B * 4, hid)
+
+        def mlp32(x_in, m, resid=None, gamma=None):
+            y = ops.layernorm(x_in, m["nw"], m["nb"], 1e-5, out_dtype=f32)
+            y = ops.small_linear(y, m["w1"], m["b1"], act=ops.ACT_GELU)
+            return ops.small_linear(y, m["w2"], m["b2"], gamma=gamma, resid=resid)
+
+        t = mlp32(t, cam["project"])
+        for agg in (cam["agg1"], cam["agg2"]):
+            xn = ops.layernorm(t, agg["nxw"], agg["nxb"], 1e-5, out_dtype=f32)
+            cn = ops.layernorm(t, agg["ncw"], agg["ncb"], 1e-5, out_dtype=f32)
+            q = ops.small_linear(xn, agg["q"])
+            kv = ops.small_linear(cn, agg["kv"])
+            a4 = ops.camera_attn4(q, kv, cam["pos"], B, hid, s.dec_heads)
+            t = ops.small_linear(a4, agg["out"], gamma=agg["ls1"], resid=t)
+            t = mlp32(t, agg["mlp"], resid=t, gamma=agg["ls2"])
+        x4 = mlp32(t, cam["pinhole"])                       # [B*4, 1] == [B,4]
+        intr4, k_net, k_out = ops.camera_intrinsics(x4, B, (nh, nw), geom["factor"], geom["paddings"][0],
+                                                    geom["paddings"][2])
+
+        # a11/a12: ray embedding
+        scales = geom["scales"]
+        # GT-camera branch (unidepthv2.py:299-303,361-362; decoder.py:400): rays come from the given
+        # pinhole K instead of the predicted one; the returned intrinsics stay the predicted ones.
+        ray_intr = intr4 if gt_intr4 is None else gt_intr4
+        remb = ops.ray_embed(ray_intr, scales, B, (nh, nw), (gh, gw), out_dtype=f32)
+        if taps is not None:
+            taps["ray_embedding"] = remb.clone().view(B, N, hid)
+            taps["intrinsics4"] = intr4.clone()
+
+        # a13: prompt blocks
+        cond = []
+        xn, cn = E(B * N, hid), E(B * N, hid)
+        qb, kvb, ab = E(B * N, hid), E(B * N, 2 * hid), E(B * N, hid)
+        mb = E(B * N, s.expansion * hid)
+        for l in range(4):
+            pr = P["prompt"][l]
+            ops.layernorm(F[l], pr["nxw"], pr["nxb"], 1e-5, out=xn)
+            ops.layernorm(remb, pr["ncw"], pr["ncb"], 1e-5, out=cn)
+            ops.gemm(xn, pr["q"], out=qb)
+            ops.gemm(cn, pr["kv"], out=kvb)
+            ops.attention(qb, kvb, kvb, ab, B=B, heads=s.dec_heads, seq_q=N, seq_k=N, head_dim=64, k_col0=0, v_col0=hid)
+            ops.gemm(ab, pr["out"], resid=F[l], out=F[l])
+            ops.layernorm(F[l], pr["mnw"], pr["mnb"], 1e-5, out=xn)
+            ops.gemm(xn, pr["w1"], bias=pr["b1"], act=ops.ACT_GELU, out=mb)
+            if taps is not None and l == 0:
+                c32_ = ops.gemm(mb, pr["w2"], bias=pr["b2"], resid=F[l], out_dtype=f32)
+                taps["cond0"] = c32_.view(B, N, hid)
+            cond.append(ops.gemm(mb, pr["w2"], bias=pr["b2"], resid=F[l], out=E(B * N, hid)))
+
+        # a14/a15: latents + up-sampling stages
+        init_latents = ops.gemm(cond[0], P["lat_w"], bias=P["lat_b"], out_dtype=f32)      # [B*N, hid] == NHWC
+        cur_h, cur_w = gh, gw
+        prev = init_latents.view(B, gh, gw, hid)
+        for i, st in enumerate(P["ups"]):
+            k, cout = st["k"], st["cout"]
+            oh, ow = cur_h, cur_w                      # spatial size of this stage (prev already at it)
+            lat = E(B, oh, ow, cout, dtype=f32)
+            act = E(B, oh, ow, cout)
+            ops.conv_transpose_ks(cond[i + 1], st["ct_w"], k, cout, (gh, gw), bias=st["ct_b"], resid=prev, out=lat,
+                                  out2=act, out2_leaky=True)
+            n_rcu = len(st["rcus"])
+            tmp = E(B, oh, ow, cout)
+            for j, r in enumerate(st["rcus"]):
+                ops.conv3x3(act, r["w1"], bias=r["b1"], act=ops.ACT_LEAKY, out=tmp)
+                ops.conv3x3(tmp, r["w2"], bias=r["b2"], gamma=r["gamma"], resid=lat, out=lat, out2=act,
+                            out2_leaky=(j + 1 < n_rcu))
+            up_c = st["up_w"].shape[0]
+            u = ops.gemm(act.view(B * oh * ow, cout), st["up_w"], bias=st["up_b"], out=E(B * oh * ow, up_c))
+            prev = ops.upsample2x(u.view(B, oh, ow, up_c))
+            cur_h, cur_w = 2 * oh, 2 * ow
+            if taps is not None:
+                taps[f"ups{i}"] = prev.clone()
+        feat_hr = prev                                  # [B, 8gh, 8gw, C] f16
+        C_hr = feat_hr.shape[-1]
+        hh, hw = feat_hr.shape[1], feat_hr.shape[2]
+
+        # a16/a17: depth + confidence heads
+        planes = []
+        for hd in P["heads"]:
+            tln = ops.layernorm(feat_hr, hd["lnw"], hd["lnb"], 1e-5, out=E(B * hh * hw, C_hr))
+            m = ops.gemm(tln, hd["w"], bias=hd["b"], out=E(B * hh * hw, hd["w"].shape[0]))
+            mp = ops.reflect_pad1(m.view(B, hh, hw, -1))
+            lr = ops.conv3x3(mp, hd["lr_w"], bias=hd["lr_b"], prepadded=True)
+            up = ops.resize_ac_pad(lr, nh, nw, 1)
+            planes.append(ops.conv3x3(up, hd["hr_w"], bias=hd["hr_b"], prepadded=True, act=ops.ACT_LEAKY,
+                                      head_w=hd["head_w"], head_b=hd["head_b"], head_add=hd["add"]))
+        radius, confidence = planes
+        if taps is not None:
+            taps["radius_net"] = radius.clone()
+
+        # a18: output assembly
+        pl, pr_, pt, pb = geom["paddings"]
+        out = ops.postprocess(radius, confidence, ray_intr, B, (nh, nw), geom["padded_hw"], pl, pt, geom["out_hw"])
+        out["intrinsics"] = k_out
+        out["depth_features"] = init_latents.view(B, gh, gw, hid).permute(0, 3, 1, 2)
+        return out
+
+    @staticmethod
+    def _gt_intrinsics(camera, B, paddings, factor, dev):
+        """`camera=` argument of infer: a (...,3,3) pinhole K (unidepthv2.py:267-279).  The reference
+        wraps it in Pinhole/BatchCamera, shifts the principal point by the paddings (`crop`,
+        utils/camera.py:115-120) and scales by the resize factor (`resize`, :78-81); rays are then
+        K^-1 [u,v,1] at pixel centres (Pinhole.unproject :252-263).  Here the adjusted
+        (fx,fy,cx,cy) is handed to the ray kernels, which evaluate the same expression."""
+        if not isinstance(camera, torch.Tensor):
+            raise NotImplementedError("camera objects are not supported yet: pass a (...,3,3) pinhole K tensor")
+        assert camera.shape[-1] == 3 and camera.shape[-2] == 3, \
+            "camera tensor should be of shape (..., 3, 3): assume pinhole"
+        K = camera.to(dev, f32).reshape(-1, 3, 3)
+        if K.shape[0] == 1 and B > 1:
+            K = K.expand(B, 3, 3)
+        if float(K[:, 0, 1].abs().max()) != 0.0:
+            raise NotImplementedError("pinhole K with skew is not supported")
+        pl, _, pt, _ = paddings
+        return torch.stack([K[:, 0, 0] * factor, K[:, 1, 1] * factor, (K[:, 0, 2] + pl) * factor,
+                            (K[:, 1, 2] + pt) * factor], dim=1).contiguous()
+
+    # ------------------------------------------------------------------ infer
+    @torch.no_grad()
+    def infer(self, rgb: torch.Tensor, camera: Optional[torch.Tensor] = None, normalize: bool = True):
+        """Same contract as the reference `UniDepthV2.infer` (unidepthv2.py:239-339)."""
+        if self.interpolation_mode != "bilinear":
+            raise NotImplementedError("interpolation_mode other than 'bilinear' is not implemented")
+        level = getattr(self, "resolution_level", None)
+        if level is None:
+            warnings.warn("!! self.resolution_level not set, using default bounds !!")
+        bounds = pixel_bounds(self.shape_constraints, level)
+        if rgb.ndim == 3:
+            rgb = rgb.unsqueeze(0)
+        B, _, H, W = rgb.shape
+        dev = self.device
+        if dev.type != "cuda":
+            raise RuntimeError("unidepth_b200 has no CPU path: move the model to a CUDA device")
+        rgb = rgb.to(dev)
+        if rgb.dtype not in (torch.uint8, f32):
+            rgb = rgb.float()
+        rgb = rgb.contiguous()
+
+        paddings, (ph, pw) = get_paddings((H, W), self.shape_constraints["ratio_bounds"])
+        factor, (nh, nw) = get_resize_factor((ph, pw), bounds)
+        gh, gw = nh // PATCH, nw // PATCH
+        bands = self.spec.hidden // 2
+        geom = dict(paddings=paddings, padded_hw=(ph, pw), factor=factor, net_hw=(nh, nw), out_hw=(H, W))
+        skey = ("scales", gh, gw)
+        if skey not in self._posembed_cache:
+            # positional_embedding.py:231-233 -- computed with the same torch expression (host, once)
+            self._posembed_cache[skey] = (2.0 ** torch.linspace(0.0, math.log2(max(gh, gw) // 2), steps=bands)).to(dev)
+        geom["scales"] = self._posembed_cache[skey]
+
+        gt_intr4 = None
+        if camera is not None:
+            gt_intr4 = self._gt_intrinsics(camera, B, paddings, factor, dev)
+
+        self._weights()
+        self._pos_embed(gh, gw)
+        if not self.use_cuda_graph or gt_intr4 is not None:
+            return self._forward(rgb, geom, normalize, gt_intr4=gt_intr4)
+
+        key = (B, H, W, rgb.dtype, level, bool(normalize), tuple(self.shape_constraints["ratio_bounds"]), bounds)
+        entry = self._graphs.get(key)
+        if entry is None:
+            static_in = rgb.clone()
+            # warm-up on a side stream (allocator + lazy module state), then capture
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._forward(static_in, geom, normalize)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_out = self._forward(static_in, geom, normalize)
+            entry = dict(graph=graph, inp=static_in, out=static_out)
+            self._graphs[key] = entry
+        entry["inp"].copy_(rgb, non_blocking=True)
+        entry["graph"].replay()
+        return {k: v.clone() for k, v in entry["out"].items()}

@@ -1,0 +1,116 @@
+"""CPU-side checks: host logic (shape arithmetic, state-dict layout, HF round trip), the C ABI
+surface (library loads, exports every symbol of include/udb.h, ctypes structs match the C structs),
+and the no-fallback rule.  No GPU compute here."""
+import ctypes
+import json
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _cfg(name="config_v2_vitl14.json"):
+    return json.load(open(os.path.join(ROOT, "tests", "golden", name)))
+
+
+def test_library_exports_every_header_symbol():
+    from unidepth_b200 import _cabi
+    from unidepth_b200.build import build
+    build()
+    hdr = open(os.path.join(ROOT, "include", "udb.h")).read()
+    names = set(re.findall(r"\b(udb_[a-z0-9_]+)\s*\(", hdr))
+    assert names, "no functions parsed from udb.h"
+    lib = ctypes.CDLL(_cabi.LIB_PATH)
+    for n in sorted(names):
+        assert hasattr(lib, n), f"libudb.so does not export {n}"
+    assert set(_cabi.EXPORTS) == names, (set(_cabi.EXPORTS) ^ names)
+    assert _cabi.lib().udb_version() == 1
+    assert _cabi.lib().udb_launch_count() == 0
+
+
+def test_ctypes_structs_match_c_layout():
+    from unidepth_b200 import _cabi
+    structs = {"udb_gemm_t": _cabi.Gemm, "udb_attn_t": _cabi.Attn, "udb_layernorm_t": _cabi.LayerNorm,
+               "udb_preprocess_t": _cabi.Preprocess, "udb_small_linear_t": _cabi.SmallLinear,
+               "udb_ray_embed_t": _cabi.RayEmbed, "udb_postprocess_t": _cabi.Postprocess}
+    last = {"udb_gemm_t": "head_add", "udb_attn_t": "scale", "udb_layernorm_t": "eps", "udb_preprocess_t": "ldp",
+            "udb_small_linear_t": "ldr", "udb_ray_embed_t": "out_f32", "udb_postprocess_t": "out_rays"}
+    src = '#include <stdio.h>\n#include <stddef.h>\n#include "udb.h"\nint main(){\n'
+    for n in structs:
+        src += f'printf("{n} %zu %zu\\n", sizeof({n}), offsetof({n}, {last[n]}));\n'
+    src += "return 0;}\n"
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(src)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "t.c"), "-o", os.path.join(d, "t")])
+        out = subprocess.check_output([os.path.join(d, "t")], text=True)
+    for line in out.strip().splitlines():
+        n, size, off = line.split()
+        cs = structs[n]
+        assert ctypes.sizeof(cs) == int(size), (n, ctypes.sizeof(cs), size)
+        field = cs._fields_[-1][0]
+        assert getattr(cs, field).offset == int(off), (n, field)
+
+
+def test_param_layout_matches_oracle_fixture():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import fixture
+    from unidepth_b200.spec import param_shapes
+    for name in ("config_v2_vits14.json", "config_v2_vitb14.json", "config_v2_vitl14.json"):
+        cfg = _cfg(name)
+        assert list(param_shapes(cfg).items()) == list(fixture.param_shapes(cfg).items())
+
+
+def test_shape_arithmetic_matches_oracle_and_reference_examples():
+    import unidepth_oracle as O
+    from unidepth_b200 import spec
+    g = torch.Generator().manual_seed(0)
+    for _ in range(300):
+        h = int(torch.randint(16, 2200, (1,), generator=g))
+        w = int(torch.randint(16, 2200, (1,), generator=g))
+        a = spec.get_paddings((h, w), (0.5, 2.5))
+        assert a == O.get_paddings((h, w), (0.5, 2.5))
+        for lvl in (None, 0, 4, 9):
+            b1 = spec.pixel_bounds({"pixels_min": 200000, "pixels_max": 600000}, lvl)
+            assert b1 == O.resolve_pixel_bounds((200000, 600000), lvl)
+            f, (nh, nw) = spec.get_resize_factor(a[1], b1)
+            assert (f, (nh, nw)) == O.get_resize_factor(a[1], b1)
+            assert nh % 14 == 0 and nw % 14 == 0
+    assert spec.get_resize_factor((480, 640), (2e5, 6e5))[1] == (490, 644)
+    assert spec.get_resize_factor((1024, 1536), (2e5, 6e5))[1] == (644, 952)
+    assert spec.get_paddings((480, 1600), (0.5, 2.5)) == ((0, 0, 80, 80), (640, 1600))
+
+
+def test_state_dict_round_trip_and_no_cpu_fallback():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import fixture
+    from unidepth_b200 import UniDepthV2
+    cfg = _cfg("config_v2_vits14.json")
+    m = UniDepthV2(cfg)
+    sd = fixture.make_state_dict(cfg, 3)
+    info = m.load_state_dict(sd, strict=True)
+    assert not info.missing_keys and not info.unexpected_keys
+    with tempfile.TemporaryDirectory() as d:
+        m.save_pretrained(d)
+        assert os.path.exists(os.path.join(d, "config.json")) and os.path.exists(os.path.join(d, "model.safetensors"))
+        m2 = UniDepthV2.from_pretrained(d)
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, m2.state_dict()[k]), k
+    assert m.device.type == "cpu"
+    with pytest.raises(RuntimeError, match="no CPU"):
+        m.infer(torch.zeros(3, 64, 64, dtype=torch.uint8))
+    with pytest.raises(NotImplementedError):
+        m(torch.zeros(1))
+
+
+def test_unknown_encoder_is_rejected():
+    from unidepth_b200 import UniDepthV2
+    cfg = _cfg("config_v2_vits14.json")
+    cfg["model"]["pixel_encoder"]["name"] = "convnext_large"
+    with pytest.raises(NotImplementedError):
+        UniDepthV2(cfg)

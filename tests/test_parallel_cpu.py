@@ -1,0 +1,64 @@
+"""Host-side logic of the image-wise data-parallel path on CPU: shard bounds, pack/unpack, and the
+single all-gather over a world_size-2 gloo group."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _fake_out(b, seed):
+    g = torch.Generator().manual_seed(seed)
+    r = lambda *s: torch.randn(*s, generator=g)
+    return {"confidence": r(b, 1, 6, 8), "intrinsics": r(b, 3, 3), "radius": r(b, 1, 6, 8), "depth": r(b, 1, 6, 8),
+            "points": r(b, 3, 6, 8), "rays": r(b, 3, 6, 8), "depth_features": r(b, 2, 3, 16).permute(0, 3, 1, 2)}
+
+
+def test_shard_bounds_cover_batch():
+    from unidepth_b200.parallel import shard_bounds
+    for n in (1, 7, 8, 64, 65):
+        for w in (1, 2, 3, 8):
+            spans = [shard_bounds(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+
+
+def test_pack_unpack_round_trip():
+    from unidepth_b200.parallel import pack_outputs, unpack_outputs
+    out = _fake_out(3, 0)
+    back = unpack_outputs(pack_outputs(out), out)
+    for k in out:
+        assert torch.equal(back[k], out[k]), k
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from unidepth_b200.parallel import gather_outputs
+    out = _fake_out(2, rank)
+    full = gather_outputs(out, world)
+    ok = True
+    for r in range(world):
+        exp = _fake_out(2, r)
+        for k in exp:
+            ok &= torch.equal(full[k][2 * r:2 * r + 2], exp[k])
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_gather_outputs_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    ps = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=120) for _ in ps]
+    for p in ps:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]

@@ -32,6 +32,12 @@ def test_layernorm(dim):
     assert _err(ops.layernorm(x, w, b, 1e-6, out_dtype=torch.float16), ref, "ln f16") < 8e-3
     assert _err(ops.layernorm(x.half(), w, b, 1e-5, out_dtype=torch.float32),
                 F.layer_norm(x.half().float(), (dim,), w, b, 1e-5), "ln f16 in") < 2e-5
+    if dim in (128,):
+        for d2 in (64, 128, 256):
+            xs = (torch.randn(100003, d2, device=dev) * 2 + 0.3).half()
+            w2, b2 = torch.randn(d2, device=dev), torch.randn(d2, device=dev)
+            assert _err(ops.layernorm(xs, w2, b2, 1e-5, out_dtype=torch.float16),
+                        F.layer_norm(xs.float(), (d2,), w2, b2, 1e-5), f"ln f16->f16 small {d2}") < 8e-3
     # drop the cls row of each image: rows (b, 1 + n)
     Bn, T = 7, 143
     xt = torch.randn(Bn * T, dim, device=dev)

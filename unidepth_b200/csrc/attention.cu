@@ -140,70 +140,94 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int row = quad * 32 + lane;           // query row inside the tile == TMEM lane
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
     float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
-    float acc[HD];
+    uint64_t acc2[HD / 2];                      // running output, packed f32x2
 #pragma unroll
-    for (int i = 0; i < HD; ++i) acc[i] = 0.f;
+    for (int i = 0; i < HD / 2; ++i) acc2[i] = 0ull;
     uint8_t* p_row = sP + row * 128;
     const int sw = row & 7;
+    const float sc = p.scale_log2;
+
+    auto fold_output = [&](float a) {           // acc = acc * a + O_j   (O_j from TMEM)
+      uint32_t r0[32], r1[32];
+      tmem_ld_32x32b_x32(tmem_O + lane_addr, r0);
+      tmem_ld_32x32b_x32(tmem_O + lane_addr + 32, r1);
+      tmem_ld_wait();
+      const uint64_t a2 = pack2(a, a);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        acc2[i] = fma2(acc2[i], a2, pack2u(r0[2 * i], r0[2 * i + 1]));
+        acc2[16 + i] = fma2(acc2[16 + i], a2, pack2u(r1[2 * i], r1[2 * i + 1]));
+      }
+    };
 
     for (int j = 0; j < n_tiles; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after_sync();
       const int kv_left = p.seq_k - j * AT_BK;   // valid keys in this tile (>= 1)
-      // pass 1: row max
+      const bool full = kv_left >= AT_BK;
+      // ---- pass 1: row max (two 32-column chunks in flight)
       float mx = -INFINITY;
 #pragma unroll 1
-      for (int c = 0; c < AT_BK; c += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_S + lane_addr + c, r);
+      for (int c = 0; c < AT_BK; c += 64) {
+        uint32_t r0[32], r1[32];
+        tmem_ld_32x32b_x32(tmem_S + lane_addr + c, r0);
+        tmem_ld_32x32b_x32(tmem_S + lane_addr + c + 32, r1);
         tmem_ld_wait();
+        if (full) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float s = __uint_as_float(r[i]);
-          mx = (c + i < kv_left) ? fmaxf(mx, s) : mx;
+          for (int i = 0; i < 32; i += 2) {
+            mx = max3(mx, __uint_as_float(r0[i]), __uint_as_float(r0[i + 1]));
+            mx = max3(mx, __uint_as_float(r1[i]), __uint_as_float(r1[i + 1]));
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            mx = (c + i < kv_left) ? fmaxf(mx, __uint_as_float(r0[i])) : mx;
+            mx = (c + 32 + i < kv_left) ? fmaxf(mx, __uint_as_float(r1[i])) : mx;
+          }
         }
       }
-      const float m_new = fmaxf(m_run, mx * p.scale_log2);
+      const float m_new = fmaxf(m_run, mx * sc);
       const float alpha = ex2(m_run - m_new);
       // fold in the previous tile's P V (also guarantees the PV MMA finished reading sP)
       if (j > 0) {
         mbar_wait(o_full, (j - 1) & 1);
         tc_fence_after_sync();
-#pragma unroll
-        for (int c = 0; c < HD; c += 32) {
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(tmem_O + lane_addr + c, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) acc[c + i] = fmaf(acc[c + i], alpha_prev, __uint_as_float(r[i]));
-        }
+        fold_output(alpha_prev);
       }
       alpha_prev = alpha;
       m_run = m_new;
-      // pass 2: p = exp2(s*scale - m), row sum, f16 P into swizzled smem
-      float psum = 0.f;
+      // ---- pass 2: p = exp2(s*scale - m), row sum, f16 P into swizzled smem
+      uint64_t psum2 = 0ull;
+      const uint64_t sc2 = pack2(sc, sc), nm2 = pack2(-m_new, -m_new);
 #pragma unroll 1
       for (int c = 0; c < AT_BK; c += 32) {
         uint32_t r[32];
         tmem_ld_32x32b_x32(tmem_S + lane_addr + c, r);
         tmem_ld_wait();
-        float pv[32];
+        uint32_t ph[16];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float e = ex2(fmaf(__uint_as_float(r[i]), p.scale_log2, -m_new));
-          pv[i] = (c + i < kv_left) ? e : 0.f;
-          psum += pv[i];
+        for (int i = 0; i < 16; ++i) {
+          float t0, t1;
+          unpack2(fma2(pack2u(r[2 * i], r[2 * i + 1]), sc2, nm2), t0, t1);
+          float e0 = ex2(t0), e1 = ex2(t1);
+          if (!full) {
+            e0 = (c + 2 * i < kv_left) ? e0 : 0.f;
+            e1 = (c + 2 * i + 1 < kv_left) ? e1 : 0.f;
+          }
+          psum2 = add2(psum2, pack2(e0, e1));
+          ph[i] = pack_half2(e0, e1);
         }
         uint8_t* sub = p_row + (c >> 6) * (kPBytes / 2);
         const int chunk0 = (c & 63) >> 3;          // first 16-byte chunk of this 32-column group
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint4 u = make_uint4(pack_half2(pv[8 * q], pv[8 * q + 1]), pack_half2(pv[8 * q + 2], pv[8 * q + 3]),
-                                     pack_half2(pv[8 * q + 4], pv[8 * q + 5]), pack_half2(pv[8 * q + 6], pv[8 * q + 7]));
-          *reinterpret_cast<uint4*>(sub + (((chunk0 + q) ^ sw) << 4)) = u;
-        }
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<uint4*>(sub + (((chunk0 + q) ^ sw) << 4)) =
+              make_uint4(ph[4 * q], ph[4 * q + 1], ph[4 * q + 2], ph[4 * q + 3]);
       }
-      l_run = fmaf(l_run, alpha, psum);
+      float ps0, ps1;
+      unpack2(psum2, ps0, ps1);
+      l_run = fmaf(l_run, alpha, ps0 + ps1);
       fence_proxy_async_smem();
       tc_fence_before_sync();
       __syncwarp();
@@ -212,23 +236,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // last tile's P V
     mbar_wait(o_full, (n_tiles - 1) & 1);
     tc_fence_after_sync();
-#pragma unroll
-    for (int c = 0; c < HD; c += 32) {
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(tmem_O + lane_addr + c, r);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) acc[c + i] = fmaf(acc[c + i], alpha_prev, __uint_as_float(r[i]));
-    }
+    fold_output(alpha_prev);
     const int q = q0 + row;
     if (q < p.seq_q) {
       const float inv = 1.0f / l_run;
       __half* op = p.out + ((long long)b * p.seq_q + q) * p.ldo + p.o_col0 + head * HD;
 #pragma unroll
-      for (int i = 0; i < HD; i += 8) {
-        *reinterpret_cast<uint4*>(op + i) =
-            make_uint4(pack_half2(acc[i] * inv, acc[i + 1] * inv), pack_half2(acc[i + 2] * inv, acc[i + 3] * inv),
-                       pack_half2(acc[i + 4] * inv, acc[i + 5] * inv), pack_half2(acc[i + 6] * inv, acc[i + 7] * inv));
+      for (int i = 0; i < HD / 8; ++i) {
+        float v[8];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) unpack2(acc2[4 * i + t], v[2 * t], v[2 * t + 1]);
+        *reinterpret_cast<uint4*>(op + 8 * i) =
+            make_uint4(pack_half2(v[0] * inv, v[1] * inv), pack_half2(v[2] * inv, v[3] * inv),
+                       pack_half2(v[4] * inv, v[5] * inv), pack_half2(v[6] * inv, v[7] * inv));
       }
     }
   }

@@ -76,6 +76,52 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const udb_layernorm_t p)
   }
 }
 
+// f16 -> f16 rows of 8*LPR elements (64 / 128 / 256): LPR lanes per row, 16 bytes per lane, so a warp
+// moves 512 contiguous bytes per instruction (the one-warp-per-row kernel above would move 128-256 B).
+template <int LPR>
+__global__ void __launch_bounds__(256) layernorm_f16_small_kernel(const udb_layernorm_t p) {
+  constexpr int RPW = 32 / LPR;                       // rows per warp
+  const int lane = threadIdx.x & 31;
+  const long long row = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * RPW + lane / LPR;
+  const int sub = lane % LPR;
+  const bool valid = row < p.rows;
+  float x[8];
+  if (valid) {
+    const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(p.in) + row * p.ld_in + sub * 8);
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float2 f = __half22float2(h[q]);
+      x[2 * q] = f.x;
+      x[2 * q + 1] = f.y;
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) x[q] = 0.f;
+  }
+  float s = ((x[0] + x[1]) + (x[2] + x[3])) + ((x[4] + x[5]) + (x[6] + x[7]));
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)p.dim;
+  float v = 0.f;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) v += (x[q] - mean) * (x[q] - mean);
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const float rstd = rsqrtf(v / (float)p.dim + p.eps);
+  if (valid) {
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.weight + sub * 8)), w1 = __ldg(reinterpret_cast<const float4*>(p.weight + sub * 8 + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + sub * 8)), b1 = __ldg(reinterpret_cast<const float4*>(p.bias + sub * 8 + 4));
+    const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+    const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    float y[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) y[q] = (x[q] - mean) * rstd * w[q] + b[q];
+    *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + row * p.ld_out + sub * 8) =
+        make_uint4(pack_half2(y[0], y[1]), pack_half2(y[2], y[3]), pack_half2(y[4], y[5]), pack_half2(y[6], y[7]));
+  }
+}
+
 // ------------------------------------------------------------------------------------ preprocess
 __device__ __forceinline__ void bilinear_src(float scale, int dst, int in_size, int& i0, int& i1, float& l0, float& l1) {
   // ATen area_pixel_compute_source_index (align_corners=False): fp32 index arithmetic
@@ -466,6 +512,15 @@ using namespace udb;
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
 
 extern "C" int udb_layernorm(const udb_layernorm_t* p, void* stream) {
+  if (!p->in_f32 && !p->out_f32 && p->rows_per_group <= 0 && (p->dim == 64 || p->dim == 128 || p->dim == 256)) {
+    const int lpr = p->dim / 8, rpb = 8 * (32 / lpr);
+    const int g = (p->rows + rpb - 1) / rpb;
+    if (g == 0) return 0;
+    if (lpr == 8) layernorm_f16_small_kernel<8><<<g, 256, 0, ST(stream)>>>(*p);
+    else if (lpr == 16) layernorm_f16_small_kernel<16><<<g, 256, 0, ST(stream)>>>(*p);
+    else layernorm_f16_small_kernel<32><<<g, 256, 0, ST(stream)>>>(*p);
+    return check_launch("layernorm_f16_small_kernel");
+  }
   if (p->dim % 128 != 0 || p->dim > 1024) { set_error("udb_layernorm: dim %d unsupported (multiple of 128, <= 1024)", p->dim); return 1; }
   const int grid = (p->rows + 7) / 8;
   if (grid == 0) return 0;

@@ -232,7 +232,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
           if (p.act == UDB_ACT_GELU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
           } else if (p.act == UDB_ACT_LEAKY) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = leaky(v[j]);

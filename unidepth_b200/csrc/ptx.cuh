@@ -187,9 +187,58 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int m, int n, bool a_mn_ma
          | (static_cast<uint32_t>(m >> 4) << 24); // M / 16
 }
 
+// ----------------------------------------------------------------------------- packed f32x2 math
+// Blackwell issues two fp32 FMAs / adds per instruction (FFMA2 / FADD2) on 64-bit register pairs.
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+  return d;
+}
+__device__ __forceinline__ uint64_t pack2u(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
 // ----------------------------------------------------------------------------- misc math
 __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+// GELU(erf) with erf from Abramowitz & Stegun 7.1.26 (|erf error| < 1.5e-7): 1 rcp + 1 ex2 + 8 FMA,
+// about half the instructions of erff(); used in the GEMM epilogue where the result is rounded
+// to f16 (5e-4 relative) anyway.
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
+  const float erf_abs = fmaf(-poly, e, 1.0f);          // erf(|x|/sqrt2)
+  const float h = 0.5f * x;
+  return fmaf(copysignf(erf_abs, x), h, h);            // 0.5 x (1 + erf)
 }
 __device__ __forceinline__ float leaky(float x) { return x > 0.f ? x : 0.01f * x; }
 

@@ -49,7 +49,10 @@ struct GemmCfg {
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = (2 * BN) < 32 ? 32 : (2 * BN);
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  // epilogue staging: per epilogue warp a 32x32 f32 transpose tile (XOR-swizzled, no padding) and
+  // 2 x 32 row offsets, so that global loads/stores are row-contiguous (coalesced) per instruction
+  static constexpr int kStagingBytes = kEpiWarps * (32 * 32 * 4 + 2 * 32 * 4);
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 256 /*barriers*/;
 };
 
 template <int BN>
@@ -58,11 +61,11 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const GemmArgs p) {
   using Cfg = GemmCfg<BN>;
   constexpr int kStages = Cfg::kStages;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sB = smem + kStages * Cfg::kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint8_t* staging = smem + kStages * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::kStagingBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kStages;
   uint64_t* tmem_full = bars + 2 * kStages;
@@ -73,6 +76,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
+    if (smem_u32(smem) & 1023) __trap();   // 128B-swizzle atoms need a 1024 B aligned base
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
   }
@@ -170,6 +174,9 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int grp = ew >> 2;              // column half
     constexpr int kColsPerGrp = BN / kGroups;
     const int r_in_tile = quad * 32 + lane;
+    float* T = reinterpret_cast<float*>(staging) + ew * 1024;                       // [32][32], col ^ row
+    uint32_t* roff_out = reinterpret_cast<uint32_t*>(staging + kEpiWarps * 4096) + ew * 64;
+    uint32_t* roff_res = roff_out + 32;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
@@ -210,6 +217,10 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           res_off = (p.resid_mod > 0) ? ((long long)(m % p.resid_mod) + p.resid_roff) * p.ldr
                                       : orow * p.ldr;
         }
+        const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+        roff_out[lane] = static_cast<uint32_t>(out_off);
+        roff_res[lane] = static_cast<uint32_t>(res_off);
+        __syncwarp();
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
 #pragma unroll 1
         for (int c = 0; c < kColsPerGrp; c += 32) {
@@ -218,7 +229,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           uint32_t r[32];
           tmem_ld_32x32b_x32(t_row + col, r);
           tmem_ld_wait();
-          if (!valid || n0 >= p.N) continue;
+          if (n0 >= p.N) continue;   // warp-uniform
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
@@ -242,7 +253,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
             for (int j = 0; j < 32; ++j) acc = fmaf(v[j], __ldg(p.head_w + j), acc);
             acc = fminf(fmaxf(acc, -8.0f), 8.0f) + p.head_add;
-            reinterpret_cast<float*>(p.out)[out_off] = expf(acc);
+            if (valid) reinterpret_cast<float*>(p.out)[out_off] = expf(acc);
             continue;
           }
           if (p.gamma) {
@@ -260,59 +271,73 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const long long W2 = (long long)p.ct_w * p.ct_k;
             coff = ((long long)(tap / p.ct_k) * W2 + (tap % p.ct_k)) * p.ct_cout + co;
           }
+          // ---- residual / stores through the per-warp transpose tile: thread == row in registers,
+          //      lane == column in global memory (each instruction touches one contiguous row segment)
+          const uint32_t c32 = static_cast<uint32_t>(coff);
           if (p.resid) {
             if (p.resid_f32) {
-              const float4* rp = reinterpret_cast<const float4*>(
-                  reinterpret_cast<const float*>(p.resid) + res_off + coff);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 r4 = rp[j];
-                v[4 * j] += r4.x; v[4 * j + 1] += r4.y; v[4 * j + 2] += r4.z; v[4 * j + 3] += r4.w;
-              }
+              const float* rp = reinterpret_cast<const float*>(p.resid);
+#pragma unroll 8
+              for (int r = 0; r < 32; ++r)
+                T[r * 32 + (lane ^ r)] = ((vmask >> r) & 1u) ? rp[(size_t)roff_res[r] + c32 + lane] : 0.f;
             } else {
-              const uint4* rp = reinterpret_cast<const uint4*>(
-                  reinterpret_cast<const __half*>(p.resid) + res_off + coff);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const uint4 u = rp[j];
-                const __half2* h = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  const float2 f = __half22float2(h[q]);
-                  v[8 * j + 2 * q] += f.x;
-                  v[8 * j + 2 * q + 1] += f.y;
-                }
+              const __half* rp = reinterpret_cast<const __half*>(p.resid);
+              const int l2 = (lane & 15) * 2;
+#pragma unroll 8
+              for (int r = 0; r < 32; r += 2) {
+                const int rr = r + (lane >> 4);
+                float2 f = make_float2(0.f, 0.f);
+                if ((vmask >> rr) & 1u)
+                  f = __half22float2(*reinterpret_cast<const __half2*>(rp + (size_t)roff_res[rr] + c32 + l2));
+                T[rr * 32 + (l2 ^ rr)] = f.x;
+                T[rr * 32 + ((l2 + 1) ^ rr)] = f.y;
               }
             }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += T[lane * 32 + (j ^ lane)];
+            __syncwarp();
           }
           if (p.out) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) T[lane * 32 + (j ^ lane)] = v[j];
+            __syncwarp();
             if (p.out_f32) {
-              float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + out_off + coff);
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              float* op = reinterpret_cast<float*>(p.out);
+#pragma unroll 8
+              for (int r = 0; r < 32; ++r)
+                if ((vmask >> r) & 1u) op[(size_t)roff_out[r] + c32 + lane] = T[r * 32 + (lane ^ r)];
             } else {
-              uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + out_off + coff);
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                op[j] = make_uint4(pack_half2(v[8 * j], v[8 * j + 1]), pack_half2(v[8 * j + 2], v[8 * j + 3]),
-                                   pack_half2(v[8 * j + 4], v[8 * j + 5]), pack_half2(v[8 * j + 6], v[8 * j + 7]));
+              __half* op = reinterpret_cast<__half*>(p.out);
+              const int l2 = (lane & 15) * 2;
+#pragma unroll 8
+              for (int r = 0; r < 32; r += 2) {
+                const int rr = r + (lane >> 4);
+                if ((vmask >> rr) & 1u)
+                  *reinterpret_cast<uint32_t*>(op + (size_t)roff_out[rr] + c32 + l2) =
+                      pack_half2(T[rr * 32 + (l2 ^ rr)], T[rr * 32 + ((l2 + 1) ^ rr)]);
+              }
             }
+            __syncwarp();
           }
           if (p.out2) {
-            uint4* op = reinterpret_cast<uint4*>(p.out2 + out_off + coff);
-            if (!p.out2_leaky) {
+            if (p.out2_leaky) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                op[j] = make_uint4(pack_half2(v[8 * j], v[8 * j + 1]), pack_half2(v[8 * j + 2], v[8 * j + 3]),
-                                   pack_half2(v[8 * j + 4], v[8 * j + 5]), pack_half2(v[8 * j + 6], v[8 * j + 7]));
-            } else
+              for (int j = 0; j < 32; ++j) T[lane * 32 + (j ^ lane)] = leaky(v[j]);
+            } else if (!p.out) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              op[j] = make_uint4(pack_half2(leaky(v[8 * j]), leaky(v[8 * j + 1])),
-                                 pack_half2(leaky(v[8 * j + 2]), leaky(v[8 * j + 3])),
-                                 pack_half2(leaky(v[8 * j + 4]), leaky(v[8 * j + 5])),
-                                 pack_half2(leaky(v[8 * j + 6]), leaky(v[8 * j + 7])));
+              for (int j = 0; j < 32; ++j) T[lane * 32 + (j ^ lane)] = v[j];
+            }   // else: T still holds v from the `out` pass
+            __syncwarp();
+            const int l2 = (lane & 15) * 2;
+#pragma unroll 8
+            for (int r = 0; r < 32; r += 2) {
+              const int rr = r + (lane >> 4);
+              if ((vmask >> rr) & 1u)
+                *reinterpret_cast<uint32_t*>(p.out2 + (size_t)roff_out[rr] + c32 + l2) =
+                    pack_half2(T[rr * 32 + (l2 ^ rr)], T[rr * 32 + ((l2 + 1) ^ rr)]);
+            }
+            __syncwarp();
           }
         }
       }

@@ -38,6 +38,14 @@ def bench_gemm():
         print(f"gemm {M}x{N}x{K}: {ms:.3f} ms  {2*M*N*K/ms/1e9:.1f} TFLOP/s", flush=True)
         ms = timeit(lambda: torch.matmul(a, w.t()))
         print(f"   torch.matmul: {ms:.3f} ms  {2*M*N*K/ms/1e9:.1f} TFLOP/s", flush=True)
+        if N <= 1024:
+            x = torch.randn(M, N, device=dev)
+            gamma = torch.rand(N, device=dev)
+            ms = timeit(lambda: ops.gemm(a, w, bias=bias, gamma=gamma, resid=x, out=x))
+            print(f"   + gamma, f32 residual in place: {ms:.3f} ms  {2*M*N*K/ms/1e9:.1f} TFLOP/s", flush=True)
+        if N == 4096:
+            ms = timeit(lambda: ops.gemm(a, w, bias=bias, act=ops.ACT_GELU, out=out))
+            print(f"   + GELU: {ms:.3f} ms  {2*M*N*K/ms/1e9:.1f} TFLOP/s", flush=True)
 
 
 def bench_attn():
@@ -62,6 +70,12 @@ def bench_conv():
         ms = timeit(lambda: ops.conv3x3(x, w, bias=bias, out=out))
         fl = 2 * B * H * W * N * 9 * C
         print(f"conv3x3 {B}x{H}x{W}x{C}->{N}: {ms:.3f} ms  {fl/ms/1e9:.1f} TFLOP/s", flush=True)
+        if N == C:
+            lat = torch.randn(B, H, W, N, device=dev)
+            act = torch.empty(B, H, W, N, device=dev, dtype=torch.float16)
+            gamma = torch.rand(N, device=dev)
+            ms = timeit(lambda: ops.conv3x3(x, w, bias=bias, gamma=gamma, resid=lat, out=lat, out2=act))
+            print(f"   + gamma, f32 residual in place, f16 leaky copy: {ms:.3f} ms  {fl/ms/1e9:.1f} TFLOP/s", flush=True)
 
 
 if __name__ == "__main__":

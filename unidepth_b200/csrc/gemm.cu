@@ -275,20 +275,31 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           //      lane == column in global memory (each instruction touches one contiguous row segment)
           const uint32_t c32 = static_cast<uint32_t>(coff);
           if (p.resid) {
+            // all 32 (16) row loads are issued before the first use: the epilogue is latency-bound
+            // on these loads, so memory-level parallelism matters more than instruction count
             if (p.resid_f32) {
               const float* rp = reinterpret_cast<const float*>(p.resid);
-#pragma unroll 8
+              float tmp[32];
+#pragma unroll
               for (int r = 0; r < 32; ++r)
-                T[r * 32 + (lane ^ r)] = ((vmask >> r) & 1u) ? rp[(size_t)roff_res[r] + c32 + lane] : 0.f;
+                tmp[r] = ((vmask >> r) & 1u) ? rp[(size_t)roff_res[r] + c32 + lane] : 0.f;
+#pragma unroll
+              for (int r = 0; r < 32; ++r) T[r * 32 + (lane ^ r)] = tmp[r];
             } else {
               const __half* rp = reinterpret_cast<const __half*>(p.resid);
               const int l2 = (lane & 15) * 2;
-#pragma unroll 8
-              for (int r = 0; r < 32; r += 2) {
-                const int rr = r + (lane >> 4);
-                float2 f = make_float2(0.f, 0.f);
-                if ((vmask >> rr) & 1u)
-                  f = __half22float2(*reinterpret_cast<const __half2*>(rp + (size_t)roff_res[rr] + c32 + l2));
+              __half2 tmp[16];
+#pragma unroll
+              for (int r = 0; r < 16; ++r) {
+                const int rr = 2 * r + (lane >> 4);
+                tmp[r] = ((vmask >> rr) & 1u)
+                             ? *reinterpret_cast<const __half2*>(rp + (size_t)roff_res[rr] + c32 + l2)
+                             : __floats2half2_rn(0.f, 0.f);
+              }
+#pragma unroll
+              for (int r = 0; r < 16; ++r) {
+                const int rr = 2 * r + (lane >> 4);
+                const float2 f = __half22float2(tmp[r]);
                 T[rr * 32 + (l2 ^ rr)] = f.x;
                 T[rr * 32 + ((l2 + 1) ^ rr)] = f.y;
               }
@@ -304,13 +315,13 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             __syncwarp();
             if (p.out_f32) {
               float* op = reinterpret_cast<float*>(p.out);
-#pragma unroll 8
+#pragma unroll
               for (int r = 0; r < 32; ++r)
                 if ((vmask >> r) & 1u) op[(size_t)roff_out[r] + c32 + lane] = T[r * 32 + (lane ^ r)];
             } else {
               __half* op = reinterpret_cast<__half*>(p.out);
               const int l2 = (lane & 15) * 2;
-#pragma unroll 8
+#pragma unroll
               for (int r = 0; r < 32; r += 2) {
                 const int rr = r + (lane >> 4);
                 if ((vmask >> rr) & 1u)
@@ -330,7 +341,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }   // else: T still holds v from the `out` pass
             __syncwarp();
             const int l2 = (lane & 15) * 2;
-#pragma unroll 8
+#pragma unroll
             for (int r = 0; r < 32; r += 2) {
               const int rr = r + (lane >> 4);
               if ((vmask >> rr) & 1u)

@@ -4,9 +4,9 @@
 // <= 113 KB shared memory each) so one CTA's softmax overlaps the other's tensor-core work.
 //   warp 0      : TMA producer (Q once; K_j / V_j tiles of 128 keys through a 2-stage ring)
 //   warp 1      : TMEM allocator + MMA issuer (S = Q K_j^T : M128 N128 K64 ;  O_j = P_j V_j : M128 N64 K128)
-//   warps 2..5  : softmax, one query row per thread: S from TMEM (tcgen05.ld), online max / sum in
-//                 fp32, P_j written as f16 into 128B-swizzled shared memory for the PV MMA,
-//                 running output kept in registers (O_acc = O_acc * alpha + O_j).
+//   warps 2..9  : softmax, two threads per query row (64 keys each): S from TMEM (tcgen05.ld), max /
+//                 sum in fp32, P_j written as f16 into 128B-swizzled shared memory for the PV MMA.
+//                 O stays in TMEM, accumulated by the PV MMAs, and is rescaled lazily.
 // Replaces F.scaled_dot_product_attention (reference: metadinov2/attention.py:58,
 // layers/attention.py:136).
 #include "common.h"
@@ -16,7 +16,7 @@ namespace udb {
 
 constexpr int AT_BQ = 128;   // queries per CTA
 constexpr int AT_BK = 128;   // keys per tile
-constexpr int AT_THREADS = 192;
+constexpr int AT_THREADS = 320;   // TMA warp, MMA warp, 8 softmax warps
 
 struct AttnArgs {
   __half* out;
@@ -55,6 +55,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* p_full = bars + 8;
   uint64_t* o_full = bars + 9;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 10);
+  uint16_t* xch = reinterpret_cast<uint16_t*>(bars + 16);   // [2][128] partial row maxima (bf16, rounded up)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -75,7 +76,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(&kv_empty[i], 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(p_full, 4);
+    mbar_init(p_full, 8);
     mbar_init(o_full, 1);
     fence_barrier_init();
   }
@@ -127,7 +128,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           // A = P: sub-tile (ks/4) of 16 KB, 32 B per 16-key step inside the swizzle atom
           const uint64_t dp = umma_desc_sw128(smem_u32(sP + (ks >> 2) * (kPBytes / 2)), 16, 1024) + 2 * (ks & 3);
           // B = V (MN-major): 16 key rows = 2 KB per step
-          umma_f16_ss(tmem_O, dp, dv + (uint64_t)(ks * 2048 >> 4), idesc_pv, ks != 0);
+          umma_f16_ss(tmem_O, dp, dv + (uint64_t)(ks * 2048 >> 4), idesc_pv, (j | ks) != 0);
         }
         umma_commit(&kv_empty[st]);
         umma_commit(o_full);
@@ -136,119 +137,134 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
   } else {
     // ------------------------------------------------------------------ softmax warps
-    const int quad = warp & 3;
+    // Two threads per query row: warp (2 + quad') handles keys [0,64) of 32 rows, warp (6 + quad')
+    // keys [64,128) of the same rows.  The partial row maxima are exchanged through shared memory
+    // as bf16 values rounded UP (any common upper bound is a valid softmax reference point), so both
+    // threads derive the identical reference maximum.  O stays in TMEM, accumulated by the PV MMAs;
+    // it is rescaled (tcgen05.ld -> mul -> tcgen05.st) only when a row maximum grows by more than
+    // 2^8 over the current reference ("lazy rescale"), so probabilities are bounded by 2^8 (fine
+    // for f16) and the final O / l is exact because both use the same reference.
+    const int quad = warp & 3;                  // TMEM lane quadrant of this warp
+    const int half = (warp - 2) >> 2;           // which 64 keys of the tile
     const int row = quad * 32 + lane;           // query row inside the tile == TMEM lane
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
-    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
-    uint64_t acc2[HD / 2];                      // running output, packed f32x2
-#pragma unroll
-    for (int i = 0; i < HD / 2; ++i) acc2[i] = 0ull;
-    uint8_t* p_row = sP + row * 128;
+    float m_used = -INFINITY, l_run = 0.f;
+    uint8_t* p_sub = sP + half * (kPBytes / 2) + row * 128;
     const int sw = row & 7;
     const float sc = p.scale_log2;
-
-    auto fold_output = [&](float a) {           // acc = acc * a + O_j   (O_j from TMEM)
-      uint32_t r0[32], r1[32];
-      tmem_ld_32x32b_x32(tmem_O + lane_addr, r0);
-      tmem_ld_32x32b_x32(tmem_O + lane_addr + 32, r1);
-      tmem_ld_wait();
-      const uint64_t a2 = pack2(a, a);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        acc2[i] = fma2(acc2[i], a2, pack2u(r0[2 * i], r0[2 * i + 1]));
-        acc2[16 + i] = fma2(acc2[16 + i], a2, pack2u(r1[2 * i], r1[2 * i + 1]));
-      }
-    };
+    constexpr float kRescaleThreshold = 8.0f;   // log2 domain
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory"); };
 
     for (int j = 0; j < n_tiles; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after_sync();
-      const int kv_left = p.seq_k - j * AT_BK;   // valid keys in this tile (>= 1)
-      const bool full = kv_left >= AT_BK;
-      // ---- pass 1: row max (two 32-column chunks in flight)
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < AT_BK; c += 64) {
-        uint32_t r0[32], r1[32];
-        tmem_ld_32x32b_x32(tmem_S + lane_addr + c, r0);
-        tmem_ld_32x32b_x32(tmem_S + lane_addr + c + 32, r1);
+      const int kv_left = p.seq_k - j * AT_BK - half * 64;   // valid keys in this thread's 64 (may be <= 0)
+      const bool full = kv_left >= 64;
+      uint32_t sv[64];
+      {
+        uint32_t(&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[0]);
+        uint32_t(&s1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[32]);
+        tmem_ld_32x32b_x32(tmem_S + lane_addr + half * 64, s0);
+        tmem_ld_32x32b_x32(tmem_S + lane_addr + half * 64 + 32, s1);
         tmem_ld_wait();
-        if (full) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            mx = max3(mx, __uint_as_float(r0[i]), __uint_as_float(r0[i + 1]));
-            mx = max3(mx, __uint_as_float(r1[i]), __uint_as_float(r1[i + 1]));
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            mx = (c + i < kv_left) ? fmaxf(mx, __uint_as_float(r0[i])) : mx;
-            mx = (c + 32 + i < kv_left) ? fmaxf(mx, __uint_as_float(r1[i])) : mx;
-          }
-        }
       }
-      const float m_new = fmaxf(m_run, mx * sc);
-      const float alpha = ex2(m_run - m_new);
-      // fold in the previous tile's P V (also guarantees the PV MMA finished reading sP)
-      if (j > 0) {
+      float mx = -INFINITY;
+      if (full) {
+#pragma unroll
+        for (int i = 0; i < 64; i += 2) mx = max3(mx, __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) mx = (i < kv_left) ? fmaxf(mx, __uint_as_float(sv[i])) : mx;
+      }
+      // exchange partial maxima (scaled domain), rounded up to bf16
+      float mp = mx * sc;
+      uint32_t mb = 0xFF800000u;                               // -inf
+      if (mp > -INFINITY) mb = (__float_as_uint(mp + fabsf(mp) * 0.0079f) & 0xFFFF0000u);
+      xch[half * 128 + row] = static_cast<uint16_t>(mb >> 16);
+      pair_sync();
+      const uint32_t ob = static_cast<uint32_t>(xch[(half ^ 1) * 128 + row]) << 16;
+      const float m_tile = fmaxf(__uint_as_float(mb), __uint_as_float(ob));
+      const bool need = m_tile > m_used + kRescaleThreshold;   // always true on the first tile
+      float alpha = 1.0f;
+      if (need) {
+        alpha = ex2(m_used - m_tile);      // 0 on the first tile
+        m_used = m_tile;
+      }
+      bool o_waited = false;
+      if (j > 0 && __any_sync(0xffffffffu, need)) {
+        // rescale this warp's 32 rows x 32 columns of O (rows that do not need it multiply by 1)
         mbar_wait(o_full, (j - 1) & 1);
         tc_fence_after_sync();
-        fold_output(alpha_prev);
-      }
-      alpha_prev = alpha;
-      m_run = m_new;
-      // ---- pass 2: p = exp2(s*scale - m), row sum, f16 P into swizzled smem
-      uint64_t psum2 = 0ull;
-      const uint64_t sc2 = pack2(sc, sc), nm2 = pack2(-m_new, -m_new);
+        o_waited = true;
+        const uint64_t a2 = pack2(alpha, alpha);
 #pragma unroll 1
-      for (int c = 0; c < AT_BK; c += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_S + lane_addr + c, r);
-        tmem_ld_wait();
-        uint32_t ph[16];
+        for (int c = 0; c < 32; c += 16) {      // 16 columns at a time: the score row is still live
+          uint32_t r[16];
+          tmem_ld_32x32b_x16(tmem_O + lane_addr + half * 32 + c, r);
+          tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float t0, t1;
-          unpack2(fma2(pack2u(r[2 * i], r[2 * i + 1]), sc2, nm2), t0, t1);
-          float e0 = ex2(t0), e1 = ex2(t1);
-          if (!full) {
-            e0 = (c + 2 * i < kv_left) ? e0 : 0.f;
-            e1 = (c + 2 * i + 1 < kv_left) ? e1 : 0.f;
+          for (int i = 0; i < 16; i += 2) {
+            float lo, hi;
+            unpack2(mul2(pack2u(r[i], r[i + 1]), a2), lo, hi);
+            r[i] = __float_as_uint(lo);
+            r[i + 1] = __float_as_uint(hi);
           }
-          psum2 = add2(psum2, pack2(e0, e1));
-          ph[i] = pack_half2(e0, e1);
+          tmem_st_32x32b_x16(tmem_O + lane_addr + half * 32 + c, r);
         }
-        uint8_t* sub = p_row + (c >> 6) * (kPBytes / 2);
-        const int chunk0 = (c & 63) >> 3;          // first 16-byte chunk of this 32-column group
+        tmem_st_wait();
+      }
+      // p = exp2(s*scale - m_used); row sum; f16 P into swizzled smem
+      const uint64_t sc2 = pack2(sc, sc), nm2 = pack2(-m_used, -m_used);
+      uint64_t psum2 = 0ull;
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          *reinterpret_cast<uint4*>(sub + (((chunk0 + q) ^ sw) << 4)) =
-              make_uint4(ph[4 * q], ph[4 * q + 1], ph[4 * q + 2], ph[4 * q + 3]);
+      for (int i = 0; i < 64; i += 2) {
+        float t0, t1;
+        unpack2(fma2(pack2u(sv[i], sv[i + 1]), sc2, nm2), t0, t1);
+        float e0 = ex2(t0), e1 = ex2(t1);
+        if (!full) {
+          e0 = (i < kv_left) ? e0 : 0.f;
+          e1 = (i + 1 < kv_left) ? e1 : 0.f;
+        }
+        psum2 = add2(psum2, pack2(e0, e1));
+        sv[i >> 1] = pack_half2(e0, e1);   // in place: pair i -> word i/2 (already consumed)
       }
       float ps0, ps1;
       unpack2(psum2, ps0, ps1);
       l_run = fmaf(l_run, alpha, ps0 + ps1);
+      // the PV MMA of the previous tile must have finished reading sP before it is overwritten
+      if (j > 0 && !o_waited) {
+        mbar_wait(o_full, (j - 1) & 1);
+        tc_fence_after_sync();
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q)              // 8 chunks of 8 halves (16 B) in this thread's sub-tile row
+        *reinterpret_cast<uint4*>(p_sub + ((q ^ sw) << 4)) =
+            make_uint4(sv[4 * q], sv[4 * q + 1], sv[4 * q + 2], sv[4 * q + 3]);
       fence_proxy_async_smem();
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
     }
-    // last tile's P V
+    // epilogue: O / l ; the two threads of a row add their partial sums through the (now idle) K stage
     mbar_wait(o_full, (n_tiles - 1) & 1);
     tc_fence_after_sync();
-    fold_output(alpha_prev);
+    float* xl = reinterpret_cast<float*>(sK);
+    xl[half * 128 + row] = l_run;
+    pair_sync();
+    const float inv = 1.0f / (l_run + xl[(half ^ 1) * 128 + row]);
     const int q = q0 + row;
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(tmem_O + lane_addr + half * 32, r);
+    tmem_ld_wait();
     if (q < p.seq_q) {
-      const float inv = 1.0f / l_run;
-      __half* op = p.out + ((long long)b * p.seq_q + q) * p.ldo + p.o_col0 + head * HD;
+      __half* op = p.out + ((long long)b * p.seq_q + q) * p.ldo + p.o_col0 + head * HD + half * 32;
 #pragma unroll
-      for (int i = 0; i < HD / 8; ++i) {
-        float v[8];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) unpack2(acc2[4 * i + t], v[2 * t], v[2 * t + 1]);
-        *reinterpret_cast<uint4*>(op + 8 * i) =
-            make_uint4(pack_half2(v[0] * inv, v[1] * inv), pack_half2(v[2] * inv, v[3] * inv),
-                       pack_half2(v[4] * inv, v[5] * inv), pack_half2(v[6] * inv, v[7] * inv));
+      for (int i = 0; i < 32; i += 8) {
+        *reinterpret_cast<uint4*>(op + i) = make_uint4(
+            pack_half2(__uint_as_float(r[i]) * inv, __uint_as_float(r[i + 1]) * inv),
+            pack_half2(__uint_as_float(r[i + 2]) * inv, __uint_as_float(r[i + 3]) * inv),
+            pack_half2(__uint_as_float(r[i + 4]) * inv, __uint_as_float(r[i + 5]) * inv),
+            pack_half2(__uint_as_float(r[i + 6]) * inv, __uint_as_float(r[i + 7]) * inv));
       }
     }
   }
@@ -292,7 +308,7 @@ extern "C" int udb_attention_f16(const udb_attn_t* a, void* stream) {
   p.ldo = a->ldo; p.o_col0 = a->o_col0;
   p.q_col0 = a->q_col0; p.k_col0 = a->k_col0; p.v_col0 = a->v_col0;
   p.scale_log2 = a->scale * 1.4426950408889634f;
-  constexpr int smem_bytes = 16384 + 2 * 16384 + 2 * 16384 + 32768 + 128;
+  constexpr int smem_bytes = 16384 + 2 * 16384 + 2 * 16384 + 32768 + 128 + 512;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);

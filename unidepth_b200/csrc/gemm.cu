@@ -243,7 +243,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
           if (p.act == UDB_ACT_GELU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
+            for (int j = 0; j < 32; j += 2) gelu_erf_pair(v[j], v[j + 1]);
           } else if (p.act == UDB_ACT_LEAKY) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = leaky(v[j]);

@@ -165,6 +165,38 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
       : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]),
+      "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]),
+      "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+
 // Shared-memory matrix descriptor (sm_100 "version 1"), 128-byte swizzle.
 //  K-major operand tile  [rows][64 x 16-bit] : rows are 128 B apart, 8-row groups 1024 B apart.
 //  MN-major operand tile [k rows][64 x 16-bit]: same bytes, the 64 contiguous elements run along
@@ -212,6 +244,11 @@ __device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
   return d;
 }
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
 __device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
   uint64_t d;
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
@@ -244,6 +281,29 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   const float erf_abs = fmaf(-poly, e, 1.0f);          // erf(|x|/sqrt2)
   const float h = 0.5f * x;
   return fmaf(copysignf(erf_abs, x), h, h);            // 0.5 x (1 + erf)
+}
+// Two GELU(erf) at once with packed f32x2 math and ONE MUFU per element: erf from Abramowitz &
+// Stegun 7.1.28, erf(z) = 1 - (1 + a1 z + ... + a6 z^6)^-16, |error| <= 3e-7.
+__device__ __forceinline__ void gelu_erf_pair(float& x0, float& x1) {
+  const float z0 = fabsf(x0) * 0.70710678118654752440f, z1 = fabsf(x1) * 0.70710678118654752440f;
+  const uint64_t z = pack2(z0, z1);
+  uint64_t q = fma2(z, pack2(0.0000430638f, 0.0000430638f), pack2(0.0002765672f, 0.0002765672f));
+  q = fma2(q, z, pack2(0.0001520143f, 0.0001520143f));
+  q = fma2(q, z, pack2(0.0092705272f, 0.0092705272f));
+  q = fma2(q, z, pack2(0.0422820123f, 0.0422820123f));
+  q = fma2(q, z, pack2(0.0705230784f, 0.0705230784f));
+  q = fma2(q, z, pack2(1.0f, 1.0f));
+  q = mul2(q, q);
+  q = mul2(q, q);
+  q = mul2(q, q);
+  q = mul2(q, q);
+  float p0, p1, r0, r1;
+  unpack2(q, p0, p1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(p0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(p1));
+  const float h0 = 0.5f * x0, h1 = 0.5f * x1;
+  x0 = fmaf(copysignf(1.0f - r0, x0), h0, h0);
+  x1 = fmaf(copysignf(1.0f - r1, x1), h1, h1);
 }
 __device__ __forceinline__ float leaky(float x) { return x > 0.f ? x : 0.01f * x; }
 

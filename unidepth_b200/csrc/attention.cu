@@ -50,12 +50,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* q_full = bars;
   uint64_t* k_full = bars + 1;   // [2]
   uint64_t* v_full = bars + 3;   // [2]
-  uint64_t* kv_empty = bars + 5; // [2]
+  uint64_t* k_empty = bars + 5;  // [2]  K stage free once QK_j has completed
+  uint64_t* v_empty = bars + 12; // [2]  V stage free once PV_j has completed
   uint64_t* s_full = bars + 7;
   uint64_t* p_full = bars + 8;
   uint64_t* o_full = bars + 9;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 10);
-  uint16_t* xch = reinterpret_cast<uint16_t*>(bars + 16);   // [2][128] partial row maxima (bf16, rounded up)
+  uint16_t* xch = reinterpret_cast<uint16_t*>(bars + 16);   // bars[0..13] + tmem_ptr at bars[10] used   // [2][128] partial row maxima (bf16, rounded up)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -73,7 +74,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     for (int i = 0; i < 2; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&v_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_empty[i], 1);
     }
     mbar_init(s_full, 1);
     mbar_init(p_full, 8);
@@ -94,9 +96,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tma_load_3d(sQ, &tmQ, q_full, p.q_col0 + head * HD, q0, b);
       for (int j = 0; j < n_tiles; ++j) {
         const int st = j & 1;
-        mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+        // separate K / V rings: K_{j+2} can be fetched as soon as QK_j is done (two tiles ahead of its
+        // use) instead of after PV_j (one tile ahead) -- the K fetch latency was the critical path
+        mbar_wait(&k_empty[st], ((j >> 1) & 1) ^ 1);
         mbar_arrive_expect_tx(&k_full[st], kKBytes);
         tma_load_3d(sK + st * kKBytes, &tmK, &k_full[st], p.k_col0 + head * HD, j * AT_BK, b);
+        mbar_wait(&v_empty[st], ((j >> 1) & 1) ^ 1);
         mbar_arrive_expect_tx(&v_full[st], kKBytes);
         tma_load_3d(sV + st * kKBytes, &tmV, &v_full[st], p.v_col0 + head * HD, j * AT_BK, b);
       }
@@ -113,6 +118,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const uint64_t dk = umma_desc_sw128(smem_u32(sK + st * kKBytes), 16, 1024);
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k) umma_f16_ss(tmem_S, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0);
+        umma_commit(&k_empty[st]);
         umma_commit(s_full);
       };
       mbar_wait(q_full, 0);
@@ -130,7 +136,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           // B = V (MN-major): 16 key rows = 2 KB per step
           umma_f16_ss(tmem_O, dp, dv + (uint64_t)(ks * 2048 >> 4), idesc_pv, (j | ks) != 0);
         }
-        umma_commit(&kv_empty[st]);
+        umma_commit(&v_empty[st]);
         umma_commit(o_full);
         if (j + 1 < n_tiles) issue_qk(j + 1);
       }

@@ -9,6 +9,8 @@
 // NHWC image (4-D tensor map, one (dy,dx,64-channel) slab per k-block; zero padding comes from TMA
 // out-of-bounds fill), so linear layers, 1x1 / 3x3 convolutions and k=s transposed convolutions all
 // run through this one kernel.  See include/udb.h (udb_gemm) for the reference call sites.
+#include <stdlib.h>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -23,7 +25,7 @@ struct GemmArgs {
   int M, N, K, num_kb;
   int tiles_m, tiles_n;
   int a_mode;
-  int conv_H, conv_W, conv_cpb /*64-ch blocks per tap*/, conv_off, conv_TH, conv_TW, conv_tx, conv_ty;
+  int conv_B, conv_H, conv_W, conv_cpb /*64-ch blocks per tap*/, conv_off, conv_TH, conv_TW, conv_tx, conv_ty;
   const float* bias;
   const float* gamma;
   const void* resid;
@@ -55,137 +57,27 @@ struct GemmCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 256 /*barriers*/;
 };
 
+// One accumulator tile (128 rows x BN columns, fp32 in TMEM at `t_acc`) -> global memory.
+// `mt` indexes this CTA's 128-row block (matrix rows mt*128.. or spatial conv tile mt), `nt` the
+// BN-wide column block.  Executed by the 8 epilogue warps; warp (quad, grp) owns TMEM lanes
+// [32*quad, +32) and column half `grp`.
+struct EpiWarp {
+  float* T;              // [32][32] transpose tile, column index XOR row
+  uint32_t* roff_out;    // [32] element offsets of this warp's rows in out / out2
+  uint32_t* roff_res;    // [32] element offsets in resid
+  int quad, grp, lane, r_in_tile;
+};
+
 template <int BN>
-__global__ void __launch_bounds__(kThreads, 1)
-gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const GemmArgs p) {
-  using Cfg = GemmCfg<BN>;
-  constexpr int kStages = Cfg::kStages;
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + kStages * Cfg::kABytes;
-  uint8_t* staging = smem + kStages * Cfg::kStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::kStagingBytes);
-  uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + kStages;
-  uint64_t* tmem_full = bars + 2 * kStages;
-  uint64_t* tmem_empty = bars + 2 * kStages + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-
-  if (warp == 0 && lane == 0) {
-    if (smem_u32(smem) & 1023) __trap();   // 128B-swizzle atoms need a 1024 B aligned base
-    prefetch_tmap(&tmA);
-    prefetch_tmap(&tmB);
-  }
-  if (warp == 1 && lane == 0) {
-    for (int i = 0; i < kStages; ++i) {
-      mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], kEpiWarps);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_ptr);
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_ptr;
-
-  const int num_tiles = p.tiles_m * p.tiles_n;
-
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int mt = tile / p.tiles_n;
-        const int nt = tile % p.tiles_n;
-        int cb = 0, cy = 0, cx = 0;
-        if (p.a_mode == UDB_A_CONV3X3) {
-          const int per_img = p.conv_tx * p.conv_ty;
-          cb = mt / per_img;
-          const int r = mt % per_img;
-          cy = (r / p.conv_tx) * p.conv_TH + p.conv_off;
-          cx = (r % p.conv_tx) * p.conv_TW + p.conv_off;
-        }
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          if (p.a_mode == UDB_A_CONV3X3) {
-            const int tap = kb / p.conv_cpb;
-            const int c0 = (kb % p.conv_cpb) * BK;
-            tma_load_4d(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], c0, cx + tap % 3,
-                        cy + tap / 3, cb);
-          } else {
-            tma_load_2d(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * BK, mt * BM);
-          }
-          tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * BK, nt * BN);
-          if (++stage == kStages) {
-            stage = 0;
-            phase ^= 1;
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(BM, BN, false, false);
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const int as = it & 1;
-        const uint32_t aphase = (it >> 1) & 1;
-        mbar_wait(&tmem_empty[as], aphase ^ 1);
-        tc_fence_after_sync();
-        const uint32_t d_tmem = tmem_base + as * BN;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after_sync();
-          const uint64_t da = umma_desc_sw128(smem_u32(sA + stage * Cfg::kABytes), 16, 1024);
-          const uint64_t db = umma_desc_sw128(smem_u32(sB + stage * Cfg::kBBytes), 16, 1024);
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // advance 16 elements (32 B) along K inside the 128 B swizzle atom: +2 in 16-byte units
-            umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          }
-          umma_commit(&empty_bar[stage]);
-          if (++stage == kStages) {
-            stage = 0;
-            phase ^= 1;
-          }
-        }
-        umma_commit(&tmem_full[as]);
-      }
-    }
-  } else if (warp >= 4) {
-    // ------------------------------------------------------------------ epilogue
-    const int ew = warp - 4;
-    const int quad = warp & 3;            // TMEM lane quadrant this warp may access
-    constexpr int kGroups = BN >= 64 ? 2 : 1;
-    const int grp = ew >> 2;              // column half
-    constexpr int kColsPerGrp = BN / kGroups;
-    const int r_in_tile = quad * 32 + lane;
-    float* T = reinterpret_cast<float*>(staging) + ew * 1024;                       // [32][32], col ^ row
-    uint32_t* roff_out = reinterpret_cast<uint32_t*>(staging + kEpiWarps * 4096) + ew * 64;
-    uint32_t* roff_res = roff_out + 32;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int as = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
-      const int mt = tile / p.tiles_n;
-      const int nt = tile % p.tiles_n;
-      mbar_wait(&tmem_full[as], aphase);
-      tc_fence_after_sync();
-      if (grp < kGroups) {
+__device__ __forceinline__ void epilogue_tile(const GemmArgs& p, const EpiWarp& w, const uint32_t t_acc,
+                                              const int mt, const int nt) {
+  constexpr int kGroups = BN >= 64 ? 2 : 1;
+  constexpr int kColsPerGrp = BN / kGroups;
+  const int grp = w.grp, quad = w.quad, lane = w.lane, r_in_tile = w.r_in_tile;
+  float* T = w.T;
+  uint32_t* roff_out = w.roff_out;
+  uint32_t* roff_res = w.roff_res;
+  if (grp < kGroups) {
         // ---- per-row addressing
         bool valid;
         long long out_off = 0, res_off = 0;
@@ -196,7 +88,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const int r = mt % per_img;
           const int y = (r / p.conv_tx) * p.conv_TH + r_in_tile / p.conv_TW;
           const int x = (r % p.conv_tx) * p.conv_TW + r_in_tile % p.conv_TW;
-          valid = (y < p.conv_H) && (x < p.conv_W);
+          valid = (b < p.conv_B) && (y < p.conv_H) && (x < p.conv_W);
           out_off = (((long long)b * p.conv_H + y) * p.conv_W + x) * p.ldc;
           res_off = (((long long)b * p.conv_H + y) * p.conv_W + x) * p.ldr;
         } else if (p.store_mode == UDB_STORE_CONVT) {
@@ -221,7 +113,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         roff_out[lane] = static_cast<uint32_t>(out_off);
         roff_res[lane] = static_cast<uint32_t>(res_off);
         __syncwarp();
-        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
+        const uint32_t t_row = t_acc + (static_cast<uint32_t>(quad * 32) << 16);
 #pragma unroll 1
         for (int c = 0; c < kColsPerGrp; c += 32) {
           const int col = grp * kColsPerGrp + c;   // column inside the tile
@@ -352,6 +244,138 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
         }
       }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const GemmArgs p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kStages * Cfg::kABytes;
+  uint8_t* staging = smem + kStages * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::kStagingBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kStages;
+  uint64_t* tmem_full = bars + 2 * kStages;
+  uint64_t* tmem_empty = bars + 2 * kStages + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    if (smem_u32(smem) & 1023) __trap();   // 128B-swizzle atoms need a 1024 B aligned base
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], kEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_ptr);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int num_tiles = p.tiles_m * p.tiles_n;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int mt = tile / p.tiles_n;
+        const int nt = tile % p.tiles_n;
+        int cb = 0, cy = 0, cx = 0;
+        if (p.a_mode == UDB_A_CONV3X3) {
+          const int per_img = p.conv_tx * p.conv_ty;
+          cb = mt / per_img;
+          const int r = mt % per_img;
+          cy = (r / p.conv_tx) * p.conv_TH + p.conv_off;
+          cx = (r % p.conv_tx) * p.conv_TW + p.conv_off;
+        }
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          if (p.a_mode == UDB_A_CONV3X3) {
+            const int tap = kb / p.conv_cpb;
+            const int c0 = (kb % p.conv_cpb) * BK;
+            tma_load_4d(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], c0, cx + tap % 3,
+                        cy + tap / 3, cb);
+          } else {
+            tma_load_2d(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * BK, mt * BM);
+          }
+          tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * BK, nt * BN);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(BM, BN, false, false);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[as], aphase ^ 1);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          const uint64_t da = umma_desc_sw128(smem_u32(sA + stage * Cfg::kABytes), 16, 1024);
+          const uint64_t db = umma_desc_sw128(smem_u32(sB + stage * Cfg::kBBytes), 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 elements (32 B) along K inside the 128 B swizzle atom: +2 in 16-byte units
+            umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[as]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue
+    const int ew = warp - 4;
+    const int quad = warp & 3;            // TMEM lane quadrant this warp may access
+    const int grp = ew >> 2;              // column half
+    const int r_in_tile = quad * 32 + lane;
+    float* T = reinterpret_cast<float*>(staging) + ew * 1024;                       // [32][32], col ^ row
+    uint32_t* roff_out = reinterpret_cast<uint32_t*>(staging + kEpiWarps * 4096) + ew * 64;
+    uint32_t* roff_res = roff_out + 32;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int mt = tile / p.tiles_n;
+      const int nt = tile % p.tiles_n;
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after_sync();
+      EpiWarp ew_ctx{T, roff_out, roff_res, quad, grp, lane, r_in_tile};
+      epilogue_tile<BN>(p, ew_ctx, tmem_base + as * BN, mt, nt);
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[as]);
@@ -383,6 +407,207 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   const int grid = tiles < num_sms() ? tiles : num_sms();
   gemm_f16_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, a);
   return check_launch("gemm_f16_kernel");
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2): a cluster of two CTAs computes a 256 x BN tile.  Each CTA
+// loads its own 128 rows of A and BN/2 rows of W per k-block (so per-SM operand traffic drops to
+// 16 KB + BN*64 B per 64-deep step and the ring holds 6 stages instead of 4), the leader issues
+// M=256 MMAs for both, each CTA drains its own 128 accumulator rows from its own TMEM.
+// ---------------------------------------------------------------------------------------------
+template <int BN>
+struct Gemm2Cfg {
+  static constexpr int kStages = 6;
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = (BN / 2) * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kStagingBytes = kEpiWarps * (32 * 32 * 4 + 2 * 32 * 4);
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const GemmArgs p) {
+  using Cfg = Gemm2Cfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kStages * Cfg::kABytes;
+  uint8_t* staging = smem + kStages * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::kStagingBytes);
+  uint64_t* full_bar = bars;                    // leader's copies are the live ones (count 2)
+  uint64_t* empty_bar = bars + kStages;         // per CTA, arrived by the multicast commit
+  uint64_t* tmem_full = bars + 2 * kStages;     // per CTA, multicast commit
+  uint64_t* tmem_empty = bars + 2 * kStages + 2;  // leader's copies: 2 x kEpiWarps arrivals
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    if (smem_u32(smem) & 1023) __trap();
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 2);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 2 * kEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_2cta<Cfg::kTmemCols>(tmem_ptr);
+  tc_fence_before_sync();
+  cluster_sync_all();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int tiles_m2 = (p.tiles_m + 1) >> 1;       // 256-row (two 128-row blocks) tiles
+  const int num_tiles = tiles_m2 * p.tiles_n;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int mt = 2 * (tile / p.tiles_n) + (int)rank;   // this CTA's 128-row block
+        const int nt = tile % p.tiles_n;
+        int cb = 0, cy = 0, cx = 0;
+        if (p.a_mode == UDB_A_CONV3X3) {
+          const int per_img = p.conv_tx * p.conv_ty;
+          cb = mt / per_img;                                   // may be == conv_B: fully out of bounds -> zeros
+          const int r = mt % per_img;
+          cy = (r / p.conv_tx) * p.conv_TH + p.conv_off;
+          cx = (r % p.conv_tx) * p.conv_TW + p.conv_off;
+        }
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+          else mbar_arrive_remote(&full_bar[stage], 0);
+          if (p.a_mode == UDB_A_CONV3X3) {
+            const int tap = kb / p.conv_cpb;
+            const int c0 = (kb % p.conv_cpb) * BK;
+            tma_load_4d_2sm(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], c0, cx + tap % 3, cy + tap / 3, cb);
+          } else {
+            tma_load_2d_2sm(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * BK, mt * BM);
+          }
+          tma_load_2d_2sm(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * BK, nt * BN + (int)rank * (BN / 2));
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(2 * BM, BN, false, false);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[as], aphase ^ 1);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          const uint64_t da = umma_desc_sw128(smem_u32(sA + stage * Cfg::kABytes), 16, 1024);
+          const uint64_t db = umma_desc_sw128(smem_u32(sB + stage * Cfg::kBBytes), 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_f16_ss_2cta(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_2cta(&empty_bar[stage]);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_2cta(&tmem_full[as]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue (both CTAs)
+    const int ew = warp - 4;
+    EpiWarp ctx{reinterpret_cast<float*>(staging) + ew * 1024,
+                reinterpret_cast<uint32_t*>(staging + kEpiWarps * 4096) + ew * 64,
+                reinterpret_cast<uint32_t*>(staging + kEpiWarps * 4096) + ew * 64 + 32,
+                warp & 3, ew >> 2, lane, (warp & 3) * 32 + lane};
+    int it = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int mt = 2 * (tile / p.tiles_n) + (int)rank;
+      const int nt = tile % p.tiles_n;
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after_sync();
+      epilogue_tile<BN>(p, ctx, tmem_base + as * BN, mt, nt);
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(&tmem_empty[as]);
+        else mbar_arrive_remote(&tmem_empty[as], 0);
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after_sync();
+    tmem_dealloc_2cta<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+template <int BN>
+static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, cudaStream_t st) {
+  using Cfg = Gemm2Cfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm2_f16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes);
+    if (e != cudaSuccess) {
+      set_error("gemm2: cudaFuncSetAttribute(%d B smem): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
+      return 1;
+    }
+    attr_set = true;
+  }
+  const int tiles = ((a.tiles_m + 1) / 2) * a.tiles_n;
+  const int max_pairs = num_sms() / 2;
+  const int pairs = tiles < max_pairs ? tiles : max_pairs;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm2_f16_kernel<BN>, tmA, tmB, a);
+  if (e != cudaSuccess) {
+    set_error("gemm2_f16_kernel launch: %s", cudaGetErrorString(e));
+    return 1;
+  }
+  return check_launch("gemm2_f16_kernel");
 }
 
 }  // namespace udb
@@ -417,6 +642,12 @@ extern "C" int udb_gemm_f16(const udb_gemm_t* g, void* stream) {
     set_error("udb_gemm_f16: CONVT needs Cout %% 32 == 0"); return 1;
   }
   a.tiles_n = (g->N + bn - 1) / bn;
+  // CTA-pair kernel (cta_group::2) for the wide tiles; UDB_GEMM_PAIR=0 forces the single-CTA kernel
+  static const int pair_env = [] {
+    const char* e = getenv("UDB_GEMM_PAIR");
+    return e ? atoi(e) : 1;
+  }();
+  const bool use_pair = pair_env != 0 && (bn == 256 || bn == 128);
 
   CUtensorMap tmA, tmB;
   if (g->a_mode == UDB_A_CONV3X3) {
@@ -429,7 +660,7 @@ extern "C" int udb_gemm_f16(const udb_gemm_t* g, void* stream) {
     }
     const int TH = g->conv_TH > 0 ? g->conv_TH : 8, TW = g->conv_TW > 0 ? g->conv_TW : 16;
     if (TH * TW != BM) { set_error("udb_gemm_f16: conv tile %dx%d != 128 pixels", TH, TW); return 1; }
-    a.conv_H = g->conv_H; a.conv_W = g->conv_W; a.conv_cpb = g->conv_C / BK; a.conv_off = g->conv_off;
+    a.conv_B = g->conv_B; a.conv_H = g->conv_H; a.conv_W = g->conv_W; a.conv_cpb = g->conv_C / BK; a.conv_off = g->conv_off;
     a.conv_TH = TH; a.conv_TW = TW;
     a.conv_tx = (g->conv_W + TW - 1) / TW; a.conv_ty = (g->conv_H + TH - 1) / TH;
     a.tiles_m = g->conv_B * a.conv_tx * a.conv_ty;
@@ -452,10 +683,13 @@ extern "C" int udb_gemm_f16(const udb_gemm_t* g, void* stream) {
   {
     const uint64_t dims[2] = {(uint64_t)g->K, (uint64_t)g->N};
     const uint64_t str[1] = {(uint64_t)g->ldw * 2};
-    const uint32_t box[2] = {(uint32_t)BK, (uint32_t)bn};
+    const uint32_t box[2] = {(uint32_t)BK, (uint32_t)(use_pair ? bn / 2 : bn)};
     if (make_tmap_f16(&tmB, g->w, 2, dims, str, box, true)) return 1;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (use_pair) {
+    return bn == 256 ? launch_gemm2<256>(tmA, tmB, a, st) : launch_gemm2<128>(tmA, tmB, a, st);
+  }
   switch (bn) {
     case 256: return launch_gemm<256>(tmA, tmB, a, st);
     case 128: return launch_gemm<128>(tmA, tmB, a, st);

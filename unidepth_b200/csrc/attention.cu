@@ -1,12 +1,16 @@
 // Fused attention forward for sm_100a:  O = softmax(Q K^T * scale) V   (no mask, no dropout)
 //
 // One CTA = one (batch, head, 128-query tile); two CTAs are resident per SM (TMEM 2 x 256 columns,
-// <= 113 KB shared memory each) so one CTA's softmax overlaps the other's tensor-core work.
-//   warp 0      : TMA producer (Q once; K_j / V_j tiles of 128 keys through a 2-stage ring)
-//   warp 1      : TMEM allocator + MMA issuer (S = Q K_j^T : M128 N128 K64 ;  O_j = P_j V_j : M128 N64 K128)
-//   warps 2..9  : softmax, two threads per query row (64 keys each): S from TMEM (tcgen05.ld), max /
-//                 sum in fp32, P_j written as f16 into 128B-swizzled shared memory for the PV MMA.
-//                 O stays in TMEM, accumulated by the PV MMAs, and is rescaled lazily.
+// <= 113 KB shared memory each).  Keys are processed in tiles of 64:
+//   warp 0      : TMA producer (Q once; K_j / V_j tiles through two independent 4-stage rings)
+//   warp 1      : TMEM allocator + MMA issuer.  S_j = Q K_j^T (M128 N64 K64) goes to one of TWO score
+//                 buffers in TMEM and is issued two tiles ahead, so the scores of tile j+1 are ready
+//                 while the softmax warps are still busy with tile j; O += P_j V_j (M128 N64 K64, V is
+//                 the MN-major B operand) accumulates in TMEM.
+//   warps 2..5  : softmax, one query row per thread: S_j from TMEM (tcgen05.ld), row max / sum in fp32
+//                 with packed f32x2 math, P_j as f16 into one of two 128B-swizzled smem buffers.
+//                 O is rescaled lazily: only when a row maximum grows by more than 2^8 over the
+//                 reference the probabilities are expressed against (tcgen05.ld -> mul -> tcgen05.st).
 // Replaces F.scaled_dot_product_attention (reference: metadinov2/attention.py:58,
 // layers/attention.py:136).
 #include "common.h"
@@ -14,9 +18,10 @@
 
 namespace udb {
 
-constexpr int AT_BQ = 128;   // queries per CTA
-constexpr int AT_BK = 128;   // keys per tile
-constexpr int AT_THREADS = 320;   // TMA warp, MMA warp, 8 softmax warps
+constexpr int AT_BQ = 128;       // queries per CTA
+constexpr int AT_BK = 64;        // keys per tile
+constexpr int AT_KV_STAGES = 4;  // per ring
+constexpr int AT_THREADS = 192;  // TMA warp, MMA warp, 4 softmax warps
 
 struct AttnArgs {
   __half* out;
@@ -32,31 +37,71 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+// exp2(s*scale - m) for 64 scores of one row; returns the row sum; P (f16) packed in place into
+// sv[0..31].  MASK: only the first kv_left entries are valid keys (last tile).
+template <bool MASK>
+__device__ __forceinline__ float softmax_row(uint32_t (&sv)[AT_BK], const float sc, const float m_used,
+                                             const int kv_left) {
+  const uint64_t sc2 = pack2(sc, sc), nm2 = pack2(-m_used, -m_used);
+  uint64_t psum2 = 0ull;
+#pragma unroll
+  for (int i = 0; i < AT_BK; i += 2) {
+    float t0, t1;
+    unpack2(fma2(pack2u(sv[i], sv[i + 1]), sc2, nm2), t0, t1);
+    float e0 = ex2(t0), e1 = ex2(t1);
+    if (MASK) {
+      e0 = (i < kv_left) ? e0 : 0.f;
+      e1 = (i + 1 < kv_left) ? e1 : 0.f;
+    }
+    psum2 = add2(psum2, pack2(e0, e1));
+    sv[i >> 1] = pack_half2(e0, e1);   // pair i -> word i/2 (already consumed)
+  }
+  float ps0, ps1;
+  unpack2(psum2, ps0, ps1);
+  return ps0 + ps1;
+}
+
+template <bool MASK>
+__device__ __forceinline__ float row_max(const uint32_t (&sv)[AT_BK], const int kv_left) {
+  float m0 = -INFINITY, m1 = -INFINITY;    // two chains for ILP
+  if (!MASK) {
+#pragma unroll
+    for (int i = 0; i < AT_BK; i += 4) {
+      m0 = max3(m0, __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]));
+      m1 = max3(m1, __uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3]));
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < AT_BK; ++i) m0 = (i < kv_left) ? fmaxf(m0, __uint_as_float(sv[i])) : m0;
+  }
+  return fmaxf(m0, m1);
+}
+
 template <int HD>
 __global__ void __launch_bounds__(AT_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnArgs p) {
   static_assert(HD == 64, "head_dim 64 only");
   constexpr int kQBytes = AT_BQ * HD * 2;      // 16 KB
-  constexpr int kKBytes = AT_BK * HD * 2;      // 16 KB
-  constexpr int kPBytes = AT_BQ * AT_BK * 2;   // 32 KB (two 64-key sub-tiles of 16 KB)
-  constexpr uint32_t kTmemCols = 256;          // S: [0,128)  O: [128,192)
+  constexpr int kKBytes = AT_BK * HD * 2;      // 8 KB
+  constexpr int kPBytes = AT_BQ * AT_BK * 2;   // 16 KB per buffer
+  constexpr uint32_t kTmemCols = 256;          // S0: [0,64)  S1: [64,128)  O: [128,192)
+  constexpr int NS = AT_KV_STAGES;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
-  uint8_t* sK = sQ + kQBytes;                  // 2 stages
-  uint8_t* sV = sK + 2 * kKBytes;              // 2 stages
-  uint8_t* sP = sV + 2 * kKBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + kPBytes);
+  uint8_t* sK = sQ + kQBytes;                  // NS stages
+  uint8_t* sV = sK + NS * kKBytes;             // NS stages
+  uint8_t* sP = sV + NS * kKBytes;             // 2 buffers
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kPBytes);
   uint64_t* q_full = bars;
-  uint64_t* k_full = bars + 1;   // [2]
-  uint64_t* v_full = bars + 3;   // [2]
-  uint64_t* k_empty = bars + 5;  // [2]  K stage free once QK_j has completed
-  uint64_t* v_empty = bars + 12; // [2]  V stage free once PV_j has completed
-  uint64_t* s_full = bars + 7;
-  uint64_t* p_full = bars + 8;
-  uint64_t* o_full = bars + 9;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 10);
-  uint16_t* xch = reinterpret_cast<uint16_t*>(bars + 16);   // bars[0..13] + tmem_ptr at bars[10] used   // [2][128] partial row maxima (bf16, rounded up)
+  uint64_t* k_full = bars + 1;             // [NS]
+  uint64_t* v_full = k_full + NS;          // [NS]
+  uint64_t* k_empty = v_full + NS;         // [NS]  K stage free once its QK MMA has completed
+  uint64_t* v_empty = k_empty + NS;        // [NS]  V stage free once its PV MMA has completed
+  uint64_t* s_full = v_empty + NS;         // [2]
+  uint64_t* p_full = s_full + 2;           // [2]
+  uint64_t* p_free = p_full + 2;           // [2]  PV MMA of the tile that used P buffer / parity slot done
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(p_free + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -71,15 +116,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     prefetch_tmap(&tmK);
     prefetch_tmap(&tmV);
     mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NS; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&v_full[i], 1);
       mbar_init(&k_empty[i], 1);
       mbar_init(&v_empty[i], 1);
     }
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 8);
-    mbar_init(o_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&p_free[i], 1);
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<kTmemCols>(tmem_ptr);
@@ -87,7 +134,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
-  const uint32_t tmem_S = tmem_base;
   const uint32_t tmem_O = tmem_base + 128;
 
   if (warp == 0) {
@@ -95,13 +141,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_arrive_expect_tx(q_full, kQBytes);
       tma_load_3d(sQ, &tmQ, q_full, p.q_col0 + head * HD, q0, b);
       for (int j = 0; j < n_tiles; ++j) {
-        const int st = j & 1;
-        // separate K / V rings: K_{j+2} can be fetched as soon as QK_j is done (two tiles ahead of its
-        // use) instead of after PV_j (one tile ahead) -- the K fetch latency was the critical path
-        mbar_wait(&k_empty[st], ((j >> 1) & 1) ^ 1);
+        const int st = j % NS;
+        const uint32_t ph = ((j / NS) & 1) ^ 1;
+        mbar_wait(&k_empty[st], ph);
         mbar_arrive_expect_tx(&k_full[st], kKBytes);
         tma_load_3d(sK + st * kKBytes, &tmK, &k_full[st], p.k_col0 + head * HD, j * AT_BK, b);
-        mbar_wait(&v_empty[st], ((j >> 1) & 1) ^ 1);
+        mbar_wait(&v_empty[st], ph);
         mbar_arrive_expect_tx(&v_full[st], kKBytes);
         tma_load_3d(sV + st * kKBytes, &tmV, &v_full[st], p.v_col0 + head * HD, j * AT_BK, b);
       }
@@ -111,102 +156,79 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       constexpr uint32_t idesc_qk = umma_idesc_f16(AT_BQ, AT_BK, false, false);
       constexpr uint32_t idesc_pv = umma_idesc_f16(AT_BQ, HD, false, true);   // B = V is MN-major
       const uint64_t dq = umma_desc_sw128(smem_u32(sQ), 16, 1024);
-      auto issue_qk = [&](int j) {
-        const int st = j & 1;
-        mbar_wait(&k_full[st], (j >> 1) & 1);
+      auto issue_qk = [&](int j) {   // S[j&1] = Q K_j^T
+        const int st = j % NS;
+        mbar_wait(&k_full[st], (j / NS) & 1);
         tc_fence_after_sync();
         const uint64_t dk = umma_desc_sw128(smem_u32(sK + st * kKBytes), 16, 1024);
+        const uint32_t d = tmem_base + (j & 1) * AT_BK;
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k) umma_f16_ss(tmem_S, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0);
+        for (int k = 0; k < HD / 16; ++k) umma_f16_ss(d, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0);
         umma_commit(&k_empty[st]);
-        umma_commit(s_full);
+        umma_commit(&s_full[j & 1]);
       };
       mbar_wait(q_full, 0);
       issue_qk(0);
+      if (n_tiles > 1) issue_qk(1);
       for (int j = 0; j < n_tiles; ++j) {
-        const int st = j & 1;
-        mbar_wait(p_full, j & 1);
-        mbar_wait(&v_full[st], (j >> 1) & 1);
+        const int st = j % NS;
+        mbar_wait(&p_full[j & 1], (j >> 1) & 1);   // P_j written; S[j&1] fully consumed
+        mbar_wait(&v_full[st], (j / NS) & 1);
         tc_fence_after_sync();
+        const uint64_t dp = umma_desc_sw128(smem_u32(sP + (j & 1) * kPBytes), 16, 1024);
         const uint64_t dv = umma_desc_sw128(smem_u32(sV + st * kKBytes), 1024, 1024);
 #pragma unroll
-        for (int ks = 0; ks < AT_BK / 16; ++ks) {
-          // A = P: sub-tile (ks/4) of 16 KB, 32 B per 16-key step inside the swizzle atom
-          const uint64_t dp = umma_desc_sw128(smem_u32(sP + (ks >> 2) * (kPBytes / 2)), 16, 1024) + 2 * (ks & 3);
-          // B = V (MN-major): 16 key rows = 2 KB per step
-          umma_f16_ss(tmem_O, dp, dv + (uint64_t)(ks * 2048 >> 4), idesc_pv, (j | ks) != 0);
-        }
+        for (int ks = 0; ks < AT_BK / 16; ++ks)   // A = P: 32 B per 16-key step; B = V: 16 key rows = 2 KB per step
+          umma_f16_ss(tmem_O, dp + 2 * ks, dv + (uint64_t)(ks * 2048 >> 4), idesc_pv, (j | ks) != 0);
         umma_commit(&v_empty[st]);
-        umma_commit(o_full);
-        if (j + 1 < n_tiles) issue_qk(j + 1);
+        umma_commit(&p_free[j & 1]);
+        if (j + 2 < n_tiles) issue_qk(j + 2);
       }
     }
   } else {
     // ------------------------------------------------------------------ softmax warps
-    // Two threads per query row: warp (2 + quad') handles keys [0,64) of 32 rows, warp (6 + quad')
-    // keys [64,128) of the same rows.  The partial row maxima are exchanged through shared memory
-    // as bf16 values rounded UP (any common upper bound is a valid softmax reference point), so both
-    // threads derive the identical reference maximum.  O stays in TMEM, accumulated by the PV MMAs;
-    // it is rescaled (tcgen05.ld -> mul -> tcgen05.st) only when a row maximum grows by more than
-    // 2^8 over the current reference ("lazy rescale"), so probabilities are bounded by 2^8 (fine
-    // for f16) and the final O / l is exact because both use the same reference.
     const int quad = warp & 3;                  // TMEM lane quadrant of this warp
-    const int half = (warp - 2) >> 2;           // which 64 keys of the tile
     const int row = quad * 32 + lane;           // query row inside the tile == TMEM lane
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
     float m_used = -INFINITY, l_run = 0.f;
-    uint8_t* p_sub = sP + half * (kPBytes / 2) + row * 128;
     const int sw = row & 7;
     const float sc = p.scale_log2;
     constexpr float kRescaleThreshold = 8.0f;   // log2 domain
-    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory"); };
 
     for (int j = 0; j < n_tiles; ++j) {
-      mbar_wait(s_full, j & 1);
+      const int sb = j & 1;
+      mbar_wait(&s_full[sb], (j >> 1) & 1);
       tc_fence_after_sync();
-      const int kv_left = p.seq_k - j * AT_BK - half * 64;   // valid keys in this thread's 64 (may be <= 0)
-      const bool full = kv_left >= 64;
-      uint32_t sv[64];
+      const int kv_left = p.seq_k - j * AT_BK;   // valid keys in this tile (>= 1)
+      const bool full = kv_left >= AT_BK;
+      uint32_t sv[AT_BK];
       {
         uint32_t(&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[0]);
         uint32_t(&s1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[32]);
-        tmem_ld_32x32b_x32(tmem_S + lane_addr + half * 64, s0);
-        tmem_ld_32x32b_x32(tmem_S + lane_addr + half * 64 + 32, s1);
+        tmem_ld_32x32b_x32(tmem_base + lane_addr + sb * AT_BK, s0);
+        tmem_ld_32x32b_x32(tmem_base + lane_addr + sb * AT_BK + 32, s1);
         tmem_ld_wait();
       }
-      float mx = -INFINITY;
-      if (full) {
-#pragma unroll
-        for (int i = 0; i < 64; i += 2) mx = max3(mx, __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]));
-      } else {
-#pragma unroll
-        for (int i = 0; i < 64; ++i) mx = (i < kv_left) ? fmaxf(mx, __uint_as_float(sv[i])) : mx;
-      }
-      // exchange partial maxima (scaled domain), rounded up to bf16
-      float mp = mx * sc;
-      uint32_t mb = 0xFF800000u;                               // -inf
-      if (mp > -INFINITY) mb = (__float_as_uint(mp + fabsf(mp) * 0.0079f) & 0xFFFF0000u);
-      xch[half * 128 + row] = static_cast<uint16_t>(mb >> 16);
-      pair_sync();
-      const uint32_t ob = static_cast<uint32_t>(xch[(half ^ 1) * 128 + row]) << 16;
-      const float m_tile = fmaxf(__uint_as_float(mb), __uint_as_float(ob));
+      const float m_tile = (full ? row_max<false>(sv, kv_left) : row_max<true>(sv, kv_left)) * sc;
       const bool need = m_tile > m_used + kRescaleThreshold;   // always true on the first tile
       float alpha = 1.0f;
       if (need) {
         alpha = ex2(m_used - m_tile);      // 0 on the first tile
         m_used = m_tile;
       }
-      bool o_waited = false;
+      // P buffer sb was last read by the PV MMA of tile j-2 = phase (j>>1)-1 of p_free[sb]; the next
+      // completion of that barrier (tile j) needs this thread's own arrival, so the parity is unambiguous
+      if (j >= 2) mbar_wait(&p_free[sb], ((j >> 1) & 1) ^ 1);
       if (j > 0 && __any_sync(0xffffffffu, need)) {
-        // rescale this warp's 32 rows x 32 columns of O (rows that do not need it multiply by 1)
-        mbar_wait(o_full, (j - 1) & 1);
+        // rare: rescale this warp's 32 rows of O (rows that do not need it multiply by 1);
+        // needs every PV MMA issued so far (tile j-1 is the latest) to have completed
+        mbar_wait(&p_free[(j - 1) & 1], ((j - 1) >> 1) & 1);
         tc_fence_after_sync();
-        o_waited = true;
         const uint64_t a2 = pack2(alpha, alpha);
 #pragma unroll 1
-        for (int c = 0; c < 32; c += 16) {      // 16 columns at a time: the score row is still live
+        for (int c = 0; c < HD; c += 16) {
           uint32_t r[16];
-          tmem_ld_32x32b_x16(tmem_O + lane_addr + half * 32 + c, r);
+          tmem_ld_32x32b_x16(tmem_O + lane_addr + c, r);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 16; i += 2) {
@@ -215,62 +237,42 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             r[i] = __float_as_uint(lo);
             r[i + 1] = __float_as_uint(hi);
           }
-          tmem_st_32x32b_x16(tmem_O + lane_addr + half * 32 + c, r);
+          tmem_st_32x32b_x16(tmem_O + lane_addr + c, r);
         }
         tmem_st_wait();
       }
-      // p = exp2(s*scale - m_used); row sum; f16 P into swizzled smem
-      const uint64_t sc2 = pack2(sc, sc), nm2 = pack2(-m_used, -m_used);
-      uint64_t psum2 = 0ull;
+      const float psum = full ? softmax_row<false>(sv, sc, m_used, kv_left) : softmax_row<true>(sv, sc, m_used, kv_left);
+      l_run = fmaf(l_run, alpha, psum);
+      uint8_t* p_row = sP + sb * kPBytes + row * 128;
 #pragma unroll
-      for (int i = 0; i < 64; i += 2) {
-        float t0, t1;
-        unpack2(fma2(pack2u(sv[i], sv[i + 1]), sc2, nm2), t0, t1);
-        float e0 = ex2(t0), e1 = ex2(t1);
-        if (!full) {
-          e0 = (i < kv_left) ? e0 : 0.f;
-          e1 = (i + 1 < kv_left) ? e1 : 0.f;
-        }
-        psum2 = add2(psum2, pack2(e0, e1));
-        sv[i >> 1] = pack_half2(e0, e1);   // in place: pair i -> word i/2 (already consumed)
-      }
-      float ps0, ps1;
-      unpack2(psum2, ps0, ps1);
-      l_run = fmaf(l_run, alpha, ps0 + ps1);
-      // the PV MMA of the previous tile must have finished reading sP before it is overwritten
-      if (j > 0 && !o_waited) {
-        mbar_wait(o_full, (j - 1) & 1);
-        tc_fence_after_sync();
-      }
-#pragma unroll
-      for (int q = 0; q < 8; ++q)              // 8 chunks of 8 halves (16 B) in this thread's sub-tile row
-        *reinterpret_cast<uint4*>(p_sub + ((q ^ sw) << 4)) =
+      for (int q = 0; q < 8; ++q)              // 8 chunks of 8 halves (16 B)
+        *reinterpret_cast<uint4*>(p_row + ((q ^ sw) << 4)) =
             make_uint4(sv[4 * q], sv[4 * q + 1], sv[4 * q + 2], sv[4 * q + 3]);
       fence_proxy_async_smem();
       tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
+      if (lane == 0) mbar_arrive(&p_full[sb]);
     }
-    // epilogue: O / l ; the two threads of a row add their partial sums through the (now idle) K stage
-    mbar_wait(o_full, (n_tiles - 1) & 1);
+    // epilogue: O / l
+    mbar_wait(&p_free[(n_tiles - 1) & 1], ((n_tiles - 1) >> 1) & 1);   // last PV done => all done
     tc_fence_after_sync();
-    float* xl = reinterpret_cast<float*>(sK);
-    xl[half * 128 + row] = l_run;
-    pair_sync();
-    const float inv = 1.0f / (l_run + xl[(half ^ 1) * 128 + row]);
+    const float inv = 1.0f / l_run;
     const int q = q0 + row;
-    uint32_t r[32];
-    tmem_ld_32x32b_x32(tmem_O + lane_addr + half * 32, r);
-    tmem_ld_wait();
-    if (q < p.seq_q) {
-      __half* op = p.out + ((long long)b * p.seq_q + q) * p.ldo + p.o_col0 + head * HD + half * 32;
+    __half* op = p.out + ((long long)b * p.seq_q + (q < p.seq_q ? q : 0)) * p.ldo + p.o_col0 + head * HD;
 #pragma unroll
-      for (int i = 0; i < 32; i += 8) {
-        *reinterpret_cast<uint4*>(op + i) = make_uint4(
-            pack_half2(__uint_as_float(r[i]) * inv, __uint_as_float(r[i + 1]) * inv),
-            pack_half2(__uint_as_float(r[i + 2]) * inv, __uint_as_float(r[i + 3]) * inv),
-            pack_half2(__uint_as_float(r[i + 4]) * inv, __uint_as_float(r[i + 5]) * inv),
-            pack_half2(__uint_as_float(r[i + 6]) * inv, __uint_as_float(r[i + 7]) * inv));
+    for (int c = 0; c < HD; c += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tmem_O + lane_addr + c, r);
+      tmem_ld_wait();
+      if (q < p.seq_q) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          *reinterpret_cast<uint4*>(op + c + i) = make_uint4(
+              pack_half2(__uint_as_float(r[i]) * inv, __uint_as_float(r[i + 1]) * inv),
+              pack_half2(__uint_as_float(r[i + 2]) * inv, __uint_as_float(r[i + 3]) * inv),
+              pack_half2(__uint_as_float(r[i + 4]) * inv, __uint_as_float(r[i + 5]) * inv),
+              pack_half2(__uint_as_float(r[i + 6]) * inv, __uint_as_float(r[i + 7]) * inv));
+        }
       }
     }
   }
@@ -291,21 +293,22 @@ extern "C" int udb_attention_f16(const udb_attn_t* a, void* stream) {
   if ((a->ldq | a->ldk | a->ldv | a->ldo) % 8) { set_error("udb_attention_f16: leading dims must be multiples of 8"); return 1; }
   constexpr int HD = 64;
   CUtensorMap tq, tk, tv;
-  const uint32_t box[3] = {HD, 128, 1};
+  const uint32_t box_q[3] = {HD, AT_BQ, 1};
+  const uint32_t box_kv[3] = {HD, AT_BK, 1};
   {
     const uint64_t dims[3] = {(uint64_t)a->ldq, (uint64_t)a->seq_q, (uint64_t)a->B};
     const uint64_t str[2] = {(uint64_t)a->ldq * 2, (uint64_t)a->seq_q * a->ldq * 2};
-    if (make_tmap_f16(&tq, a->q, 3, dims, str, box, true)) return 1;
+    if (make_tmap_f16(&tq, a->q, 3, dims, str, box_q, true)) return 1;
   }
   {
     const uint64_t dims[3] = {(uint64_t)a->ldk, (uint64_t)a->seq_k, (uint64_t)a->B};
     const uint64_t str[2] = {(uint64_t)a->ldk * 2, (uint64_t)a->seq_k * a->ldk * 2};
-    if (make_tmap_f16(&tk, a->k, 3, dims, str, box, true)) return 1;
+    if (make_tmap_f16(&tk, a->k, 3, dims, str, box_kv, true)) return 1;
   }
   {
     const uint64_t dims[3] = {(uint64_t)a->ldv, (uint64_t)a->seq_k, (uint64_t)a->B};
     const uint64_t str[2] = {(uint64_t)a->ldv * 2, (uint64_t)a->seq_k * a->ldv * 2};
-    if (make_tmap_f16(&tv, a->v, 3, dims, str, box, true)) return 1;
+    if (make_tmap_f16(&tv, a->v, 3, dims, str, box_kv, true)) return 1;
   }
   AttnArgs p{};
   p.out = reinterpret_cast<__half*>(a->out);
@@ -314,7 +317,7 @@ extern "C" int udb_attention_f16(const udb_attn_t* a, void* stream) {
   p.ldo = a->ldo; p.o_col0 = a->o_col0;
   p.q_col0 = a->q_col0; p.k_col0 = a->k_col0; p.v_col0 = a->v_col0;
   p.scale_log2 = a->scale * 1.4426950408889634f;
-  constexpr int smem_bytes = 16384 + 2 * 16384 + 2 * 16384 + 32768 + 128 + 512;
+  constexpr int smem_bytes = 16384 + 2 * AT_KV_STAGES * 8192 + 2 * 16384 + 256;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);

@@ -55,6 +55,9 @@ typedef struct udb_gemm_t {
    * read 0 through TMA out-of-bounds fill) or 0 when the input was padded by the caller
    * (reflect padding, in_H = H+2, in_W = W+2). */
   int32_t conv_B, conv_H, conv_W, conv_C, conv_inH, conv_inW, conv_off, conv_TH, conv_TW;
+  /* the input may be a channel slice [conv_coff, conv_coff + conv_C) of a wider NHWC buffer with
+   * conv_cstride channels per pixel (0 = conv_C) */
+  int32_t conv_cstride, conv_coff;
   /* epilogue: v = acc + bias[n]; v = act(v); v *= gamma[n]; v += resid[...]; out = v;
    * out2 = f16(v) or f16(leaky(v)) (optional second f16 copy, e.g. the next conv's input) */
   const float* bias;
@@ -75,8 +78,9 @@ typedef struct udb_gemm_t {
   int32_t resid_mod, resid_row_offset;
   int64_t ldr;
   /* UDB_STORE_CONVT: row m = (b, y, x) of a [B,h,w] grid; column n = (dy*k+dx)*Cout + co;
-   * writes NHWC pixel (b, y*k+dy, x*k+dx, co) of a [B, h*k, w*k, Cout] map. */
-  int32_t ct_k, ct_cout, ct_h, ct_w;
+   * writes NHWC pixel (b, y*k+dy+pad, x*k+dx+pad, co) of a [B, h*k+2*pad, w*k+2*pad, Cout] map
+   * (pad > 0: the interior of a buffer whose border udb_reflect_border_fill_nhwc_f16 fills). */
+  int32_t ct_k, ct_cout, ct_h, ct_w, ct_pad;
   /* UDB_STORE_HEAD (N == 32): out_pixel = exp(clamp(sum_n head_w[n]*leaky(acc+bias)[n] + head_b,
    * -8, 8) + head_add) written as f32 to out[b*H*W + y*W + x]. */
   const float* head_w;
@@ -215,6 +219,10 @@ int udb_resize_ac_pad_nhwc_f16(const void* in, void* out, int32_t B, int32_t H, 
  * unidepthv2/decoder.py:200-213). */
 int udb_reflect_pad1_nhwc_f16(const void* in, void* out, int32_t B, int32_t H, int32_t W, int32_t C,
                               void* stream);
+
+/* Fill the 1-pixel border of a padded NHWC f16 buffer [B,H+2,W+2,C] by reflection of its interior
+ * (the interior having been written by a GEMM with ct_pad = 1). */
+int udb_reflect_border_fill_nhwc_f16(void* buf, int32_t B, int32_t H, int32_t W, int32_t C, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Output assembly (unidepthv2.py:80-89, 311-339, 375-377; unidepthv2/decoder.py:456-462):

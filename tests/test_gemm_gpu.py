@@ -140,3 +140,27 @@ def test_conv_transpose(k, cout):
     out = ops.conv_transpose_ks(xm, wp, k, cout, (h, w_), bias=bp, resid=lat, out=lat.clone(), out2=out2)
     _close(out, ref, 1.5e-3, f"convT k={k}")
     _close(out2, F.leaky_relu(ref, 0.01), 1.5e-3, f"convT k={k} out2")
+
+
+def test_padded_linear_border_fill_and_channel_slice_conv():
+    """LN->Linear written into a reflect-padded buffer + 3x3 conv over a channel slice of it."""
+    from unidepth_b200 import ops
+    dev = _dev()
+    torch.manual_seed(4)
+    B, H, W, Cin, C2 = 2, 21, 30, 128, 256
+    x = torch.randn(B * H * W, Cin, device=dev).half()
+    wl = (torch.randn(C2, Cin, device=dev) / Cin ** 0.5).half()
+    bl = torch.randn(C2, device=dev)
+    mp = torch.zeros(B, H + 2, W + 2, C2, device=dev, dtype=torch.float16)
+    ops.conv_transpose_ks(x, wl, 1, C2, (H, W), bias=bl, out=mp, pad=1)
+    ops.reflect_border_fill(mp)
+    lin = (x.float() @ wl.float().t() + bl).view(B, H, W, C2).permute(0, 3, 1, 2)
+    ref_pad = F.pad(lin, (1, 1, 1, 1), mode="reflect").permute(0, 2, 3, 1)
+    _close(mp, ref_pad, 1.5e-3, "padded linear + border fill")
+    for i in range(2):
+        wc = (torch.randn(64, 128, 3, 3, device=dev) / (9 * 128) ** 0.5).half()
+        bc = torch.randn(64, device=dev)
+        wp = wc.permute(0, 2, 3, 1).reshape(64, 9 * 128).contiguous()
+        out = ops.conv3x3(mp, wp, bias=bc, prepadded=True, out_dtype=torch.float32, c_off=128 * i, c_used=128)
+        ref = F.conv2d(mp.float().permute(0, 3, 1, 2)[:, 128 * i:128 * (i + 1)], wc.float(), bc).permute(0, 2, 3, 1)
+        _close(out, ref, 3e-5, f"conv3x3 channel slice {i}")

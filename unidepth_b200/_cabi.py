@@ -22,11 +22,12 @@ class Gemm(C.Structure):
         ("a_mode", i32),
         ("conv_B", i32), ("conv_H", i32), ("conv_W", i32), ("conv_C", i32), ("conv_inH", i32),
         ("conv_inW", i32), ("conv_off", i32), ("conv_TH", i32), ("conv_TW", i32),
+        ("conv_cstride", i32), ("conv_coff", i32),
         ("bias", vp), ("gamma", vp), ("resid", vp), ("resid_f32", i32), ("out", vp), ("out_f32", i32),
         ("out2", vp), ("out2_leaky", i32), ("act", i32), ("store_mode", i32), ("ldc", i64),
         ("rows_per_group", i32), ("group_stride", i32), ("row_offset", i32),
         ("resid_mod", i32), ("resid_row_offset", i32), ("ldr", i64),
-        ("ct_k", i32), ("ct_cout", i32), ("ct_h", i32), ("ct_w", i32),
+        ("ct_k", i32), ("ct_cout", i32), ("ct_h", i32), ("ct_w", i32), ("ct_pad", i32),
         ("head_w", vp), ("head_b", f32), ("head_add", f32),
     ]
 
@@ -97,6 +98,7 @@ EXPORTS = {
     "udb_upsample2x_nhwc_f16": (i32, [vp, vp, i32, i32, i32, i32, vp]),
     "udb_resize_ac_pad_nhwc_f16": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]),
     "udb_reflect_pad1_nhwc_f16": (i32, [vp, vp, i32, i32, i32, i32, vp]),
+    "udb_reflect_border_fill_nhwc_f16": (i32, [vp, i32, i32, i32, i32, vp]),
     "udb_postprocess": (i32, [C.POINTER(Postprocess), vp]),
 }
 

@@ -384,72 +384,76 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
   return make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
 }
 
-__global__ void __launch_bounds__(256) upsample2x_kernel(const __half* __restrict__ in, __half* __restrict__ out, int B, int H, int W, int C) {
+// grid: (ceil(out_w * C/8 / 256), out_h, B) -- 32-bit index math, no 64-bit div/mod per element
+__global__ void __launch_bounds__(256) upsample2x_kernel(const __half* __restrict__ in, __half* __restrict__ out, int H, int W, int C) {
   const int cv = C >> 3;
-  const long long total = (long long)B * (2 * H) * (2 * W) * cv;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int c8 = (int)(idx % cv);
-    const int X = (int)((idx / cv) % (2 * W));
-    const int Y = (int)((idx / ((long long)cv * 2 * W)) % (2 * H));
-    const int b = (int)(idx / ((long long)cv * 2 * W * 2 * H));
-    int y0, y1, x0, x1;
-    float ly0, ly1, lx0, lx1;
-    bilinear_src(0.5f, Y, H, y0, y1, ly0, ly1);
-    bilinear_src(0.5f, X, W, x0, x1, lx0, lx1);
-    const uint4* base = reinterpret_cast<const uint4*>(in) + (long long)b * H * W * cv + c8;
-    const uint4 v00 = base[((long long)y0 * W + x0) * cv], v01 = base[((long long)y0 * W + x1) * cv];
-    const uint4 v10 = base[((long long)y1 * W + x0) * cv], v11 = base[((long long)y1 * W + x1) * cv];
-    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    lerp8(v00, v01, lx0, lx1, acc, ly0);
-    lerp8(v10, v11, lx0, lx1, acc, ly1);
-    reinterpret_cast<uint4*>(out)[idx] = pack8(acc);
-  }
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  if (t >= 2 * W * cv) return;
+  const int X = t / cv, c8 = t - X * cv;
+  const int Y = blockIdx.y, b = blockIdx.z;
+  int y0, y1, x0, x1;
+  float ly0, ly1, lx0, lx1;
+  bilinear_src(0.5f, Y, H, y0, y1, ly0, ly1);
+  bilinear_src(0.5f, X, W, x0, x1, lx0, lx1);
+  const uint4* base = reinterpret_cast<const uint4*>(in) + (size_t)b * H * W * cv + c8;
+  const uint4 v00 = base[(size_t)(y0 * W + x0) * cv], v01 = base[(size_t)(y0 * W + x1) * cv];
+  const uint4 v10 = base[(size_t)(y1 * W + x0) * cv], v11 = base[(size_t)(y1 * W + x1) * cv];
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  lerp8(v00, v01, lx0, lx1, acc, ly0);
+  lerp8(v10, v11, lx0, lx1, acc, ly1);
+  reinterpret_cast<uint4*>(out)[((size_t)(b * 2 * H + Y) * 2 * W + X) * cv + c8] = pack8(acc);
 }
 
 __device__ __forceinline__ int reflect_idx(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * (n - 1) - i : i); }
 
-__global__ void __launch_bounds__(256) resize_ac_pad_kernel(const __half* __restrict__ in, __half* __restrict__ out, int B, int H, int W,
-                                                            int C, int oh, int ow, int pad) {
+__global__ void __launch_bounds__(256) resize_ac_pad_kernel(const __half* __restrict__ in, __half* __restrict__ out, int H, int W,
+                                                            int C, int oh, int ow, int pad, float sh, float sw) {
   const int cv = C >> 3;
   const int ph = oh + 2 * pad, pw = ow + 2 * pad;
-  const float sh = (oh > 1) ? (float)(H - 1) / (float)(oh - 1) : 0.f;
-  const float sw = (ow > 1) ? (float)(W - 1) / (float)(ow - 1) : 0.f;
-  const long long total = (long long)B * ph * pw * cv;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int c8 = (int)(idx % cv);
-    const int PX = (int)((idx / cv) % pw);
-    const int PY = (int)((idx / ((long long)cv * pw)) % ph);
-    const int b = (int)(idx / ((long long)cv * pw * ph));
-    const int Y = reflect_idx(PY - pad, oh), X = reflect_idx(PX - pad, ow);
-    const float fy = sh * (float)Y, fx = sw * (float)X;
-    const int y0 = min((int)fy, H - 1), x0 = min((int)fx, W - 1);
-    const int y1 = y0 + ((y0 < H - 1) ? 1 : 0), x1 = x0 + ((x0 < W - 1) ? 1 : 0);
-    const float ly1 = fy - (float)y0, lx1 = fx - (float)x0;
-    const float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
-    const uint4* base = reinterpret_cast<const uint4*>(in) + (long long)b * H * W * cv + c8;
-    const uint4 v00 = base[((long long)y0 * W + x0) * cv], v01 = base[((long long)y0 * W + x1) * cv];
-    const uint4 v10 = base[((long long)y1 * W + x0) * cv], v11 = base[((long long)y1 * W + x1) * cv];
-    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    lerp8(v00, v01, lx0, lx1, acc, ly0);
-    lerp8(v10, v11, lx0, lx1, acc, ly1);
-    reinterpret_cast<uint4*>(out)[idx] = pack8(acc);
-  }
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  if (t >= pw * cv) return;
+  const int PX = t / cv, c8 = t - PX * cv;
+  const int PY = blockIdx.y, b = blockIdx.z;
+  const int Y = reflect_idx(PY - pad, oh), X = reflect_idx(PX - pad, ow);
+  const float fy = sh * (float)Y, fx = sw * (float)X;
+  const int y0 = min((int)fy, H - 1), x0 = min((int)fx, W - 1);
+  const int y1 = y0 + ((y0 < H - 1) ? 1 : 0), x1 = x0 + ((x0 < W - 1) ? 1 : 0);
+  const float ly1 = fy - (float)y0, lx1 = fx - (float)x0;
+  const float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+  const uint4* base = reinterpret_cast<const uint4*>(in) + (size_t)b * H * W * cv + c8;
+  const uint4 v00 = base[(size_t)(y0 * W + x0) * cv], v01 = base[(size_t)(y0 * W + x1) * cv];
+  const uint4 v10 = base[(size_t)(y1 * W + x0) * cv], v11 = base[(size_t)(y1 * W + x1) * cv];
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  lerp8(v00, v01, lx0, lx1, acc, ly0);
+  lerp8(v10, v11, lx0, lx1, acc, ly1);
+  reinterpret_cast<uint4*>(out)[((size_t)(b * ph + PY) * pw + PX) * cv + c8] = pack8(acc);
 }
 
-__global__ void __launch_bounds__(256) reflect_pad1_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H, int W, int cv) {
+__global__ void __launch_bounds__(256) reflect_pad1_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int H, int W, int cv) {
+  const int pw = W + 2;
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  if (t >= pw * cv) return;
+  const int PX = t / cv, c8 = t - PX * cv;
+  const int PY = blockIdx.y, b = blockIdx.z;
+  const int Y = reflect_idx(PY - 1, H), X = reflect_idx(PX - 1, W);
+  out[((size_t)(b * (H + 2) + PY) * pw + PX) * cv + c8] = in[((size_t)(b * H + Y) * W + X) * cv + c8];
+}
+
+// border of a padded [B,H+2,W+2,C] buffer from its (already written) interior; grid: (blocks, B)
+__global__ void __launch_bounds__(256) reflect_border_fill_kernel(uint4* __restrict__ buf, int H, int W, int cv) {
   const int ph = H + 2, pw = W + 2;
-  const long long total = (long long)B * ph * pw * cv;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int c8 = (int)(idx % cv);
-    const int PX = (int)((idx / cv) % pw);
-    const int PY = (int)((idx / ((long long)cv * pw)) % ph);
-    const int b = (int)(idx / ((long long)cv * pw * ph));
-    const int Y = reflect_idx(PY - 1, H), X = reflect_idx(PX - 1, W);
-    out[idx] = in[(((long long)b * H + Y) * W + X) * cv + c8];
-  }
+  const int n_border = 2 * pw + 2 * H;               // top row, bottom row, left / right columns
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  if (t >= n_border * cv) return;
+  const int i = t / cv, c8 = t - i * cv;
+  int PY, PX;
+  if (i < pw) { PY = 0; PX = i; }
+  else if (i < 2 * pw) { PY = ph - 1; PX = i - pw; }
+  else if (i < 2 * pw + H) { PY = i - 2 * pw + 1; PX = 0; }
+  else { PY = i - 2 * pw - H + 1; PX = pw - 1; }
+  const int Y = reflect_idx(PY - 1, H) + 1, X = reflect_idx(PX - 1, W) + 1;
+  uint4* img = buf + (size_t)blockIdx.y * ph * pw * cv;
+  img[((size_t)PY * pw + PX) * cv + c8] = img[((size_t)Y * pw + X) * cv + c8];
 }
 
 // ------------------------------------------------------------------------------------ output assembly
@@ -577,24 +581,33 @@ extern "C" int udb_ray_embed(const udb_ray_embed_t* p, void* stream) {
 
 extern "C" int udb_upsample2x_nhwc_f16(const void* in, void* out, int32_t B, int32_t H, int32_t W, int32_t C, void* stream) {
   if (C % 8) { set_error("udb_upsample2x_nhwc_f16: C %% 8 != 0"); return 1; }
-  const long long total = (long long)B * 4 * H * W * (C / 8);
-  upsample2x_kernel<<<grid_for(total), 256, 0, ST(stream)>>>(reinterpret_cast<const __half*>(in), reinterpret_cast<__half*>(out), B, H, W, C);
+  dim3 grid((2 * W * (C / 8) + 255) / 256, 2 * H, B);
+  upsample2x_kernel<<<grid, 256, 0, ST(stream)>>>(reinterpret_cast<const __half*>(in), reinterpret_cast<__half*>(out), H, W, C);
   return check_launch("upsample2x_kernel");
 }
 
 extern "C" int udb_resize_ac_pad_nhwc_f16(const void* in, void* out, int32_t B, int32_t H, int32_t W, int32_t C, int32_t oh,
                                           int32_t ow, int32_t pad, void* stream) {
   if (C % 8) { set_error("udb_resize_ac_pad_nhwc_f16: C %% 8 != 0"); return 1; }
-  const long long total = (long long)B * (oh + 2 * pad) * (ow + 2 * pad) * (C / 8);
-  resize_ac_pad_kernel<<<grid_for(total), 256, 0, ST(stream)>>>(reinterpret_cast<const __half*>(in), reinterpret_cast<__half*>(out), B, H, W, C, oh, ow, pad);
+  const float sh = (oh > 1) ? (float)(H - 1) / (float)(oh - 1) : 0.f;
+  const float sw = (ow > 1) ? (float)(W - 1) / (float)(ow - 1) : 0.f;
+  dim3 grid(((ow + 2 * pad) * (C / 8) + 255) / 256, oh + 2 * pad, B);
+  resize_ac_pad_kernel<<<grid, 256, 0, ST(stream)>>>(reinterpret_cast<const __half*>(in), reinterpret_cast<__half*>(out), H, W, C, oh, ow, pad, sh, sw);
   return check_launch("resize_ac_pad_kernel");
 }
 
 extern "C" int udb_reflect_pad1_nhwc_f16(const void* in, void* out, int32_t B, int32_t H, int32_t W, int32_t C, void* stream) {
   if (C % 8) { set_error("udb_reflect_pad1_nhwc_f16: C %% 8 != 0"); return 1; }
-  const long long total = (long long)B * (H + 2) * (W + 2) * (C / 8);
-  reflect_pad1_kernel<<<grid_for(total), 256, 0, ST(stream)>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), B, H, W, C / 8);
+  dim3 grid(((W + 2) * (C / 8) + 255) / 256, H + 2, B);
+  reflect_pad1_kernel<<<grid, 256, 0, ST(stream)>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), H, W, C / 8);
   return check_launch("reflect_pad1_kernel");
+}
+
+extern "C" int udb_reflect_border_fill_nhwc_f16(void* buf, int32_t B, int32_t H, int32_t W, int32_t C, void* stream) {
+  if (C % 8) { set_error("udb_reflect_border_fill_nhwc_f16: C %% 8 != 0"); return 1; }
+  dim3 grid(((2 * (W + 2) + 2 * H) * (C / 8) + 255) / 256, B);
+  reflect_border_fill_kernel<<<grid, 256, 0, ST(stream)>>>(reinterpret_cast<uint4*>(buf), H, W, C / 8);
+  return check_launch("reflect_border_fill_kernel");
 }
 
 extern "C" int udb_postprocess(const udb_postprocess_t* p, void* stream) {

@@ -39,7 +39,8 @@ struct GemmArgs {
   long long ldc, ldr;
   int rpg, gstride, roff;
   int resid_mod, resid_roff;
-  int ct_k, ct_cout, ct_h, ct_w;
+  int ct_k, ct_cout, ct_h, ct_w, ct_pad;
+  int conv_coff;
   const float* head_w;
   float head_b, head_add;
 };
@@ -97,9 +98,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, const EpiWarp& 
           const int b = m / hw;
           const int r = m % hw;
           const int y = r / p.ct_w, x = r % p.ct_w;
-          const long long W2 = (long long)p.ct_w * p.ct_k;
-          const long long H2 = (long long)p.ct_h * p.ct_k;
-          out_off = ((b * H2 + (long long)y * p.ct_k) * W2 + (long long)x * p.ct_k) * p.ct_cout;
+          const long long W2 = (long long)p.ct_w * p.ct_k + 2 * p.ct_pad;
+          const long long H2 = (long long)p.ct_h * p.ct_k + 2 * p.ct_pad;
+          out_off = ((b * H2 + (long long)y * p.ct_k + p.ct_pad) * W2 + (long long)x * p.ct_k + p.ct_pad) * p.ct_cout;
           res_off = out_off;
         } else {
           valid = m < p.M;
@@ -160,7 +161,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, const EpiWarp& 
           if (p.store_mode == UDB_STORE_CONVT) {
             const int tap = n0 / p.ct_cout;
             const int co = n0 % p.ct_cout;
-            const long long W2 = (long long)p.ct_w * p.ct_k;
+            const long long W2 = (long long)p.ct_w * p.ct_k + 2 * p.ct_pad;
             coff = ((long long)(tap / p.ct_k) * W2 + (tap % p.ct_k)) * p.ct_cout + co;
           }
           // ---- residual / stores through the per-warp transpose tile: thread == row in registers,
@@ -311,7 +312,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           if (p.a_mode == UDB_A_CONV3X3) {
             const int tap = kb / p.conv_cpb;
-            const int c0 = (kb % p.conv_cpb) * BK;
+            const int c0 = p.conv_coff + (kb % p.conv_cpb) * BK;
             tma_load_4d(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], c0, cx + tap % 3,
                         cy + tap / 3, cb);
           } else {
@@ -498,7 +499,7 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           else mbar_arrive_remote(&full_bar[stage], 0);
           if (p.a_mode == UDB_A_CONV3X3) {
             const int tap = kb / p.conv_cpb;
-            const int c0 = (kb % p.conv_cpb) * BK;
+            const int c0 = p.conv_coff + (kb % p.conv_cpb) * BK;
             tma_load_4d_2sm(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], c0, cx + tap % 3, cy + tap / 3, cb);
           } else {
             tma_load_2d_2sm(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * BK, mt * BM);
@@ -626,7 +627,8 @@ extern "C" int udb_gemm_f16(const udb_gemm_t* g, void* stream) {
   a.ldc = g->ldc; a.ldr = g->ldr > 0 ? g->ldr : g->ldc;
   a.rpg = g->rows_per_group; a.gstride = g->group_stride; a.roff = g->row_offset;
   a.resid_mod = g->resid_mod; a.resid_roff = g->resid_row_offset;
-  a.ct_k = g->ct_k; a.ct_cout = g->ct_cout; a.ct_h = g->ct_h; a.ct_w = g->ct_w;
+  a.ct_k = g->ct_k; a.ct_cout = g->ct_cout; a.ct_h = g->ct_h; a.ct_w = g->ct_w; a.ct_pad = g->ct_pad;
+  a.conv_coff = g->conv_coff;
   a.head_w = g->head_w; a.head_b = g->head_b; a.head_add = g->head_add;
 
   // tile width: widest that divides the work sensibly
@@ -665,9 +667,13 @@ extern "C" int udb_gemm_f16(const udb_gemm_t* g, void* stream) {
     a.conv_tx = (g->conv_W + TW - 1) / TW; a.conv_ty = (g->conv_H + TH - 1) / TH;
     a.tiles_m = g->conv_B * a.conv_tx * a.conv_ty;
     a.M = a.tiles_m * BM;
-    const uint64_t dims[4] = {(uint64_t)g->conv_C, (uint64_t)g->conv_inW, (uint64_t)g->conv_inH, (uint64_t)g->conv_B};
-    const uint64_t str[3] = {(uint64_t)g->conv_C * 2, (uint64_t)g->conv_inW * g->conv_C * 2,
-                             (uint64_t)g->conv_inH * g->conv_inW * g->conv_C * 2};
+    const uint64_t cs = g->conv_cstride > 0 ? g->conv_cstride : g->conv_C;
+    if ((uint64_t)g->conv_coff + g->conv_C > cs || (g->conv_coff % 8)) {
+      set_error("udb_gemm_f16: bad conv channel slice (off %d, C %d, stride %d)", g->conv_coff, g->conv_C, (int)cs);
+      return 1;
+    }
+    const uint64_t dims[4] = {cs, (uint64_t)g->conv_inW, (uint64_t)g->conv_inH, (uint64_t)g->conv_B};
+    const uint64_t str[3] = {cs * 2, (uint64_t)g->conv_inW * cs * 2, (uint64_t)g->conv_inH * g->conv_inW * cs * 2};
     const uint32_t box[4] = {(uint32_t)BK, (uint32_t)TW, (uint32_t)TH, 1};
     if (make_tmap_f16(&tmA, g->a, 4, dims, str, box, true)) return 1;
   } else {

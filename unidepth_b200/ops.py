@@ -79,15 +79,16 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, act=ACT_NONE, gamma=Non
 
 def conv3x3(x: torch.Tensor, w: torch.Tensor, *, bias=None, act=ACT_NONE, gamma=None, resid=None,
             out: Optional[torch.Tensor] = None, out_dtype=f16, out2=None, out2_leaky=True, prepadded=False,
-            head_w=None, head_b=0.0, head_add=0.0, tile=(8, 16)):
+            head_w=None, head_b=0.0, head_add=0.0, tile=(8, 16), c_off=0, c_used=None):
     """3x3 convolution over an NHWC f16 image x [B,H,W,C] (or [B,H+2,W+2,C] if prepadded) with
     packed weights w [Cout, 9*C] ordered (dy,dx,c).  Zero padding unless prepadded.
     With head_w: fused LeakyReLU + 1x1 (32->1) + clamp/exp head, returns f32 [B,H,W]."""
     assert x.dtype == f16 and w.dtype == f16 and x.is_contiguous() and w.is_contiguous()
-    B, inH, inW, Cin = x.shape
+    B, inH, inW, Ctot = x.shape
+    Cin = c_used if c_used is not None else Ctot        # channel slice [c_off, c_off + Cin) of the buffer
     H, W = (inH - 2, inW - 2) if prepadded else (inH, inW)
     N = w.shape[0]
-    assert w.shape[1] == 9 * Cin
+    assert w.shape[1] == 9 * Cin and c_off + Cin <= Ctot
     g = cabi.Gemm()
     g.a, g.w = _ptr(x), _ptr(w)
     g.M, g.N, g.K = B * H * W, N, 9 * Cin
@@ -97,6 +98,7 @@ def conv3x3(x: torch.Tensor, w: torch.Tensor, *, bias=None, act=ACT_NONE, gamma=
     g.conv_inH, g.conv_inW = inH, inW
     g.conv_off = 0 if prepadded else -1
     g.conv_TH, g.conv_TW = tile
+    g.conv_cstride, g.conv_coff = Ctot, c_off
     g.bias, g.gamma = _ptr(bias), _ptr(gamma)
     g.act = act
     if head_w is not None:
@@ -119,15 +121,17 @@ def conv3x3(x: torch.Tensor, w: torch.Tensor, *, bias=None, act=ACT_NONE, gamma=
 
 
 def conv_transpose_ks(x: torch.Tensor, w: torch.Tensor, k: int, cout: int, grid_hw, *, bias=None,
-                      resid=None, out: Optional[torch.Tensor] = None, out_dtype=f16, out2=None, out2_leaky=True):
+                      resid=None, out: Optional[torch.Tensor] = None, out_dtype=f16, out2=None, out2_leaky=True,
+                      pad=0):
     """ConvTranspose2d with kernel == stride == k as a GEMM with a pixel-shuffle store.
     x f16 [B*h*w, Cin]; w f16 [k*k*cout, Cin] ordered (dy,dx,co); bias f32 [k*k*cout].
-    out NHWC [B, h*k, w*k, cout] (+ resid of the same shape, may alias out)."""
+    out NHWC [B, h*k + 2*pad, w*k + 2*pad, cout] (+ resid of the same shape, may alias out); with
+    pad > 0 only the interior is written (k == 1: a per-pixel linear layer into a padded buffer)."""
     h, ww = grid_hw
     M, K = x.shape
     B = M // (h * ww)
     if out is None:
-        out = torch.empty((B, h * k, ww * k, cout), device=x.device, dtype=out_dtype)
+        out = torch.empty((B, h * k + 2 * pad, ww * k + 2 * pad, cout), device=x.device, dtype=out_dtype)
     g = cabi.Gemm()
     g.a, g.w = _ptr(x), _ptr(w)
     g.M, g.N, g.K = M, k * k * cout, K
@@ -139,7 +143,7 @@ def conv_transpose_ks(x: torch.Tensor, w: torch.Tensor, k: int, cout: int, grid_
     g.out, g.out_f32, g.ldc = _ptr(out), _is32(out), cout
     g.out2, g.out2_leaky = _ptr(out2), int(out2_leaky)
     g.store_mode = STORE_CONVT
-    g.ct_k, g.ct_cout, g.ct_h, g.ct_w = k, cout, h, ww
+    g.ct_k, g.ct_cout, g.ct_h, g.ct_w, g.ct_pad = k, cout, h, ww, pad
     cabi.check(_launch("gemm_f16_kernel", 2.0 * M * k * k * cout * K,
                        lambda: cabi.lib().udb_gemm_f16(C.byref(g), _stream())), "udb_gemm_f16(convT)")
     return out
@@ -263,6 +267,14 @@ def reflect_pad1(x):
     out = torch.empty((B, H + 2, W + 2, Cc), device=x.device, dtype=f16)
     cabi.check(cabi.lib().udb_reflect_pad1_nhwc_f16(_ptr(x), _ptr(out), B, H, W, Cc, _stream()), "udb_reflect_pad1_nhwc_f16")
     return out
+
+
+def reflect_border_fill(buf):
+    """In place: 1-pixel reflect border of a padded NHWC f16 buffer [B,H+2,W+2,C] from its interior."""
+    B, PH, PW, Cc = buf.shape
+    cabi.check(cabi.lib().udb_reflect_border_fill_nhwc_f16(_ptr(buf), B, PH - 2, PW - 2, Cc, _stream()),
+               "udb_reflect_border_fill_nhwc_f16")
+    return buf
 
 
 def postprocess(radius, confidence, intr4, B, net_hw, padded_hw, pad_l, pad_t, out_hw, rays_in=None):

@@ -199,16 +199,26 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
             st["up_w"], st["up_b"] = h16(uw.reshape(uw.shape[0], uw.shape[1])), c32(sd[f"{dl}ups.{i}.up.0.bias"])
             P["ups"].append(st)
         last = len(s.dec_depths) - 1
+        # heads: LN(x) = xhat * w + b with the SAME xhat for depth and confidence, so the two
+        # LN -> Linear pairs fold into one GEMM on xhat with W' = W * w (per input channel) and
+        # b' = W b + bias, depth rows first then confidence rows (decoder.py:190-199, 288, 306-307)
         P["heads"] = []
+        wm, bm = [], []
         for mlp_p, lr, hr, add in ((f"{dl}depth_mlp.{last}", "to_depth_lr", "to_depth_hr", 2.0),
                                    (f"{dl}confidence_mlp", "to_confidence_lr", "to_confidence_hr", 0.0)):
+            lnw, lnb = sd[mlp_p + ".0.weight"].float(), sd[mlp_p + ".0.bias"].float()
+            w, bb = sd[mlp_p + ".1.weight"].float(), sd[mlp_p + ".1.bias"].float()
+            wm.append(w * lnw.unsqueeze(0))
+            bm.append(w @ lnb + bb)
             P["heads"].append(dict(
-                lnw=c32(sd[mlp_p + ".0.weight"]), lnb=c32(sd[mlp_p + ".0.bias"]),
-                w=h16(sd[mlp_p + ".1.weight"]), b=c32(sd[mlp_p + ".1.bias"]),
                 lr_w=conv_pack(sd[f"{dl}{lr}.weight"]), lr_b=c32(sd[f"{dl}{lr}.bias"]),
                 hr_w=conv_pack(sd[f"{dl}{hr}.0.weight"]), hr_b=c32(sd[f"{dl}{hr}.0.bias"]),
                 head_w=c32(sd[f"{dl}{hr}.2.weight"].reshape(32)), head_b=float(sd[f"{dl}{hr}.2.bias"].item()),
                 add=add))
+        P["head_mlp_w"], P["head_mlp_b"] = h16(torch.cat(wm, 0)), c32(torch.cat(bm, 0))
+        c_hr = wm[0].shape[1]
+        P["ln_ones"] = torch.ones(c_hr, device=dev, dtype=f32)
+        P["ln_zeros"] = torch.zeros(c_hr, device=dev, dtype=f32)
         self._packed = P
         self._packed_key = self._fingerprint()
         self._graphs.clear()
@@ -369,13 +379,16 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
         C_hr = feat_hr.shape[-1]
         hh, hw = feat_hr.shape[1], feat_hr.shape[2]
 
-        # a16/a17: depth + confidence heads
+        # a16/a17: depth + confidence heads (shared normalisation, merged LN->Linear GEMM written
+        # straight into the reflect-padded buffer the 3x3 "lr" convs read)
+        xhat = ops.layernorm(feat_hr, P["ln_ones"], P["ln_zeros"], 1e-5, out=E(B * hh * hw, C_hr))
+        n_mlp = P["head_mlp_w"].shape[0]                      # 2 * out_dim: [depth | confidence]
+        mp = E(B, hh + 2, hw + 2, n_mlp)
+        ops.conv_transpose_ks(xhat, P["head_mlp_w"], 1, n_mlp, (hh, hw), bias=P["head_mlp_b"], out=mp, pad=1)
+        ops.reflect_border_fill(mp)
         planes = []
-        for hd in P["heads"]:
-            tln = ops.layernorm(feat_hr, hd["lnw"], hd["lnb"], 1e-5, out=E(B * hh * hw, C_hr))
-            m = ops.gemm(tln, hd["w"], bias=hd["b"], out=E(B * hh * hw, hd["w"].shape[0]))
-            mp = ops.reflect_pad1(m.view(B, hh, hw, -1))
-            lr = ops.conv3x3(mp, hd["lr_w"], bias=hd["lr_b"], prepadded=True)
+        for i, hd in enumerate(P["heads"]):
+            lr = ops.conv3x3(mp, hd["lr_w"], bias=hd["lr_b"], prepadded=True, c_off=i * (n_mlp // 2), c_used=n_mlp // 2)
             up = ops.resize_ac_pad(lr, nh, nw, 1)
             planes.append(ops.conv3x3(up, hd["hr_w"], bias=hd["hr_b"], prepadded=True, act=ops.ACT_LEAKY,
                                       head_w=hd["head_w"], head_b=hd["head_b"], head_add=hd["add"]))

@@ -37,18 +37,46 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+// exp2 of two values on the FMA / ALU pipes (no MUFU): x = n + f with n = round(x), f in [-0.5, 0.5];
+// 2^f by a degree-3 minimax polynomial (max relative error 7.6e-5, far below the f16 rounding of P);
+// 2^n is added into the exponent field.  Requires -126 < x < 126 (callers clamp the scores).
+__device__ __forceinline__ void exp2_poly_pair(const uint64_t x2, float& e0, float& e1) {
+  const uint64_t magic = pack2(12582912.f, 12582912.f);        // 1.5 * 2^23: x + magic rounds to integer
+  const uint64_t t2 = add2(x2, magic);
+  const uint64_t n2 = add2(t2, pack2(-12582912.f, -12582912.f));
+  const uint64_t f2 = fma2(n2, pack2(-1.f, -1.f), x2);
+  uint64_t q = fma2(pack2(0.05520550534129143f, 0.05520550534129143f), f2, pack2(0.24261397123336792f, 0.24261397123336792f));
+  q = fma2(q, f2, pack2(0.6932547688484192f, 0.6932547688484192f));
+  q = fma2(q, f2, pack2(0.9999276995658875f, 0.9999276995658875f));
+  float p0, p1, t0, t1;
+  unpack2(q, p0, p1);
+  unpack2(t2, t0, t1);
+  e0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23));
+  e1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
+}
+
 // exp2(s*scale - m) for 64 scores of one row; returns the row sum; P (f16) packed in place into
-// sv[0..31].  MASK: only the first kv_left entries are valid keys (last tile).
+// sv[0..31].  MASK: only the first kv_left entries are valid keys (last tile).  The MUFU unit
+// (16 ex2 / clk / SM) is the bottleneck of d=64 attention, so every second pair of elements is
+// computed with the polynomial instead.
 template <bool MASK>
 __device__ __forceinline__ float softmax_row(uint32_t (&sv)[AT_BK], const float sc, const float m_used,
                                              const int kv_left) {
   const uint64_t sc2 = pack2(sc, sc), nm2 = pack2(-m_used, -m_used);
+  const float s_floor = (m_used - 100.0f) / sc;      // scores below this give exp2(< -100) = 0 in f16 anyway
   uint64_t psum2 = 0ull;
 #pragma unroll
   for (int i = 0; i < AT_BK; i += 2) {
-    float t0, t1;
-    unpack2(fma2(pack2u(sv[i], sv[i + 1]), sc2, nm2), t0, t1);
-    float e0 = ex2(t0), e1 = ex2(t1);
+    float e0, e1;
+    if ((i >> 1) & 1) {
+      const float s0 = fmaxf(__uint_as_float(sv[i]), s_floor), s1 = fmaxf(__uint_as_float(sv[i + 1]), s_floor);
+      exp2_poly_pair(fma2(pack2(s0, s1), sc2, nm2), e0, e1);
+    } else {
+      float t0, t1;
+      unpack2(fma2(pack2u(sv[i], sv[i + 1]), sc2, nm2), t0, t1);
+      e0 = ex2(t0);
+      e1 = ex2(t1);
+    }
     if (MASK) {
       e0 = (i < kv_left) ? e0 : 0.f;
       e1 = (i + 1 < kv_left) ? e1 : 0.f;

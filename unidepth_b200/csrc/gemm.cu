@@ -19,6 +19,7 @@ namespace udb {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int kEpiWarps = 8;
+constexpr int kTP = 36;   // pitch (floats) of the per-warp 32-row transpose tile: 16 B aligned rows, conflict-free 128-bit access
 constexpr int kThreads = (4 + kEpiWarps) * 32;
 
 struct GemmArgs {
@@ -47,14 +48,14 @@ struct GemmArgs {
 
 template <int BN>
 struct GemmCfg {
-  static constexpr int kStages = BN >= 256 ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int kStages = BN >= 256 ? 3 : (BN >= 128 ? 5 : 7);
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = (2 * BN) < 32 ? 32 : (2 * BN);
   // epilogue staging: per epilogue warp a 32x32 f32 transpose tile (XOR-swizzled, no padding) and
   // 2 x 32 row offsets, so that global loads/stores are row-contiguous (coalesced) per instruction
-  static constexpr int kStagingBytes = kEpiWarps * (32 * 32 * 4 + 2 * 32 * 4);
+  static constexpr int kStagingBytes = kEpiWarps * (32 * kTP * 4 + 2 * 32 * 4);
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 256 /*barriers*/;
 };
 
@@ -63,7 +64,7 @@ struct GemmCfg {
 // BN-wide column block.  Executed by the 8 epilogue warps; warp (quad, grp) owns TMEM lanes
 // [32*quad, +32) and column half `grp`.
 struct EpiWarp {
-  float* T;              // [32][32] transpose tile, column index XOR row
+  float* T;              // [32][kTP] transpose tile
   uint32_t* roff_out;    // [32] element offsets of this warp's rows in out / out2
   uint32_t* roff_res;    // [32] element offsets in resid
   int quad, grp, lane, r_in_tile;
@@ -164,83 +165,91 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, const EpiWarp& 
             const long long W2 = (long long)p.ct_w * p.ct_k + 2 * p.ct_pad;
             coff = ((long long)(tap / p.ct_k) * W2 + (tap % p.ct_k)) * p.ct_cout + co;
           }
-          // ---- residual / stores through the per-warp transpose tile: thread == row in registers,
-          //      lane == column in global memory (each instruction touches one contiguous row segment)
+          // ---- residual / stores through the per-warp transpose tile T[32][TP]: in registers a thread
+          //      owns a row; in global memory 8 lanes x 16 B (f32) or 8 B (f16) cover one 32-column row
+          //      segment and one instruction covers 4 rows, so every access is contiguous.  All smem
+          //      traffic is 128-bit and conflict-free with the 36-float pitch.
           const uint32_t c32 = static_cast<uint32_t>(coff);
-          if (p.resid) {
-            // all 32 (16) row loads are issued before the first use: the epilogue is latency-bound
-            // on these loads, so memory-level parallelism matters more than instruction count
-            if (p.resid_f32) {
-              const float* rp = reinterpret_cast<const float*>(p.resid);
-              float tmp[32];
+          const int l4 = (lane & 7) * 4, rq = lane >> 3;
+          float* Trow = T + lane * kTP;
+          auto stage_rows = [&](const float (&x)[32]) {      // thread == row  ->  T
 #pragma unroll
-              for (int r = 0; r < 32; ++r)
-                tmp[r] = ((vmask >> r) & 1u) ? rp[(size_t)roff_res[r] + c32 + lane] : 0.f;
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(Trow + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
+          };
+          auto for_rows = [&](auto&& body) {                 // body(rr, valid) for this lane's 8 rows
+            if (vmask == 0xffffffffu) {
 #pragma unroll
-              for (int r = 0; r < 32; ++r) T[r * 32 + (lane ^ r)] = tmp[r];
+              for (int i = 0; i < 8; ++i) body(4 * i + rq, true);
             } else {
-              const __half* rp = reinterpret_cast<const __half*>(p.resid);
-              const int l2 = (lane & 15) * 2;
-              __half2 tmp[16];
 #pragma unroll
-              for (int r = 0; r < 16; ++r) {
-                const int rr = 2 * r + (lane >> 4);
-                tmp[r] = ((vmask >> rr) & 1u)
-                             ? *reinterpret_cast<const __half2*>(rp + (size_t)roff_res[rr] + c32 + l2)
-                             : __floats2half2_rn(0.f, 0.f);
-              }
+              for (int i = 0; i < 8; ++i) body(4 * i + rq, ((vmask >> (4 * i + rq)) & 1u) != 0);
+            }
+          };
+          if (p.resid) {
+            // all 8 row-segment loads of a lane are issued before the first use (latency-bound)
+            if (p.resid_f32) {
+              const float* rp = reinterpret_cast<const float*>(p.resid) + c32 + l4;
+              float4 tmp[8];
+              int k = 0;
+              for_rows([&](int rr, bool ok) {
+                tmp[k++] = ok ? *reinterpret_cast<const float4*>(rp + roff_res[rr]) : make_float4(0.f, 0.f, 0.f, 0.f);
+              });
 #pragma unroll
-              for (int r = 0; r < 16; ++r) {
-                const int rr = 2 * r + (lane >> 4);
-                const float2 f = __half22float2(tmp[r]);
-                T[rr * 32 + (l2 ^ rr)] = f.x;
-                T[rr * 32 + ((l2 + 1) ^ rr)] = f.y;
+              for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(T + (4 * i + rq) * kTP + l4) = tmp[i];
+            } else {
+              const __half* rp = reinterpret_cast<const __half*>(p.resid) + c32 + l4;
+              uint2 tmp[8];
+              int k = 0;
+              for_rows([&](int rr, bool ok) {
+                tmp[k++] = ok ? *reinterpret_cast<const uint2*>(rp + roff_res[rr]) : make_uint2(0u, 0u);
+              });
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&tmp[i].x));
+                const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&tmp[i].y));
+                *reinterpret_cast<float4*>(T + (4 * i + rq) * kTP + l4) = make_float4(a.x, a.y, b.x, b.y);
               }
             }
             __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += T[lane * 32 + (j ^ lane)];
+            for (int j = 0; j < 32; j += 4) {
+              const float4 t = *reinterpret_cast<const float4*>(Trow + j);
+              v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+            }
             __syncwarp();
           }
           if (p.out) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) T[lane * 32 + (j ^ lane)] = v[j];
+            stage_rows(v);
             __syncwarp();
             if (p.out_f32) {
-              float* op = reinterpret_cast<float*>(p.out);
-#pragma unroll
-              for (int r = 0; r < 32; ++r)
-                if ((vmask >> r) & 1u) op[(size_t)roff_out[r] + c32 + lane] = T[r * 32 + (lane ^ r)];
+              float* op = reinterpret_cast<float*>(p.out) + c32 + l4;
+              for_rows([&](int rr, bool ok) {
+                if (ok) *reinterpret_cast<float4*>(op + roff_out[rr]) = *reinterpret_cast<const float4*>(T + rr * kTP + l4);
+              });
             } else {
-              __half* op = reinterpret_cast<__half*>(p.out);
-              const int l2 = (lane & 15) * 2;
-#pragma unroll
-              for (int r = 0; r < 32; r += 2) {
-                const int rr = r + (lane >> 4);
-                if ((vmask >> rr) & 1u)
-                  *reinterpret_cast<uint32_t*>(op + (size_t)roff_out[rr] + c32 + l2) =
-                      pack_half2(T[rr * 32 + (l2 ^ rr)], T[rr * 32 + ((l2 + 1) ^ rr)]);
-              }
+              __half* op = reinterpret_cast<__half*>(p.out) + c32 + l4;
+              for_rows([&](int rr, bool ok) {
+                const float4 t = *reinterpret_cast<const float4*>(T + rr * kTP + l4);
+                if (ok) *reinterpret_cast<uint2*>(op + roff_out[rr]) = make_uint2(pack_half2(t.x, t.y), pack_half2(t.z, t.w));
+              });
             }
             __syncwarp();
           }
           if (p.out2) {
             if (p.out2_leaky) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) T[lane * 32 + (j ^ lane)] = leaky(v[j]);
+              for (int j = 0; j < 32; ++j) v[j] = leaky(v[j]);
+              stage_rows(v);
             } else if (!p.out) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) T[lane * 32 + (j ^ lane)] = v[j];
+              stage_rows(v);
             }   // else: T still holds v from the `out` pass
             __syncwarp();
-            const int l2 = (lane & 15) * 2;
-#pragma unroll
-            for (int r = 0; r < 32; r += 2) {
-              const int rr = r + (lane >> 4);
-              if ((vmask >> rr) & 1u)
-                *reinterpret_cast<uint32_t*>(p.out2 + (size_t)roff_out[rr] + c32 + l2) =
-                    pack_half2(T[rr * 32 + (l2 ^ rr)], T[rr * 32 + ((l2 + 1) ^ rr)]);
-            }
+            __half* op = p.out2 + c32 + l4;
+            for_rows([&](int rr, bool ok) {
+              const float4 t = *reinterpret_cast<const float4*>(T + rr * kTP + l4);
+              if (ok) *reinterpret_cast<uint2*>(op + roff_out[rr]) = make_uint2(pack_half2(t.x, t.y), pack_half2(t.z, t.w));
+            });
             __syncwarp();
           }
         }
@@ -364,8 +373,8 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int quad = warp & 3;            // TMEM lane quadrant this warp may access
     const int grp = ew >> 2;              // column half
     const int r_in_tile = quad * 32 + lane;
-    float* T = reinterpret_cast<float*>(staging) + ew * 1024;                       // [32][32], col ^ row
-    uint32_t* roff_out = reinterpret_cast<uint32_t*>(staging + kEpiWarps * 4096) + ew * 64;
+    float* T = reinterpret_cast<float*>(staging) + ew * 32 * kTP;                   // [32][kTP]
+    uint32_t* roff_out = reinterpret_cast<uint32_t*>(staging + kEpiWarps * 32 * kTP * 4) + ew * 64;
     uint32_t* roff_res = roff_out + 32;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -419,12 +428,12 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
 // ---------------------------------------------------------------------------------------------
 template <int BN>
 struct Gemm2Cfg {
-  static constexpr int kStages = 6;
+  static constexpr int kStages = BN >= 256 ? 5 : 7;
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = (BN / 2) * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BN;
-  static constexpr int kStagingBytes = kEpiWarps * (32 * 32 * 4 + 2 * 32 * 4);
+  static constexpr int kStagingBytes = kEpiWarps * (32 * kTP * 4 + 2 * 32 * 4);
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 256;
 };
 
@@ -545,9 +554,9 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue (both CTAs)
     const int ew = warp - 4;
-    EpiWarp ctx{reinterpret_cast<float*>(staging) + ew * 1024,
-                reinterpret_cast<uint32_t*>(staging + kEpiWarps * 4096) + ew * 64,
-                reinterpret_cast<uint32_t*>(staging + kEpiWarps * 4096) + ew * 64 + 32,
+    EpiWarp ctx{reinterpret_cast<float*>(staging) + ew * 32 * kTP,
+                reinterpret_cast<uint32_t*>(staging + kEpiWarps * 32 * kTP * 4) + ew * 64,
+                reinterpret_cast<uint32_t*>(staging + kEpiWarps * 32 * kTP * 4) + ew * 64 + 32,
                 warp & 3, ew >> 2, lane, (warp & 3) * 32 + lane};
     int it = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {

@@ -2,16 +2,13 @@
 //
 // One CTA = one (batch, head, 128-query tile); two CTAs are resident per SM (TMEM 2 x 256 columns,
 // <= 113 KB shared memory each).  Keys are processed in tiles of 64:
-//   warp 0      : TMA producer (Q once; K_j / V_j tiles through two independent 3-stage rings)
+//   warp 0      : TMA producer (Q once; K_j / V_j tiles through two independent 4-stage rings)
 //   warp 1      : TMEM allocator + MMA issuer.  S_j = Q K_j^T (M128 N64 K64) goes to one of TWO score
 //                 buffers in TMEM and is issued two tiles ahead, so the scores of tile j+1 are ready
 //                 while the softmax warps are still busy with tile j; O += P_j V_j (M128 N64 K64, V is
 //                 the MN-major B operand) accumulates in TMEM.
-//   warps 2..9  : softmax, TWO threads per query row (32 keys each; 4 softmax warps per SM
-//                 sub-partition hide the MUFU / TMEM latencies that 2 could not): S_j from TMEM
-//                 (tcgen05.ld), row max / sum in fp32 with packed f32x2 math, half of the exp2 on the
-//                 FMA pipe (polynomial), P_j as f16 into one of two 128B-swizzled smem buffers.  The two
-//                 threads of a row exchange their partial maxima through smem (bf16, rounded up).
+//   warps 2..5  : softmax, one query row per thread: S_j from TMEM (tcgen05.ld), row max / sum in fp32
+//                 with packed f32x2 math, P_j as f16 into one of two 128B-swizzled smem buffers.
 //                 O is rescaled lazily: only when a row maximum grows by more than 2^8 over the
 //                 reference the probabilities are expressed against (tcgen05.ld -> mul -> tcgen05.st).
 // Replaces F.scaled_dot_product_attention (reference: metadinov2/attention.py:58,
@@ -23,9 +20,8 @@ namespace udb {
 
 constexpr int AT_BQ = 128;       // queries per CTA
 constexpr int AT_BK = 64;        // keys per tile
-constexpr int AT_KV_STAGES = 3;  // per ring
-constexpr int AT_THREADS = 320;  // TMA warp, MMA warp, 8 softmax warps
-constexpr int AT_HK = AT_BK / 2; // keys per softmax thread and tile (two threads share a query row)
+constexpr int AT_KV_STAGES = 4;  // per ring
+constexpr int AT_THREADS = 192;  // TMA warp, MMA warp, 4 softmax warps
 
 struct AttnArgs {
   __half* out;
@@ -59,18 +55,18 @@ __device__ __forceinline__ void exp2_poly_pair(const uint64_t x2, float& e0, flo
   e1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
 }
 
-// exp2(s*scale - m) for this thread's 32 scores of one row; returns the row sum; P (f16) packed in place into
-// sv[0..AT_HK/2).  MASK: only the first kv_left entries are valid keys (last tile).  The MUFU unit
+// exp2(s*scale - m) for 64 scores of one row; returns the row sum; P (f16) packed in place into
+// sv[0..31].  MASK: only the first kv_left entries are valid keys (last tile).  The MUFU unit
 // (16 ex2 / clk / SM) is the bottleneck of d=64 attention, so every second pair of elements is
 // computed with the polynomial instead.
 template <bool MASK>
-__device__ __forceinline__ float softmax_row(uint32_t (&sv)[AT_HK], const float sc, const float m_used,
+__device__ __forceinline__ float softmax_row(uint32_t (&sv)[AT_BK], const float sc, const float m_used,
                                              const int kv_left) {
   const uint64_t sc2 = pack2(sc, sc), nm2 = pack2(-m_used, -m_used);
   const float s_floor = (m_used - 100.0f) / sc;      // scores below this give exp2(< -100) = 0 in f16 anyway
   uint64_t psum2 = 0ull;
 #pragma unroll
-  for (int i = 0; i < AT_HK; i += 2) {
+  for (int i = 0; i < AT_BK; i += 2) {
     float e0, e1;
     if ((i >> 1) & 1) {
       const float s0 = fmaxf(__uint_as_float(sv[i]), s_floor), s1 = fmaxf(__uint_as_float(sv[i + 1]), s_floor);
@@ -94,17 +90,17 @@ __device__ __forceinline__ float softmax_row(uint32_t (&sv)[AT_HK], const float 
 }
 
 template <bool MASK>
-__device__ __forceinline__ float row_max(const uint32_t (&sv)[AT_HK], const int kv_left) {
+__device__ __forceinline__ float row_max(const uint32_t (&sv)[AT_BK], const int kv_left) {
   float m0 = -INFINITY, m1 = -INFINITY;    // two chains for ILP
   if (!MASK) {
 #pragma unroll
-    for (int i = 0; i < AT_HK; i += 4) {
+    for (int i = 0; i < AT_BK; i += 4) {
       m0 = max3(m0, __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]));
       m1 = max3(m1, __uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3]));
     }
   } else {
 #pragma unroll
-    for (int i = 0; i < AT_HK; ++i) m0 = (i < kv_left) ? fmaxf(m0, __uint_as_float(sv[i])) : m0;
+    for (int i = 0; i < AT_BK; ++i) m0 = (i < kv_left) ? fmaxf(m0, __uint_as_float(sv[i])) : m0;
   }
   return fmaxf(m0, m1);
 }
@@ -134,7 +130,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* p_full = s_full + 2;           // [2]
   uint64_t* p_free = p_full + 2;           // [2]  PV MMA of the tile that used P buffer / parity slot done
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(p_free + 2);
-  uint16_t* xch = reinterpret_cast<uint16_t*>(bars + 32);   // [2 tile parities][2 halves][128] partial row maxima
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -142,6 +137,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int head = blockIdx.y;
   const int b = blockIdx.z;
   const int n_tiles = p.n_kv_tiles;
+  pdl_launch_dependents();
 
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023) __trap();
@@ -157,7 +153,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 8);
+      mbar_init(&p_full[i], 4);
       mbar_init(&p_free[i], 1);
     }
     fence_barrier_init();
@@ -168,6 +164,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t tmem_O = tmem_base + 128;
+  pdl_wait();   // everything above overlapped the previous kernel's tail
 
   if (warp == 0) {
     if (lane == 0) {
@@ -221,33 +218,28 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   } else {
     // ------------------------------------------------------------------ softmax warps
     const int quad = warp & 3;                  // TMEM lane quadrant of this warp
-    const int half = (warp - 2) >> 2;           // which 32 keys of each 64-key tile
     const int row = quad * 32 + lane;           // query row inside the tile == TMEM lane
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
     float m_used = -INFINITY, l_run = 0.f;
     const int sw = row & 7;
     const float sc = p.scale_log2;
     constexpr float kRescaleThreshold = 8.0f;   // log2 domain
-    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory"); };
 
     for (int j = 0; j < n_tiles; ++j) {
       const int sb = j & 1;
       mbar_wait(&s_full[sb], (j >> 1) & 1);
       tc_fence_after_sync();
-      const int kv_left = p.seq_k - j * AT_BK - half * AT_HK;   // valid keys among this thread's 32 (may be <= 0)
-      const bool full = kv_left >= AT_HK;
-      uint32_t sv[AT_HK];
-      tmem_ld_32x32b_x32(tmem_base + lane_addr + sb * AT_BK + half * AT_HK, sv);
-      tmem_ld_wait();
-      // partial row maximum (scaled), exchanged as bf16 rounded UP: any common upper bound of the two
-      // halves is a valid softmax reference, and both threads derive the identical value
-      const float mp = (full ? row_max<false>(sv, kv_left) : row_max<true>(sv, kv_left)) * sc;
-      uint32_t mb = 0xFF800000u;                               // -inf
-      if (mp > -INFINITY) mb = __float_as_uint(mp + fabsf(mp) * 0.0079f) & 0xFFFF0000u;
-      xch[(sb * 2 + half) * 128 + row] = static_cast<uint16_t>(mb >> 16);   // double-buffered by tile parity
-      pair_sync();
-      const uint32_t ob = static_cast<uint32_t>(xch[(sb * 2 + (half ^ 1)) * 128 + row]) << 16;
-      const float m_tile = fmaxf(__uint_as_float(mb), __uint_as_float(ob));
+      const int kv_left = p.seq_k - j * AT_BK;   // valid keys in this tile (>= 1)
+      const bool full = kv_left >= AT_BK;
+      uint32_t sv[AT_BK];
+      {
+        uint32_t(&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[0]);
+        uint32_t(&s1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[32]);
+        tmem_ld_32x32b_x32(tmem_base + lane_addr + sb * AT_BK, s0);
+        tmem_ld_32x32b_x32(tmem_base + lane_addr + sb * AT_BK + 32, s1);
+        tmem_ld_wait();
+      }
+      const float m_tile = (full ? row_max<false>(sv, kv_left) : row_max<true>(sv, kv_left)) * sc;
       const bool need = m_tile > m_used + kRescaleThreshold;   // always true on the first tile
       float alpha = 1.0f;
       if (need) {
@@ -258,15 +250,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // completion of that barrier (tile j) needs this thread's own arrival, so the parity is unambiguous
       if (j >= 2) mbar_wait(&p_free[sb], ((j >> 1) & 1) ^ 1);
       if (j > 0 && __any_sync(0xffffffffu, need)) {
-        // rare: rescale this warp's 32 rows x 32 columns of O (rows that do not need it multiply by 1);
+        // rare: rescale this warp's 32 rows of O (rows that do not need it multiply by 1);
         // needs every PV MMA issued so far (tile j-1 is the latest) to have completed
         mbar_wait(&p_free[(j - 1) & 1], ((j - 1) >> 1) & 1);
         tc_fence_after_sync();
         const uint64_t a2 = pack2(alpha, alpha);
 #pragma unroll 1
-        for (int c = 0; c < 32; c += 16) {
+        for (int c = 0; c < HD; c += 16) {
           uint32_t r[16];
-          tmem_ld_32x32b_x16(tmem_O + lane_addr + half * 32 + c, r);
+          tmem_ld_32x32b_x16(tmem_O + lane_addr + c, r);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 16; i += 2) {
@@ -275,7 +267,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             r[i] = __float_as_uint(lo);
             r[i + 1] = __float_as_uint(hi);
           }
-          tmem_st_32x32b_x16(tmem_O + lane_addr + half * 32 + c, r);
+          tmem_st_32x32b_x16(tmem_O + lane_addr + c, r);
         }
         tmem_st_wait();
       }
@@ -283,34 +275,34 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       l_run = fmaf(l_run, alpha, psum);
       uint8_t* p_row = sP + sb * kPBytes + row * 128;
 #pragma unroll
-      for (int q = 0; q < 4; ++q)              // this thread's 4 chunks of 8 halves (16 B)
-        *reinterpret_cast<uint4*>(p_row + (((half * 4 + q) ^ sw) << 4)) =
+      for (int q = 0; q < 8; ++q)              // 8 chunks of 8 halves (16 B)
+        *reinterpret_cast<uint4*>(p_row + ((q ^ sw) << 4)) =
             make_uint4(sv[4 * q], sv[4 * q + 1], sv[4 * q + 2], sv[4 * q + 3]);
       fence_proxy_async_smem();
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[sb]);
     }
-    // epilogue: O / l ; the two threads of a row add their partial sums through the (now idle) K ring
+    // epilogue: O / l
     mbar_wait(&p_free[(n_tiles - 1) & 1], ((n_tiles - 1) >> 1) & 1);   // last PV done => all done
     tc_fence_after_sync();
-    float* xl = reinterpret_cast<float*>(sK);
-    xl[half * 128 + row] = l_run;
-    pair_sync();
-    const float inv = 1.0f / (l_run + xl[(half ^ 1) * 128 + row]);
+    const float inv = 1.0f / l_run;
     const int q = q0 + row;
-    uint32_t r[32];
-    tmem_ld_32x32b_x32(tmem_O + lane_addr + half * 32, r);
-    tmem_ld_wait();
-    if (q < p.seq_q) {
-      __half* op = p.out + ((long long)b * p.seq_q + q) * p.ldo + p.o_col0 + head * HD + half * 32;
+    __half* op = p.out + ((long long)b * p.seq_q + (q < p.seq_q ? q : 0)) * p.ldo + p.o_col0 + head * HD;
 #pragma unroll
-      for (int i = 0; i < 32; i += 8) {
-        *reinterpret_cast<uint4*>(op + i) = make_uint4(
-            pack_half2(__uint_as_float(r[i]) * inv, __uint_as_float(r[i + 1]) * inv),
-            pack_half2(__uint_as_float(r[i + 2]) * inv, __uint_as_float(r[i + 3]) * inv),
-            pack_half2(__uint_as_float(r[i + 4]) * inv, __uint_as_float(r[i + 5]) * inv),
-            pack_half2(__uint_as_float(r[i + 6]) * inv, __uint_as_float(r[i + 7]) * inv));
+    for (int c = 0; c < HD; c += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tmem_O + lane_addr + c, r);
+      tmem_ld_wait();
+      if (q < p.seq_q) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          *reinterpret_cast<uint4*>(op + c + i) = make_uint4(
+              pack_half2(__uint_as_float(r[i]) * inv, __uint_as_float(r[i + 1]) * inv),
+              pack_half2(__uint_as_float(r[i + 2]) * inv, __uint_as_float(r[i + 3]) * inv),
+              pack_half2(__uint_as_float(r[i + 4]) * inv, __uint_as_float(r[i + 5]) * inv),
+              pack_half2(__uint_as_float(r[i + 6]) * inv, __uint_as_float(r[i + 7]) * inv));
+        }
       }
     }
   }
@@ -355,7 +347,7 @@ extern "C" int udb_attention_f16(const udb_attn_t* a, void* stream) {
   p.ldo = a->ldo; p.o_col0 = a->o_col0;
   p.q_col0 = a->q_col0; p.k_col0 = a->k_col0; p.v_col0 = a->v_col0;
   p.scale_log2 = a->scale * 1.4426950408889634f;
-  constexpr int smem_bytes = 16384 + 2 * AT_KV_STAGES * 8192 + 2 * 16384 + 256 + 1024;
+  constexpr int smem_bytes = 16384 + 2 * AT_KV_STAGES * 8192 + 2 * 16384 + 256;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
@@ -363,6 +355,8 @@ extern "C" int udb_attention_f16(const udb_attn_t* a, void* stream) {
     attr_set = true;
   }
   dim3 grid((a->seq_q + AT_BQ - 1) / AT_BQ, a->heads, a->B);
-  attn_fwd_kernel<HD><<<grid, AT_THREADS, smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
+  cudaError_t e = launch_ex(attn_fwd_kernel<HD>, grid, dim3(AT_THREADS), smem_bytes, reinterpret_cast<cudaStream_t>(stream), 1,
+                            tq, tk, tv, p);
+  if (e != cudaSuccess) { set_error("attn_fwd_kernel launch: %s", cudaGetErrorString(e)); return 1; }
   return check_launch("attn_fwd_kernel");
 }

@@ -1,6 +1,7 @@
 #include "common.h"
 
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace udb {
@@ -24,6 +25,14 @@ int num_sms() {
     if (n <= 0) n = 148;
   }
   return n;
+}
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("UDB_PDL");
+    return e ? atoi(e) != 0 : true;
+  }();
+  return on;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,

@@ -26,6 +26,37 @@ inline int check_launch(const char* what) {
 
 int num_sms();
 
+// UDB_PDL=0 disables programmatic dependent launch (default on)
+bool pdl_enabled();
+
+// Launch with optional cluster dimension and the programmatic-stream-serialization attribute.
+template <typename Kernel, typename... Args>
+inline cudaError_t launch_ex(Kernel kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x,
+                             Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda).
 // dims/strides innermost first; strides_bytes has rank-1 entries (stride of dim 1..rank-1).
 int make_tmap_f16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,

@@ -23,6 +23,8 @@ template <bool IN_F32, bool OUT_F32>
 __global__ void __launch_bounds__(256) layernorm_kernel(const udb_layernorm_t p) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  pdl_wait();
   if (row >= p.rows) return;
   long long irow = row;
   if (p.rows_per_group > 0)
@@ -528,10 +530,12 @@ extern "C" int udb_layernorm(const udb_layernorm_t* p, void* stream) {
   if (p->dim % 128 != 0 || p->dim > 1024) { set_error("udb_layernorm: dim %d unsupported (multiple of 128, <= 1024)", p->dim); return 1; }
   const int grid = (p->rows + 7) / 8;
   if (grid == 0) return 0;
-  if (p->in_f32 && p->out_f32) layernorm_kernel<true, true><<<grid, 256, 0, ST(stream)>>>(*p);
-  else if (p->in_f32) layernorm_kernel<true, false><<<grid, 256, 0, ST(stream)>>>(*p);
-  else if (p->out_f32) layernorm_kernel<false, true><<<grid, 256, 0, ST(stream)>>>(*p);
-  else layernorm_kernel<false, false><<<grid, 256, 0, ST(stream)>>>(*p);
+  cudaError_t e;
+  if (p->in_f32 && p->out_f32) e = launch_ex(layernorm_kernel<true, true>, dim3(grid), dim3(256), 0, ST(stream), 1, *p);
+  else if (p->in_f32) e = launch_ex(layernorm_kernel<true, false>, dim3(grid), dim3(256), 0, ST(stream), 1, *p);
+  else if (p->out_f32) e = launch_ex(layernorm_kernel<false, true>, dim3(grid), dim3(256), 0, ST(stream), 1, *p);
+  else e = launch_ex(layernorm_kernel<false, false>, dim3(grid), dim3(256), 0, ST(stream), 1, *p);
+  if (e != cudaSuccess) { set_error("layernorm_kernel launch: %s", cudaGetErrorString(e)); return 1; }
   return check_launch("layernorm_kernel");
 }
 

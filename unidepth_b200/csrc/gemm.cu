@@ -275,6 +275,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
 
   if (warp == 0 && lane == 0) {
     if (smem_u32(smem) & 1023) __trap();   // 128B-swizzle atoms need a 1024 B aligned base
@@ -297,6 +298,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();   // everything above overlapped the previous kernel's tail
 
   const int num_tiles = p.tiles_m * p.tiles_n;
 
@@ -415,7 +417,11 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   }
   const int tiles = a.tiles_m * a.tiles_n;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_f16_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, a);
+  cudaError_t e = launch_ex(gemm_f16_kernel<BN>, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, st, 1, tmA, tmB, a);
+  if (e != cudaSuccess) {
+    set_error("gemm_f16_kernel launch: %s", cudaGetErrorString(e));
+    return 1;
+  }
   return check_launch("gemm_f16_kernel");
 }
 
@@ -460,6 +466,7 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const bool leader = rank == 0;
   const int pair = blockIdx.x >> 1;
   const int num_pairs = gridDim.x >> 1;
+  pdl_launch_dependents();
 
   if (warp == 0 && lane == 0) {
     if (smem_u32(smem) & 1023) __trap();
@@ -482,6 +489,7 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   cluster_sync_all();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();   // everything above overlapped the previous kernel's tail
 
   const int tiles_m2 = (p.tiles_m + 1) >> 1;       // 256-row (two 128-row blocks) tiles
   const int num_tiles = tiles_m2 * p.tiles_n;
@@ -600,19 +608,7 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ge
   const int tiles = ((a.tiles_m + 1) / 2) * a.tiles_n;
   const int max_pairs = num_sms() / 2;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(2 * pairs);
-  cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm2_f16_kernel<BN>, tmA, tmB, a);
+  cudaError_t e = launch_ex(gemm2_f16_kernel<BN>, dim3(2 * pairs), dim3(kThreads), Cfg::kSmemBytes, st, 2, tmA, tmB, a);
   if (e != cudaSuccess) {
     set_error("gemm2_f16_kernel launch: %s", cudaGetErrorString(e));
     return 1;

@@ -90,6 +90,28 @@ typedef struct udb_gemm_t {
 int udb_gemm_f16(const udb_gemm_t* g, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * 3x3 convolution with few output channels over a PRE-PADDED NHWC f16 image [B, H+2, W+2, cstride]
+ * (channel slice [coff, coff+C)), weights f16 [Cout, 9*C] ordered (dy,dx,c), Cout in {32, 64}.
+ * The input halo of each 16x8-pixel tile is loaded once and shared by the nine taps (shifted UMMA
+ * descriptors); weights stay resident in shared memory.  out: f16 NHWC [B,H,W,ldc] -- or, with
+ * head_out != NULL (Cout == 32), the fused head exp(clamp(sum_n head_w[n]*act(conv)[n] + head_b,
+ * -8, 8) + head_add) as an f32 plane [B,H,W].  Replaces the reflect-padded nn.Conv2d calls of
+ * unidepth/models/unidepthv2/decoder.py:200-229 (to_depth_lr/hr, to_confidence_lr/hr).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct udb_conv_halo_t {
+  const void* x;
+  const void* w;
+  const float* bias;
+  int32_t B, H, W, C, cstride, coff, cout, act;
+  void* out;
+  int64_t ldc;
+  const float* head_w;
+  float head_b, head_add;
+  float* head_out;
+} udb_conv_halo_t;
+int udb_conv3x3_halo_f16(const udb_conv_halo_t* c, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Fused softmax(Q K^T / sqrt(d)) V  (flash-style, tcgen05 QK^T and PV, S/O accumulators in TMEM).
  * Replaces F.scaled_dot_product_attention: metadinov2/attention.py:58, layers/attention.py:136.
  * q/k/v are f16 matrices with row stride ld* (elements); head h occupies columns

@@ -164,3 +164,27 @@ def test_padded_linear_border_fill_and_channel_slice_conv():
         out = ops.conv3x3(mp, wp, bias=bc, prepadded=True, out_dtype=torch.float32, c_off=128 * i, c_used=128)
         ref = F.conv2d(mp.float().permute(0, 3, 1, 2)[:, 128 * i:128 * (i + 1)], wc.float(), bc).permute(0, 2, 3, 1)
         _close(out, ref, 3e-5, f"conv3x3 channel slice {i}")
+
+
+@pytest.mark.parametrize("C,N,H,W", [(64, 32, 37, 50), (128, 64, 40, 21), (64, 32, 490, 644)])
+def test_conv3x3_halo(C, N, H, W):
+    """Halo-reuse conv kernel (shifted UMMA descriptors) vs F.conv2d on the reflect-padded input."""
+    from unidepth_b200 import ops
+    dev = _dev()
+    torch.manual_seed(5)
+    B = 2
+    x = torch.randn(B, C, H, W, device=dev).half()
+    w = (torch.randn(N, C, 3, 3, device=dev) / (9 * C) ** 0.5).half()
+    bias = torch.randn(N, device=dev)
+    xp = F.pad(x.float(), (1, 1, 1, 1), mode="reflect")
+    ref = F.conv2d(xp, w.float(), bias)
+    xpad = xp.permute(0, 2, 3, 1).contiguous().half()
+    wp = w.permute(0, 2, 3, 1).reshape(N, 9 * C).contiguous()
+    if N == 64:
+        out = ops.conv3x3_halo(xpad, wp, bias=bias)
+        _close(out, ref.permute(0, 2, 3, 1), 1.5e-3, f"halo conv {C}->{N}")
+    else:
+        hw = torch.randn(32, device=dev) * 0.3
+        head = ops.conv3x3_halo(xpad, wp, bias=bias, act=ops.ACT_LEAKY, head_w=hw, head_b=0.1, head_add=2.0)
+        hr = torch.exp((F.leaky_relu(ref, 0.01) * hw.view(1, -1, 1, 1)).sum(1).add(0.1).clip(-8, 8) + 2.0)
+        _close(head, hr, 3e-5, f"halo conv head {C}->{N} {H}x{W}")

@@ -36,10 +36,10 @@ def test_library_exports_every_header_symbol():
 
 def test_ctypes_structs_match_c_layout():
     from unidepth_b200 import _cabi
-    structs = {"udb_gemm_t": _cabi.Gemm, "udb_attn_t": _cabi.Attn, "udb_layernorm_t": _cabi.LayerNorm,
+    structs = {"udb_gemm_t": _cabi.Gemm, "udb_conv_halo_t": _cabi.ConvHalo, "udb_attn_t": _cabi.Attn, "udb_layernorm_t": _cabi.LayerNorm,
                "udb_preprocess_t": _cabi.Preprocess, "udb_small_linear_t": _cabi.SmallLinear,
                "udb_ray_embed_t": _cabi.RayEmbed, "udb_postprocess_t": _cabi.Postprocess}
-    last = {"udb_gemm_t": "head_add", "udb_attn_t": "scale", "udb_layernorm_t": "eps", "udb_preprocess_t": "ldp",
+    last = {"udb_gemm_t": "head_add", "udb_conv_halo_t": "head_out", "udb_attn_t": "scale", "udb_layernorm_t": "eps", "udb_preprocess_t": "ldp",
             "udb_small_linear_t": "ldr", "udb_ray_embed_t": "out_f32", "udb_postprocess_t": "out_rays"}
     src = '#include <stdio.h>\n#include <stddef.h>\n#include "udb.h"\nint main(){\n'
     for n in structs:

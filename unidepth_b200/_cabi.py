@@ -32,6 +32,14 @@ class Gemm(C.Structure):
     ]
 
 
+class ConvHalo(C.Structure):
+    _fields_ = [
+        ("x", vp), ("w", vp), ("bias", vp),
+        ("B", i32), ("H", i32), ("W", i32), ("C", i32), ("cstride", i32), ("coff", i32), ("cout", i32), ("act", i32),
+        ("out", vp), ("ldc", i64), ("head_w", vp), ("head_b", f32), ("head_add", f32), ("head_out", vp),
+    ]
+
+
 class Attn(C.Structure):
     _fields_ = [
         ("q", vp), ("k", vp), ("v", vp), ("out", vp),
@@ -86,6 +94,7 @@ EXPORTS = {
     "udb_last_error": (C.c_char_p, []),
     "udb_launch_count": (i64, []),
     "udb_gemm_f16": (i32, [C.POINTER(Gemm), vp]),
+    "udb_conv3x3_halo_f16": (i32, [C.POINTER(ConvHalo), vp]),
     "udb_attention_f16": (i32, [C.POINTER(Attn), vp]),
     "udb_layernorm": (i32, [C.POINTER(LayerNorm), vp]),
     "udb_preprocess_patchify": (i32, [C.POINTER(Preprocess), vp]),

@@ -120,6 +120,31 @@ def conv3x3(x: torch.Tensor, w: torch.Tensor, *, bias=None, act=ACT_NONE, gamma=
     return out
 
 
+def conv3x3_halo(x: torch.Tensor, w: torch.Tensor, *, bias, act=ACT_NONE, c_off=0, c_used=None, out=None,
+                 head_w=None, head_b=0.0, head_add=0.0):
+    """3x3 conv over a pre-padded NHWC f16 image x [B,H+2,W+2,Ctot] (channel slice), w [Cout, 9*C],
+    Cout in {32, 64}, halo-reuse kernel.  Returns f16 [B,H,W,Cout] or (head_w given) f32 [B,H,W]."""
+    assert x.dtype == f16 and w.dtype == f16 and x.is_contiguous() and w.is_contiguous()
+    B, PH, PW, Ctot = x.shape
+    Cin = c_used if c_used is not None else Ctot
+    H, W, N = PH - 2, PW - 2, w.shape[0]
+    assert w.shape[1] == 9 * Cin
+    c = cabi.ConvHalo()
+    c.x, c.w, c.bias = _ptr(x), _ptr(w), _ptr(bias)
+    c.B, c.H, c.W, c.C, c.cstride, c.coff, c.cout, c.act = B, H, W, Cin, Ctot, c_off, N, act
+    if head_w is not None:
+        if out is None:
+            out = torch.empty((B, H, W), device=x.device, dtype=f32)
+        c.head_w, c.head_b, c.head_add, c.head_out = _ptr(head_w), float(head_b), float(head_add), _ptr(out)
+    else:
+        if out is None:
+            out = torch.empty((B, H, W, N), device=x.device, dtype=f16)
+        c.out, c.ldc = _ptr(out), out.stride(2)
+    cabi.check(_launch("conv3x3_halo_kernel", 2.0 * B * H * W * N * 9 * Cin,
+                       lambda: cabi.lib().udb_conv3x3_halo_f16(C.byref(c), _stream())), "udb_conv3x3_halo_f16")
+    return out
+
+
 def conv_transpose_ks(x: torch.Tensor, w: torch.Tensor, k: int, cout: int, grid_hw, *, bias=None,
                       resid=None, out: Optional[torch.Tensor] = None, out_dtype=f16, out2=None, out2_leaky=True,
                       pad=0):

@@ -78,6 +78,21 @@ def bench_conv():
             print(f"   + gamma, f32 residual in place, f16 leaky copy: {ms:.3f} ms  {fl/ms/1e9:.1f} TFLOP/s", flush=True)
 
 
+def bench_halo():
+    import torch.nn.functional as F
+    for (B, H, W, C, N) in [(8, 280, 368, 128, 64), (8, 490, 644, 64, 32)]:
+        x = torch.randn(B, H + 2, W + 2, C, device=dev).half()
+        w = torch.randn(N, 9 * C, device=dev).half()
+        bias = torch.randn(N, device=dev)
+        fl = 2 * B * H * W * N * 9 * C
+        if N == 64:
+            ms = timeit(lambda: ops.conv3x3_halo(x, w, bias=bias))
+        else:
+            hw = torch.randn(32, device=dev)
+            ms = timeit(lambda: ops.conv3x3_halo(x, w, bias=bias, act=ops.ACT_LEAKY, head_w=hw))
+        print(f"conv3x3 halo {B}x{H}x{W}x{C}->{N}: {ms:.3f} ms  {fl/ms/1e9:.1f} TFLOP/s", flush=True)
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("gemm", "all"):
@@ -86,3 +101,4 @@ if __name__ == "__main__":
         bench_attn()
     if what in ("conv", "all"):
         bench_conv()
+        bench_halo()

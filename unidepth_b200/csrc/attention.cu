@@ -1,16 +1,16 @@
 // Fused attention forward for sm_100a:  O = softmax(Q K^T * scale) V   (no mask, no dropout)
 //
 // One CTA = one (batch, head, 128-query tile); two CTAs are resident per SM (TMEM 2 x 256 columns,
-// <= 113 KB shared memory each).  Keys are processed in tiles of 64:
-//   warp 0      : TMA producer (Q once; K_j / V_j tiles through two independent 4-stage rings)
-//   warp 1      : TMEM allocator + MMA issuer.  S_j = Q K_j^T (M128 N64 K64) goes to one of TWO score
-//                 buffers in TMEM and is issued two tiles ahead, so the scores of tile j+1 are ready
-//                 while the softmax warps are still busy with tile j; O += P_j V_j (M128 N64 K64, V is
-//                 the MN-major B operand) accumulates in TMEM.
-//   warps 2..5  : softmax, one query row per thread: S_j from TMEM (tcgen05.ld), row max / sum in fp32
-//                 with packed f32x2 math, P_j as f16 into one of two 128B-swizzled smem buffers.
-//                 O is rescaled lazily: only when a row maximum grows by more than 2^8 over the
-//                 reference the probabilities are expressed against (tcgen05.ld -> mul -> tcgen05.st).
+// <= 113 KB shared memory each).  Keys are processed in tiles of 128:
+//   warp 0      : TMA producer (Q once; K_j / V_j tiles through two independent 2-stage rings)
+//   warp 1      : TMEM allocator + MMA issuer.  S_j = Q K_j^T (M128 N128 K64) into TMEM; the softmax
+//                 warps copy the whole score row to registers first thing and release the buffer, so
+//                 S_{j+1} is computed while they work on tile j.  O += P_j V_j (M128 N64 K128, V is the
+//                 MN-major B operand) accumulates in TMEM.
+//   warps 2..5  : softmax, one query row per thread, 128 scores in registers: row max / sum in fp32
+//                 with packed f32x2 math, half of the exp2 on the FMA pipe (polynomial), P_j as f16
+//                 into 128B-swizzled shared memory.  O is rescaled lazily: only when a row maximum
+//                 grows by more than 2^8 over the reference the probabilities are expressed against.
 // Replaces F.scaled_dot_product_attention (reference: metadinov2/attention.py:58,
 // layers/attention.py:136).
 #include "common.h"
@@ -19,8 +19,8 @@
 namespace udb {
 
 constexpr int AT_BQ = 128;       // queries per CTA
-constexpr int AT_BK = 64;        // keys per tile
-constexpr int AT_KV_STAGES = 4;  // per ring
+constexpr int AT_BK = 128;       // keys per tile
+constexpr int AT_KV_STAGES = 2;  // per ring
 constexpr int AT_THREADS = 192;  // TMA warp, MMA warp, 4 softmax warps
 
 struct AttnArgs {
@@ -55,8 +55,8 @@ __device__ __forceinline__ void exp2_poly_pair(const uint64_t x2, float& e0, flo
   e1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
 }
 
-// exp2(s*scale - m) for 64 scores of one row; returns the row sum; P (f16) packed in place into
-// sv[0..31].  MASK: only the first kv_left entries are valid keys (last tile).  The MUFU unit
+// exp2(s*scale - m) for the 128 scores of one row; returns the row sum; P (f16) packed in place into
+// sv[0..63].  MASK: only the first kv_left entries are valid keys (last tile).  The MUFU unit
 // (16 ex2 / clk / SM) is the bottleneck of d=64 attention, so every second pair of elements is
 // computed with the polynomial instead.
 template <bool MASK>
@@ -111,25 +111,26 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 const __grid_constant__ CUtensorMap tmV, const AttnArgs p) {
   static_assert(HD == 64, "head_dim 64 only");
   constexpr int kQBytes = AT_BQ * HD * 2;      // 16 KB
-  constexpr int kKBytes = AT_BK * HD * 2;      // 8 KB
-  constexpr int kPBytes = AT_BQ * AT_BK * 2;   // 16 KB per buffer
-  constexpr uint32_t kTmemCols = 256;          // S0: [0,64)  S1: [64,128)  O: [128,192)
+  constexpr int kKBytes = AT_BK * HD * 2;      // 16 KB
+  constexpr int kPBytes = AT_BQ * AT_BK * 2;   // 32 KB (two 64-key sub-tiles of 16 KB)
+  constexpr uint32_t kTmemCols = 256;          // S: [0,128)  O: [128,192)
   constexpr int NS = AT_KV_STAGES;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + kQBytes;                  // NS stages
   uint8_t* sV = sK + NS * kKBytes;             // NS stages
-  uint8_t* sP = sV + NS * kKBytes;             // 2 buffers
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kPBytes);
+  uint8_t* sP = sV + NS * kKBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + kPBytes);
   uint64_t* q_full = bars;
   uint64_t* k_full = bars + 1;             // [NS]
   uint64_t* v_full = k_full + NS;          // [NS]
   uint64_t* k_empty = v_full + NS;         // [NS]  K stage free once its QK MMA has completed
   uint64_t* v_empty = k_empty + NS;        // [NS]  V stage free once its PV MMA has completed
-  uint64_t* s_full = v_empty + NS;         // [2]
-  uint64_t* p_full = s_full + 2;           // [2]
-  uint64_t* p_free = p_full + 2;           // [2]  PV MMA of the tile that used P buffer / parity slot done
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(p_free + 2);
+  uint64_t* s_full = v_empty + NS;         // S_j complete in TMEM
+  uint64_t* s_free = s_full + 1;           // S_j copied to registers by all softmax warps
+  uint64_t* p_full = s_free + 1;           // P_j written to smem
+  uint64_t* p_free = p_full + 1;           // PV_j MMA done (one phase per tile)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(p_free + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -151,11 +152,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(&k_empty[i], 1);
       mbar_init(&v_empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 4);
-      mbar_init(&p_free[i], 1);
-    }
+    mbar_init(s_full, 1);
+    mbar_init(s_free, 4);
+    mbar_init(p_full, 4);
+    mbar_init(p_free, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<kTmemCols>(tmem_ptr);
@@ -186,33 +186,36 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       constexpr uint32_t idesc_qk = umma_idesc_f16(AT_BQ, AT_BK, false, false);
       constexpr uint32_t idesc_pv = umma_idesc_f16(AT_BQ, HD, false, true);   // B = V is MN-major
       const uint64_t dq = umma_desc_sw128(smem_u32(sQ), 16, 1024);
-      auto issue_qk = [&](int j) {   // S[j&1] = Q K_j^T
+      auto issue_qk = [&](int j) {   // S = Q K_j^T
         const int st = j % NS;
         mbar_wait(&k_full[st], (j / NS) & 1);
         tc_fence_after_sync();
         const uint64_t dk = umma_desc_sw128(smem_u32(sK + st * kKBytes), 16, 1024);
-        const uint32_t d = tmem_base + (j & 1) * AT_BK;
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k) umma_f16_ss(d, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0);
+        for (int k = 0; k < HD / 16; ++k) umma_f16_ss(tmem_base, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0);
         umma_commit(&k_empty[st]);
-        umma_commit(&s_full[j & 1]);
+        umma_commit(s_full);
       };
       mbar_wait(q_full, 0);
       issue_qk(0);
-      if (n_tiles > 1) issue_qk(1);
       for (int j = 0; j < n_tiles; ++j) {
         const int st = j % NS;
-        mbar_wait(&p_full[j & 1], (j >> 1) & 1);   // P_j written; S[j&1] fully consumed
+        if (j + 1 < n_tiles) {
+          mbar_wait(s_free, j & 1);                // score row of tile j is in registers: S may be overwritten
+          issue_qk(j + 1);
+        }
+        mbar_wait(p_full, j & 1);                  // P_j written
         mbar_wait(&v_full[st], (j / NS) & 1);
         tc_fence_after_sync();
-        const uint64_t dp = umma_desc_sw128(smem_u32(sP + (j & 1) * kPBytes), 16, 1024);
         const uint64_t dv = umma_desc_sw128(smem_u32(sV + st * kKBytes), 1024, 1024);
 #pragma unroll
-        for (int ks = 0; ks < AT_BK / 16; ++ks)   // A = P: 32 B per 16-key step; B = V: 16 key rows = 2 KB per step
-          umma_f16_ss(tmem_O, dp + 2 * ks, dv + (uint64_t)(ks * 2048 >> 4), idesc_pv, (j | ks) != 0);
+        for (int ks = 0; ks < AT_BK / 16; ++ks) {
+          // A = P: sub-tile (ks/4) of 16 KB, 32 B per 16-key step inside the swizzle atom; B = V: 2 KB per step
+          const uint64_t dp = umma_desc_sw128(smem_u32(sP + (ks >> 2) * (kPBytes / 2)), 16, 1024) + 2 * (ks & 3);
+          umma_f16_ss(tmem_O, dp, dv + (uint64_t)(ks * 2048 >> 4), idesc_pv, (j | ks) != 0);
+        }
         umma_commit(&v_empty[st]);
-        umma_commit(&p_free[j & 1]);
-        if (j + 2 < n_tiles) issue_qk(j + 2);
+        umma_commit(p_free);
       }
     }
   } else {
@@ -226,8 +229,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     constexpr float kRescaleThreshold = 8.0f;   // log2 domain
 
     for (int j = 0; j < n_tiles; ++j) {
-      const int sb = j & 1;
-      mbar_wait(&s_full[sb], (j >> 1) & 1);
+      mbar_wait(s_full, j & 1);
       tc_fence_after_sync();
       const int kv_left = p.seq_k - j * AT_BK;   // valid keys in this tile (>= 1)
       const bool full = kv_left >= AT_BK;
@@ -235,10 +237,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       {
         uint32_t(&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[0]);
         uint32_t(&s1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[32]);
-        tmem_ld_32x32b_x32(tmem_base + lane_addr + sb * AT_BK, s0);
-        tmem_ld_32x32b_x32(tmem_base + lane_addr + sb * AT_BK + 32, s1);
+        uint32_t(&s2)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[64]);
+        uint32_t(&s3)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[96]);
+        tmem_ld_32x32b_x32(tmem_base + lane_addr, s0);
+        tmem_ld_32x32b_x32(tmem_base + lane_addr + 32, s1);
+        tmem_ld_32x32b_x32(tmem_base + lane_addr + 64, s2);
+        tmem_ld_32x32b_x32(tmem_base + lane_addr + 96, s3);
         tmem_ld_wait();
       }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_free);        // the MMA warp may now compute S_{j+1}
       const float m_tile = (full ? row_max<false>(sv, kv_left) : row_max<true>(sv, kv_left)) * sc;
       const bool need = m_tile > m_used + kRescaleThreshold;   // always true on the first tile
       float alpha = 1.0f;
@@ -246,14 +255,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         alpha = ex2(m_used - m_tile);      // 0 on the first tile
         m_used = m_tile;
       }
-      // P buffer sb was last read by the PV MMA of tile j-2 = phase (j>>1)-1 of p_free[sb]; the next
-      // completion of that barrier (tile j) needs this thread's own arrival, so the parity is unambiguous
-      if (j >= 2) mbar_wait(&p_free[sb], ((j >> 1) & 1) ^ 1);
+      bool pv_done = false;
       if (j > 0 && __any_sync(0xffffffffu, need)) {
-        // rare: rescale this warp's 32 rows of O (rows that do not need it multiply by 1);
-        // needs every PV MMA issued so far (tile j-1 is the latest) to have completed
-        mbar_wait(&p_free[(j - 1) & 1], ((j - 1) >> 1) & 1);
+        // rare: rescale this warp's 32 rows of O (rows that do not need it multiply by 1)
+        mbar_wait(p_free, (j - 1) & 1);
         tc_fence_after_sync();
+        pv_done = true;
         const uint64_t a2 = pack2(alpha, alpha);
 #pragma unroll 1
         for (int c = 0; c < HD; c += 16) {
@@ -273,18 +280,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       const float psum = full ? softmax_row<false>(sv, sc, m_used, kv_left) : softmax_row<true>(sv, sc, m_used, kv_left);
       l_run = fmaf(l_run, alpha, psum);
-      uint8_t* p_row = sP + sb * kPBytes + row * 128;
+      // the PV MMA of tile j-1 must have finished reading sP (the next completion of p_free needs
+      // this thread's own arrival on p_full, so the parity is unambiguous)
+      if (j > 0 && !pv_done) mbar_wait(p_free, (j - 1) & 1);
+      uint8_t* p_row = sP + row * 128;
 #pragma unroll
-      for (int q = 0; q < 8; ++q)              // 8 chunks of 8 halves (16 B)
-        *reinterpret_cast<uint4*>(p_row + ((q ^ sw) << 4)) =
+      for (int q = 0; q < 16; ++q)             // 16 chunks of 8 halves (16 B): two 64-key sub-tiles
+        *reinterpret_cast<uint4*>(p_row + (q >> 3) * (kPBytes / 2) + (((q & 7) ^ sw) << 4)) =
             make_uint4(sv[4 * q], sv[4 * q + 1], sv[4 * q + 2], sv[4 * q + 3]);
       fence_proxy_async_smem();
       tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[sb]);
+      if (lane == 0) mbar_arrive(p_full);
     }
     // epilogue: O / l
-    mbar_wait(&p_free[(n_tiles - 1) & 1], ((n_tiles - 1) >> 1) & 1);   // last PV done => all done
+    mbar_wait(p_free, (n_tiles - 1) & 1);   // last PV done => all done
     tc_fence_after_sync();
     const float inv = 1.0f / l_run;
     const int q = q0 + row;
@@ -347,7 +357,7 @@ extern "C" int udb_attention_f16(const udb_attn_t* a, void* stream) {
   p.ldo = a->ldo; p.o_col0 = a->o_col0;
   p.q_col0 = a->q_col0; p.k_col0 = a->k_col0; p.v_col0 = a->v_col0;
   p.scale_log2 = a->scale * 1.4426950408889634f;
-  constexpr int smem_bytes = 16384 + 2 * AT_KV_STAGES * 8192 + 2 * 16384 + 256;
+  constexpr int smem_bytes = 16384 + 2 * AT_KV_STAGES * 16384 + 32768 + 256;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);

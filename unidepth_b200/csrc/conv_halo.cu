@@ -207,7 +207,11 @@ extern "C" int udb_conv3x3_halo_f16(const udb_conv_halo_t* c, void* stream) {
   a.slabs = c->C / 64; a.coff = c->coff;
   a.tiles_x = (c->W + HC_TW - 1) / HC_TW; a.tiles_y = (c->H + HC_TH - 1) / HC_TH;
   a.num_tiles = c->B * a.tiles_x * a.tiles_y;
-  static const int mode = [] { const char* e = getenv("UDB_HALO_BASEOFF"); return e ? atoi(e) : 1; }();
+  // Measured on B200: the UMMA 128B swizzle is a function of the absolute shared-memory address bits
+  // (like TMA's), so a descriptor that starts dx pixel-rows into the 8-row pattern needs NO
+  // base_offset; UDB_HALO_BASEOFF=1 (descriptor base_offset = dx) gives wrong results and is kept
+  // only as the recorded experiment.
+  static const int mode = [] { const char* e = getenv("UDB_HALO_BASEOFF"); return e ? atoi(e) : 0; }();
   a.base_off_mode = mode;
   a.bias = c->bias; a.act = c->act;
   a.out = reinterpret_cast<__half*>(c->out); a.ldc = c->ldc > 0 ? c->ldc : c->cout;

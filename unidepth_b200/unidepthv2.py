@@ -388,10 +388,11 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
         ops.reflect_border_fill(mp)
         planes = []
         for i, hd in enumerate(P["heads"]):
-            lr = ops.conv3x3(mp, hd["lr_w"], bias=hd["lr_b"], prepadded=True, c_off=i * (n_mlp // 2), c_used=n_mlp // 2)
+            # small-Cout convs: halo-reuse kernel (input tile loaded once for the nine taps)
+            lr = ops.conv3x3_halo(mp, hd["lr_w"], bias=hd["lr_b"], c_off=i * (n_mlp // 2), c_used=n_mlp // 2)
             up = ops.resize_ac_pad(lr, nh, nw, 1)
-            planes.append(ops.conv3x3(up, hd["hr_w"], bias=hd["hr_b"], prepadded=True, act=ops.ACT_LEAKY,
-                                      head_w=hd["head_w"], head_b=hd["head_b"], head_add=hd["add"]))
+            planes.append(ops.conv3x3_halo(up, hd["hr_w"], bias=hd["hr_b"], act=ops.ACT_LEAKY,
+                                           head_w=hd["head_w"], head_b=hd["head_b"], head_add=hd["add"]))
         radius, confidence = planes
         if taps is not None:
             taps["radius_net"] = radius.clone()

@@ -247,7 +247,7 @@ def main():
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "gemm_traffic.json")
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath))
+            traffic = json.load(open(tpath)).get("bytes_per_launch_avg")   # ncu capture of the 4 encoder GEMM flavours
         roof = {"bound": "tensor", "kernel": "gemm_f16_kernel / gemm2_f16_kernel (linear + conv3x3 + convT launches)",
                 "achieved": round(ach, 1), "peak": sustained, "unit": "TFLOP/s", "frac": round(ach / sustained, 4),
                 "peak_source": f"{how} bf16_tflops_sustained (MEASURED_PEAKS.json)", "traffic": traffic,

@@ -160,3 +160,23 @@ def test_full_vitl_480x640():
     m = _model(cfg, sd)
     out = m.infer(rgb)
     _check(out, ref)
+
+
+@pytest.mark.parametrize("name", ["vits_120x160", "vits_pad_96x288_rl3"])
+def test_vits_against_reference_golden(name):
+    """CUDA path vs outputs of the UNMODIFIED reference (tests/golden/*.npz, made by
+    oracle/make_golden.py from /root/reference): UniDepthV2 ViT-S/14, the reference's own config."""
+    import numpy as np
+    from fixture import make_state_dict
+    z = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+    meta = json.loads(str(z["__meta__"]))
+    cfg = json.load(open(os.path.join(ROOT, "tests", "golden", meta["config"])))
+    sd = make_state_dict(cfg, meta["seed"])
+    m = _model(cfg, sd)
+    if meta["resolution_level"] is not None:
+        m.resolution_level = meta["resolution_level"]
+    out = m.infer(_rgb(meta["shape"], meta["seed"]))
+    ref = {k: torch.from_numpy(z[k]) for k in z.files if k != "__meta__"}
+    out = dict(out)
+    out["depth_features"] = out["depth_features"][:, ::4]      # the fixture keeps every 4th channel
+    _check(out, ref)

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libudb.so")
+LIB_PATH = os.environ.get("UDB_LIB", os.path.join(_HERE, "libudb.so"))   # UDB_LIB: alternative build (experiments)
 
 A_MATRIX, A_CONV3X3 = 0, 1
 ACT_NONE, ACT_GELU, ACT_LEAKY = 0, 1, 2

@@ -8,7 +8,7 @@
 //                 S_{j+1} is computed while they work on tile j.  O += P_j V_j (M128 N64 K128, V is the
 //                 MN-major B operand) accumulates in TMEM.
 //   warps 2..5  : softmax, one query row per thread, 128 scores in registers: row max / sum in fp32
-//                 with packed f32x2 math, half of the exp2 on the FMA pipe (polynomial), P_j as f16
+//                 with packed f32x2 math (optional FMA-pipe polynomial exp2, off by default), P_j as f16
 //                 into 128B-swizzled shared memory.  O is rescaled lazily: only when a row maximum
 //                 grows by more than 2^8 over the reference the probabilities are expressed against.
 // Replaces F.scaled_dot_product_attention (reference: metadinov2/attention.py:58,
@@ -16,10 +16,22 @@
 #include "common.h"
 #include "ptx.cuh"
 
+// every UDB_ATTN_POLY-th pair of probabilities uses the FMA-pipe polynomial exp2 (0 = never).
+// Measured on B200 (8x16x1611^2): POLY 0: 162 us, 4: 174 us, 2: 180 us -- the kernel is issue /
+// latency bound (2 softmax warps per SM sub-partition), not MUFU bound, so the extra FMA-pipe
+// instructions cost more than the MUFU work they save; kept as a compile-time option.
+#ifndef UDB_ATTN_POLY
+#define UDB_ATTN_POLY 0
+#endif
+
 namespace udb {
 
 constexpr int AT_BQ = 128;       // queries per CTA
-constexpr int AT_BK = 128;       // keys per tile
+#ifndef UDB_ATTN_BK
+#define UDB_ATTN_BK 128
+#endif
+constexpr int AT_BK = UDB_ATTN_BK;   // keys per tile (128: 2 CTAs/SM; 64: 3 CTAs/SM)
+constexpr int AT_CTAS_PER_SM = AT_BK == 128 ? 2 : 3;
 constexpr int AT_KV_STAGES = 2;  // per ring
 constexpr int AT_THREADS = 192;  // TMA warp, MMA warp, 4 softmax warps
 
@@ -68,7 +80,7 @@ __device__ __forceinline__ float softmax_row(uint32_t (&sv)[AT_BK], const float 
 #pragma unroll
   for (int i = 0; i < AT_BK; i += 2) {
     float e0, e1;
-    if ((i >> 1) & 1) {
+    if (UDB_ATTN_POLY > 0 && ((i >> 1) % (UDB_ATTN_POLY > 0 ? UDB_ATTN_POLY : 1)) == (UDB_ATTN_POLY > 0 ? UDB_ATTN_POLY : 1) - 1) {
       const float s0 = fmaxf(__uint_as_float(sv[i]), s_floor), s1 = fmaxf(__uint_as_float(sv[i + 1]), s_floor);
       exp2_poly_pair(fma2(pack2(s0, s1), sc2, nm2), e0, e1);
     } else {
@@ -106,14 +118,14 @@ __device__ __forceinline__ float row_max(const uint32_t (&sv)[AT_BK], const int 
 }
 
 template <int HD>
-__global__ void __launch_bounds__(AT_THREADS, 2)
+__global__ void __launch_bounds__(AT_THREADS, AT_CTAS_PER_SM)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnArgs p) {
   static_assert(HD == 64, "head_dim 64 only");
   constexpr int kQBytes = AT_BQ * HD * 2;      // 16 KB
   constexpr int kKBytes = AT_BK * HD * 2;      // 16 KB
   constexpr int kPBytes = AT_BQ * AT_BK * 2;   // 32 KB (two 64-key sub-tiles of 16 KB)
-  constexpr uint32_t kTmemCols = 256;          // S: [0,128)  O: [128,192)
+  constexpr uint32_t kTmemCols = AT_BK == 128 ? 256 : 128;   // S: [0,AT_BK)  O: [AT_BK, AT_BK+64)
   constexpr int NS = AT_KV_STAGES;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
@@ -163,7 +175,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
-  const uint32_t tmem_O = tmem_base + 128;
+  const uint32_t tmem_O = tmem_base + AT_BK;
   pdl_wait();   // everything above overlapped the previous kernel's tail
 
   if (warp == 0) {
@@ -211,7 +223,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int ks = 0; ks < AT_BK / 16; ++ks) {
           // A = P: sub-tile (ks/4) of 16 KB, 32 B per 16-key step inside the swizzle atom; B = V: 2 KB per step
-          const uint64_t dp = umma_desc_sw128(smem_u32(sP + (ks >> 2) * (kPBytes / 2)), 16, 1024) + 2 * (ks & 3);
+          const uint64_t dp = umma_desc_sw128(smem_u32(sP + (ks >> 2) * (AT_BQ * 128)), 16, 1024) + 2 * (ks & 3);
           umma_f16_ss(tmem_O, dp, dv + (uint64_t)(ks * 2048 >> 4), idesc_pv, (j | ks) != 0);
         }
         umma_commit(&v_empty[st]);
@@ -234,17 +246,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int kv_left = p.seq_k - j * AT_BK;   // valid keys in this tile (>= 1)
       const bool full = kv_left >= AT_BK;
       uint32_t sv[AT_BK];
-      {
-        uint32_t(&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[0]);
-        uint32_t(&s1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[32]);
-        uint32_t(&s2)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[64]);
-        uint32_t(&s3)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[96]);
-        tmem_ld_32x32b_x32(tmem_base + lane_addr, s0);
-        tmem_ld_32x32b_x32(tmem_base + lane_addr + 32, s1);
-        tmem_ld_32x32b_x32(tmem_base + lane_addr + 64, s2);
-        tmem_ld_32x32b_x32(tmem_base + lane_addr + 96, s3);
-        tmem_ld_wait();
-      }
+#pragma unroll
+      for (int c = 0; c < AT_BK; c += 32)
+        tmem_ld_32x32b_x32(tmem_base + lane_addr + c, *reinterpret_cast<uint32_t(*)[32]>(&sv[c]));
+      tmem_ld_wait();
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(s_free);        // the MMA warp may now compute S_{j+1}
@@ -285,8 +290,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (j > 0 && !pv_done) mbar_wait(p_free, (j - 1) & 1);
       uint8_t* p_row = sP + row * 128;
 #pragma unroll
-      for (int q = 0; q < 16; ++q)             // 16 chunks of 8 halves (16 B): two 64-key sub-tiles
-        *reinterpret_cast<uint4*>(p_row + (q >> 3) * (kPBytes / 2) + (((q & 7) ^ sw) << 4)) =
+      for (int q = 0; q < AT_BK / 8; ++q)      // chunks of 8 halves (16 B); 64-key sub-tiles of 16 KB
+        *reinterpret_cast<uint4*>(p_row + (q >> 3) * (AT_BQ * 128) + (((q & 7) ^ sw) << 4)) =
             make_uint4(sv[4 * q], sv[4 * q + 1], sv[4 * q + 2], sv[4 * q + 3]);
       fence_proxy_async_smem();
       tc_fence_before_sync();
@@ -357,7 +362,7 @@ extern "C" int udb_attention_f16(const udb_attn_t* a, void* stream) {
   p.ldo = a->ldo; p.o_col0 = a->o_col0;
   p.q_col0 = a->q_col0; p.k_col0 = a->k_col0; p.v_col0 = a->v_col0;
   p.scale_log2 = a->scale * 1.4426950408889634f;
-  constexpr int smem_bytes = 16384 + 2 * AT_KV_STAGES * 16384 + 32768 + 256;
+  constexpr int smem_bytes = 16384 + 2 * AT_KV_STAGES * (AT_BK * 128) + AT_BQ * AT_BK * 2 + 256;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);

@@ -213,46 +213,48 @@ __global__ void set_cls_rows_kernel(float* x, const float* cls, const float* pos
 }
 
 // ------------------------------------------------------------------------------------ camera head (fp32)
-// one warp per 4 output features, 8 rows per pass
+// one warp per output feature and 8 rows (the 32-row camera head is latency bound: favour many
+// small warps over reuse); lanes stride over K with 128-bit loads when K % 128 == 0
 __global__ void __launch_bounds__(128) small_linear_kernel(const udb_small_linear_t p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = (blockIdx.x * 4 + warp) * 4;
+  const int n = blockIdx.x * 4 + warp;
   const int m0 = blockIdx.y * 8;
-  if (n0 >= p.N) return;
+  if (n >= p.N) return;
   const long long ldx = p.ldx > 0 ? p.ldx : p.K, ldy = p.ldy > 0 ? p.ldy : p.N, ldr = p.ldr > 0 ? p.ldr : p.N;
-  float acc[4][8];
+  float acc[8];
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+  for (int m = 0; m < 8; ++m) acc[m] = 0.f;
+  const float* wr = p.w + (long long)n * p.K;
+  if ((p.K & 127) == 0 && (ldx & 3) == 0) {
+    for (int k = lane * 4; k < p.K; k += 128) {
+      const float4 wv = __ldg(reinterpret_cast<const float4*>(wr + k));
 #pragma unroll
-    for (int m = 0; m < 8; ++m) acc[a][m] = 0.f;
-  for (int k = lane; k < p.K; k += 32) {
-    float xv[8];
+      for (int m = 0; m < 8; ++m) {
+        if (m0 + m < p.M) {
+          const float4 xv = *reinterpret_cast<const float4*>(p.x + (long long)(m0 + m) * ldx + k);
+          acc[m] = fmaf(wv.x, xv.x, fmaf(wv.y, xv.y, fmaf(wv.z, xv.z, fmaf(wv.w, xv.w, acc[m]))));
+        }
+      }
+    }
+  } else {
+    for (int k = lane; k < p.K; k += 32) {
+      const float wv = wr[k];
 #pragma unroll
-    for (int m = 0; m < 8; ++m) xv[m] = (m0 + m < p.M) ? p.x[(long long)(m0 + m) * ldx + k] : 0.f;
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      const float wv = (n0 + a < p.N) ? p.w[(long long)(n0 + a) * p.K + k] : 0.f;
-#pragma unroll
-      for (int m = 0; m < 8; ++m) acc[a][m] = fmaf(wv, xv[m], acc[a][m]);
+      for (int m = 0; m < 8; ++m)
+        if (m0 + m < p.M) acc[m] = fmaf(wv, p.x[(long long)(m0 + m) * ldx + k], acc[m]);
     }
   }
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+  for (int m = 0; m < 8; ++m) acc[m] = warp_sum(acc[m]);
+  if (lane < 8 && m0 + lane < p.M) {
+    float v = 0.f;
 #pragma unroll
-    for (int m = 0; m < 8; ++m) acc[a][m] = warp_sum(acc[a][m]);
-  if (lane == 0) {
-    for (int a = 0; a < 4; ++a) {
-      const int n = n0 + a;
-      if (n >= p.N) break;
-      for (int m = 0; m < 8; ++m) {
-        if (m0 + m >= p.M) break;
-        float v = acc[a][m] + (p.bias ? p.bias[n] : 0.f);
-        if (p.act == UDB_ACT_GELU) v = gelu_erf(v);
-        if (p.gamma) v *= p.gamma[n];
-        if (p.resid) v += p.resid[(long long)(m0 + m) * ldr + n];
-        p.y[(long long)(m0 + m) * ldy + n] = v;
-      }
-    }
+    for (int m = 0; m < 8; ++m) v = (lane == m) ? acc[m] : v;
+    v += p.bias ? p.bias[n] : 0.f;
+    if (p.act == UDB_ACT_GELU) v = gelu_erf(v);
+    if (p.gamma) v *= p.gamma[n];
+    if (p.resid) v += p.resid[(long long)(m0 + lane) * ldr + n];
+    p.y[(long long)(m0 + lane) * ldy + n] = v;
   }
 }
 
@@ -560,7 +562,7 @@ extern "C" int udb_set_cls_rows(float* x, const float* cls_token, const float* p
 }
 
 extern "C" int udb_small_linear_f32(const udb_small_linear_t* p, void* stream) {
-  dim3 grid((p->N + 15) / 16, (p->M + 7) / 8);
+  dim3 grid((p->N + 3) / 4, (p->M + 7) / 8);
   small_linear_kernel<<<grid, 128, 0, ST(stream)>>>(*p);
   return check_launch("small_linear_kernel");
 }

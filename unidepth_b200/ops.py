@@ -174,13 +174,13 @@ def conv_transpose_ks(x: torch.Tensor, w: torch.Tensor, k: int, cout: int, grid_
     return out
 
 
-def attention(q, k, v, out, *, B, heads, seq_q, seq_k, head_dim, q_col0=0, k_col0=0, v_col0=0, o_col0=0):
+def attention(q, k, v, out, *, B, heads, seq_q, seq_k, head_dim, q_col0=0, k_col0=0, v_col0=0, o_col0=0, scale=None):
     a = cabi.Attn()
     a.q, a.k, a.v, a.out = _ptr(q), _ptr(k), _ptr(v), _ptr(out)
     a.B, a.heads, a.seq_q, a.seq_k, a.head_dim = B, heads, seq_q, seq_k, head_dim
     a.ldq, a.ldk, a.ldv, a.ldo = q.stride(0), k.stride(0), v.stride(0), out.stride(0)
     a.q_col0, a.k_col0, a.v_col0, a.o_col0 = q_col0, k_col0, v_col0, o_col0
-    a.scale = head_dim ** -0.5
+    a.scale = head_dim ** -0.5 if scale is None else scale   # explicit scale: zero-padded narrower heads
     cabi.check(_launch("attn_fwd_kernel", 4.0 * B * heads * seq_q * seq_k * head_dim,
                        lambda: cabi.lib().udb_attention_f16(C.byref(a), _stream())), "udb_attention_f16")
     return out

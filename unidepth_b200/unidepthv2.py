@@ -124,9 +124,17 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
         c32 = lambda t: t.to(f32).contiguous()
         P: dict = {}
         d, hid = s.embed_dim, s.hidden
-        if hid // s.dec_heads != 64 or d // s.enc_heads != 64:
-            raise NotImplementedError("attention kernel supports head_dim 64 only (ViT-L/B encoders with a "
-                                      "512-wide decoder); ViT-S decoder heads (32) are a later round")
+        # The attention kernel works on 64-wide heads.  Narrower decoder heads (ViT-S: 256/8 = 32) are
+        # zero-padded to 64 in the packed q / kv / out weights: padded q,k columns add 0 to q.k, padded
+        # v columns produce zeros that meet zero columns of the out projection; the softmax scale stays
+        # 1/sqrt(true head dim).
+        hd = hid // s.dec_heads
+        if d // s.enc_heads != 64 or hd > 64 or 64 % hd:
+            raise NotImplementedError(f"head dims (encoder {d // s.enc_heads}, decoder {hd}) not supported")
+        for cch in list(s.cur) + list(s.outd):
+            if cch % 64:
+                raise NotImplementedError(f"decoder channel count {cch} is not a multiple of 64 (ViT-B decoder: later round)")
+        P["dec_hd"], P["dec_hp"] = hd, s.dec_heads * 64
         pe = "pixel_encoder."
         wpe = torch.zeros((d, 640), device=dev, dtype=f16)
         wpe[:, :588] = sd[pe + "patch_embed.proj.weight"].reshape(d, 588).to(f16)
@@ -170,13 +178,31 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
                         agg2=agg32(cl + "aggregate2"), project=mlp32(cl + "project"),
                         pinhole=mlp32(cl + "out_pinhole"))
         dl = pd + "depth_layer."
+        nh_dec = s.dec_heads
+
+        def pad_heads_rows(w):      # [heads*hd, K] -> [heads*64, K], zero rows for the padded head dims
+            if hd == 64:
+                return w
+            out_w = torch.zeros((nh_dec, 64, w.shape[1]), device=w.device, dtype=w.dtype)
+            out_w[:, :hd] = w.reshape(nh_dec, hd, w.shape[1])
+            return out_w.reshape(nh_dec * 64, w.shape[1])
+
+        def pad_heads_cols(w):      # [N, heads*hd] -> [N, heads*64]
+            if hd == 64:
+                return w
+            out_w = torch.zeros((w.shape[0], nh_dec, 64), device=w.device, dtype=w.dtype)
+            out_w[:, :, :hd] = w.reshape(w.shape[0], nh_dec, hd)
+            return out_w.reshape(w.shape[0], nh_dec * 64)
+
         P["prompt"] = []
         for i in range(4):
             p = f"{dl}prompt_camera.{i}.layers.0"
             P["prompt"].append(dict(
                 nxw=c32(sd[p + ".norm_attnx.weight"]), nxb=c32(sd[p + ".norm_attnx.bias"]),
                 ncw=c32(sd[p + ".norm_attnctx.weight"]), ncb=c32(sd[p + ".norm_attnctx.bias"]),
-                q=h16(sd[p + ".q.weight"]), kv=h16(sd[p + ".kv.weight"]), out=h16(sd[p + ".out.weight"]),
+                q=h16(pad_heads_rows(sd[p + ".q.weight"])),
+                kv=h16(torch.cat([pad_heads_rows(sd[p + ".kv.weight"][:hid]), pad_heads_rows(sd[p + ".kv.weight"][hid:])], 0)),
+                out=h16(pad_heads_cols(sd[p + ".out.weight"])),
                 mnw=c32(sd[p + ".mlp.norm.weight"]), mnb=c32(sd[p + ".mlp.norm.bias"]),
                 w1=h16(sd[p + ".mlp.proj1.weight"]), b1=c32(sd[p + ".mlp.proj1.bias"]),
                 w2=h16(sd[p + ".mlp.proj2.weight"]), b2=c32(sd[p + ".mlp.proj2.bias"])))
@@ -210,9 +236,15 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
             w, bb = sd[mlp_p + ".1.weight"].float(), sd[mlp_p + ".1.bias"].float()
             wm.append(w * lnw.unsqueeze(0))
             bm.append(w @ lnb + bb)
+            lr_w, lr_b, hr_w = sd[f"{dl}{lr}.weight"].float(), sd[f"{dl}{lr}.bias"].float(), sd[f"{dl}{hr}.0.weight"].float()
+            if lr_w.shape[0] < 64:      # ViT-S: 32 lr channels -> zero-pad to the kernels' 64-channel granularity
+                pad_c = 64 - lr_w.shape[0]
+                lr_w = torch.cat([lr_w, torch.zeros((pad_c,) + tuple(lr_w.shape[1:]), device=dev)], 0)
+                lr_b = torch.cat([lr_b, torch.zeros(pad_c, device=dev)], 0)
+                hr_w = torch.cat([hr_w, torch.zeros((hr_w.shape[0], pad_c, 3, 3), device=dev)], 1)
             P["heads"].append(dict(
-                lr_w=conv_pack(sd[f"{dl}{lr}.weight"]), lr_b=c32(sd[f"{dl}{lr}.bias"]),
-                hr_w=conv_pack(sd[f"{dl}{hr}.0.weight"]), hr_b=c32(sd[f"{dl}{hr}.0.bias"]),
+                lr_w=conv_pack(lr_w), lr_b=c32(lr_b),
+                hr_w=conv_pack(hr_w), hr_b=c32(sd[f"{dl}{hr}.0.bias"]),
                 head_w=c32(sd[f"{dl}{hr}.2.weight"].reshape(32)), head_b=float(sd[f"{dl}{hr}.2.bias"].item()),
                 add=add))
         P["head_mlp_w"], P["head_mlp_b"] = h16(torch.cat(wm, 0)), c32(torch.cat(bm, 0))
@@ -335,7 +367,8 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
         # a13: prompt blocks
         cond = []
         xn, cn = E(B * N, hid), E(B * N, hid)
-        qb, kvb, ab = E(B * N, hid), E(B * N, 2 * hid), E(B * N, hid)
+        hp = P["dec_hp"]                               # heads * 64 (heads zero-padded to 64 dims)
+        qb, kvb, ab = E(B * N, hp), E(B * N, 2 * hp), E(B * N, hp)
         mb = E(B * N, s.expansion * hid)
         for l in range(4):
             pr = P["prompt"][l]
@@ -343,7 +376,8 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
             ops.layernorm(remb, pr["ncw"], pr["ncb"], 1e-5, out=cn)
             ops.gemm(xn, pr["q"], out=qb)
             ops.gemm(cn, pr["kv"], out=kvb)
-            ops.attention(qb, kvb, kvb, ab, B=B, heads=s.dec_heads, seq_q=N, seq_k=N, head_dim=64, k_col0=0, v_col0=hid)
+            ops.attention(qb, kvb, kvb, ab, B=B, heads=s.dec_heads, seq_q=N, seq_k=N, head_dim=64, k_col0=0, v_col0=hp,
+                          scale=P["dec_hd"] ** -0.5)
             ops.gemm(ab, pr["out"], resid=F[l], out=F[l])
             ops.layernorm(F[l], pr["mnw"], pr["mnb"], 1e-5, out=xn)
             ops.gemm(xn, pr["w1"], bias=pr["b1"], act=ops.ACT_GELU, out=mb)

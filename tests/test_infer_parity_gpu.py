@@ -180,3 +180,21 @@ def test_vits_against_reference_golden(name):
     out = dict(out)
     out["depth_features"] = out["depth_features"][:, ::4]      # the fixture keeps every 4th channel
     _check(out, ref)
+
+
+def test_high_res_1024x1536_long_sequence():
+    """BASELINE config 5 shape: 3x1024x1536 is resized by infer to 644x952 -> 3129 tokens (long-sequence
+    attention, 25 key tiles).  ViT-L widths with a 2-block encoder so the CPU oracle stays fast."""
+    import unidepth_oracle as O
+    from fixture import make_state_dict
+    cfg = _cfg(depth=2)
+    cfg["model"]["pixel_encoder"]["output_idx"] = [1, 1, 2, 2]
+    sd = make_state_dict(cfg, 2)
+    rgb = _rgb((1, 1024, 1536), 5)
+    torch.set_num_threads(min(32, os.cpu_count()))
+    ref = O.infer_v2(sd, copy.deepcopy(cfg), rgb)
+    m = _model(cfg, sd)
+    out = m.infer(rgb)
+    assert out["depth"].shape == (1, 1, 1024, 1536)
+    assert out["depth_features"].shape == (1, 512, 46, 68)
+    _check(out, ref)

@@ -184,11 +184,10 @@ def test_vits_against_reference_golden(name):
 
 def test_high_res_1024x1536_long_sequence():
     """BASELINE config 5 shape: 3x1024x1536 is resized by infer to 644x952 -> 3129 tokens (long-sequence
-    attention, 25 key tiles).  ViT-L widths with a 2-block encoder so the CPU oracle stays fast."""
+    attention, 25 key tiles).  ViT-L widths with a 4-block encoder so the CPU oracle stays fast."""
     import unidepth_oracle as O
     from fixture import make_state_dict
-    cfg = _cfg(depth=2)
-    cfg["model"]["pixel_encoder"]["output_idx"] = [1, 1, 2, 2]
+    cfg = _cfg(depth=4)
     sd = make_state_dict(cfg, 2)
     rgb = _rgb((1, 1024, 1536), 5)
     torch.set_num_threads(min(32, os.cpu_count()))

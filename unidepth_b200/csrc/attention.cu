@@ -76,7 +76,7 @@ __device__ __forceinline__ float softmax_row(uint32_t (&sv)[AT_BK], const float 
                                              const int kv_left) {
   const uint64_t sc2 = pack2(sc, sc), nm2 = pack2(-m_used, -m_used);
   const float s_floor = (m_used - 100.0f) / sc;      // scores below this give exp2(< -100) = 0 in f16 anyway
-  uint64_t psum2 = 0ull;
+  uint64_t ps[4] = {0ull, 0ull, 0ull, 0ull};   // independent partial sums: no serial FADD chain behind the MUFUs
 #pragma unroll
   for (int i = 0; i < AT_BK; i += 2) {
     float e0, e1;
@@ -93,11 +93,47 @@ __device__ __forceinline__ float softmax_row(uint32_t (&sv)[AT_BK], const float 
       e0 = (i < kv_left) ? e0 : 0.f;
       e1 = (i + 1 < kv_left) ? e1 : 0.f;
     }
-    psum2 = add2(psum2, pack2(e0, e1));
+    ps[(i >> 1) & 3] = add2(ps[(i >> 1) & 3], pack2(e0, e1));
     sv[i >> 1] = pack_half2(e0, e1);   // pair i -> word i/2 (already consumed)
   }
   float ps0, ps1;
-  unpack2(psum2, ps0, ps1);
+  unpack2(add2(add2(ps[0], ps[1]), add2(ps[2], ps[3])), ps0, ps1);
+  return ps0 + ps1;
+}
+
+// Speculative variant: probabilities against the CURRENT reference m_used AND the tile's row maximum
+// in one pass, so the max (ALU pipe, FMNMX3) overlaps the exp2 (MUFU pipe) instead of preceding it.
+// The caller checks afterwards that the maximum did not outgrow the reference by more than the
+// lazy-rescale threshold; if it did (rare) the results -- possibly overflowed -- are discarded and
+// the tile is redone from the scores still held in TMEM.
+template <bool MASK>
+__device__ __forceinline__ float softmax_row_spec(uint32_t (&sv)[AT_BK], const float sc, const float m_used,
+                                                  const int kv_left, float& mx_out) {
+  const uint64_t sc2 = pack2(sc, sc), nm2 = pack2(-m_used, -m_used);
+  uint64_t ps[4] = {0ull, 0ull, 0ull, 0ull};
+  float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < AT_BK; i += 2) {
+    const float s0 = __uint_as_float(sv[i]), s1 = __uint_as_float(sv[i + 1]);
+    float t0, t1;
+    unpack2(fma2(pack2(s0, s1), sc2, nm2), t0, t1);
+    float e0 = ex2(t0), e1 = ex2(t1);
+    if (MASK) {
+      e0 = (i < kv_left) ? e0 : 0.f;
+      e1 = (i + 1 < kv_left) ? e1 : 0.f;
+      m0 = (i < kv_left) ? fmaxf(m0, s0) : m0;
+      m1 = (i + 1 < kv_left) ? fmaxf(m1, s1) : m1;
+    } else if ((i >> 1) & 1) {
+      m1 = max3(m1, s0, s1);
+    } else {
+      m0 = max3(m0, s0, s1);
+    }
+    ps[(i >> 1) & 3] = add2(ps[(i >> 1) & 3], pack2(e0, e1));
+    sv[i >> 1] = pack_half2(e0, e1);
+  }
+  mx_out = fmaxf(m0, m1);
+  float ps0, ps1;
+  unpack2(add2(add2(ps[0], ps[1]), add2(ps[2], ps[3])), ps0, ps1);
   return ps0 + ps1;
 }
 
@@ -246,45 +282,62 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int kv_left = p.seq_k - j * AT_BK;   // valid keys in this tile (>= 1)
       const bool full = kv_left >= AT_BK;
       uint32_t sv[AT_BK];
+      auto load_scores = [&]() {
 #pragma unroll
-      for (int c = 0; c < AT_BK; c += 32)
-        tmem_ld_32x32b_x32(tmem_base + lane_addr + c, *reinterpret_cast<uint32_t(*)[32]>(&sv[c]));
-      tmem_ld_wait();
+        for (int c = 0; c < AT_BK; c += 32)
+          tmem_ld_32x32b_x32(tmem_base + lane_addr + c, *reinterpret_cast<uint32_t(*)[32]>(&sv[c]));
+        tmem_ld_wait();
+      };
+      load_scores();
+      bool careful = (j == 0);           // first tile: no reference yet
+      bool pv_done = false;
+      if (!careful) {
+        // common case: exp2 against the current reference and the row max in the same pass
+        float mx;
+        const float psum = full ? softmax_row_spec<false>(sv, sc, m_used, kv_left, mx)
+                                : softmax_row_spec<true>(sv, sc, m_used, kv_left, mx);
+        careful = __any_sync(0xffffffffu, mx * sc > m_used + kRescaleThreshold);
+        if (careful) load_scores();      // rare: the speculative results are discarded
+        else l_run += psum;
+      }
+      if (careful) {
+        const float m_tile = (full ? row_max<false>(sv, kv_left) : row_max<true>(sv, kv_left)) * sc;
+        const bool need = m_tile > m_used + kRescaleThreshold;   // always true on the first tile
+        float alpha = 1.0f;
+        if (need) {
+          alpha = ex2(m_used - m_tile);      // 0 on the first tile
+          m_used = m_tile;
+        }
+        if (j > 0 && __any_sync(0xffffffffu, need)) {
+          // rescale this warp's 32 rows of O (rows that do not need it multiply by 1)
+          mbar_wait(p_free, (j - 1) & 1);
+          tc_fence_after_sync();
+          pv_done = true;
+          const uint64_t a2 = pack2(alpha, alpha);
+#pragma unroll 1
+          for (int c = 0; c < HD; c += 16) {
+            uint32_t r[16];
+            tmem_ld_32x32b_x16(tmem_O + lane_addr + c, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+              float lo, hi;
+              unpack2(mul2(pack2u(r[i], r[i + 1]), a2), lo, hi);
+              r[i] = __float_as_uint(lo);
+              r[i + 1] = __float_as_uint(hi);
+            }
+            tmem_st_32x32b_x16(tmem_O + lane_addr + c, r);
+          }
+          tmem_st_wait();
+        }
+        const float psum = full ? softmax_row<false>(sv, sc, m_used, kv_left) : softmax_row<true>(sv, sc, m_used, kv_left);
+        l_run = fmaf(l_run, alpha, psum);
+      }
+      // the score buffer is released only now (the rare path re-reads it); S_{j+1} is then computed
+      // while P_j is packed / stored and is ready when the next iteration starts
       tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(s_free);        // the MMA warp may now compute S_{j+1}
-      const float m_tile = (full ? row_max<false>(sv, kv_left) : row_max<true>(sv, kv_left)) * sc;
-      const bool need = m_tile > m_used + kRescaleThreshold;   // always true on the first tile
-      float alpha = 1.0f;
-      if (need) {
-        alpha = ex2(m_used - m_tile);      // 0 on the first tile
-        m_used = m_tile;
-      }
-      bool pv_done = false;
-      if (j > 0 && __any_sync(0xffffffffu, need)) {
-        // rare: rescale this warp's 32 rows of O (rows that do not need it multiply by 1)
-        mbar_wait(p_free, (j - 1) & 1);
-        tc_fence_after_sync();
-        pv_done = true;
-        const uint64_t a2 = pack2(alpha, alpha);
-#pragma unroll 1
-        for (int c = 0; c < HD; c += 16) {
-          uint32_t r[16];
-          tmem_ld_32x32b_x16(tmem_O + lane_addr + c, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 16; i += 2) {
-            float lo, hi;
-            unpack2(mul2(pack2u(r[i], r[i + 1]), a2), lo, hi);
-            r[i] = __float_as_uint(lo);
-            r[i + 1] = __float_as_uint(hi);
-          }
-          tmem_st_32x32b_x16(tmem_O + lane_addr + c, r);
-        }
-        tmem_st_wait();
-      }
-      const float psum = full ? softmax_row<false>(sv, sc, m_used, kv_left) : softmax_row<true>(sv, sc, m_used, kv_left);
-      l_run = fmaf(l_run, alpha, psum);
+      if (lane == 0) mbar_arrive(s_free);
       // the PV MMA of tile j-1 must have finished reading sP (the next completion of p_free needs
       // this thread's own arrival on p_full, so the parity is unambiguous)
       if (j > 0 && !pv_done) mbar_wait(p_free, (j - 1) & 1);

@@ -1,0 +1,27 @@
+"""Event timeline of one attention CTA (needs a -DUDB_ATTN_TRACE variant build, see tools/build_variant.sh).
+Columns are clock64 deltas relative to the softmax warp's 's_full seen' of each tile."""
+import ctypes
+import os
+import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from unidepth_b200 import ops, _cabi
+
+lib = ctypes.CDLL(_cabi.LIB_PATH)
+dev = torch.device("cuda:0")
+B, H, S = 8, 16, 1611
+D = H * 64
+qkv = torch.randn(B * S, 3 * D, device=dev).half()
+out = torch.empty(B * S, D, device=dev, dtype=torch.float16)
+for _ in range(2):
+    ops.attention(qkv, qkv, qkv, out, B=B, heads=H, seq_q=S, seq_k=S, head_dim=64, k_col0=D, v_col0=2 * D)
+    torch.cuda.synchronize()
+buf = (ctypes.c_longlong * (32 * 16))()
+lib.udb_attn_trace_read(buf)
+ev = [[buf[j * 16 + k] for k in range(16)] for j in range(13)]
+t0 = ev[0][0]
+names = {0: "sm:s_full", 1: "sm:ld", 2: "sm:exp", 3: "sm:s_free!", 4: "sm:p_free", 5: "sm:p_full!",
+         8: "mma:s_free", 9: "mma:qk_iss", 10: "mma:p_full", 11: "mma:pv_iss"}
+for j in range(13):
+    items = sorted((ev[j][k] - t0, names[k]) for k in names if ev[j][k])
+    print(f"tile {j:2d}: " + "  ".join(f"{n}@{t}" for t, n in items))

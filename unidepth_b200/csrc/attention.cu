@@ -27,6 +27,21 @@
 namespace udb {
 
 constexpr int AT_BQ = 128;       // queries per CTA
+#ifndef UDB_ATTN_SPEC
+#define UDB_ATTN_SPEC 1   // speculative exp2 against the running reference (rare redo)
+#endif
+#ifdef UDB_ATTN_TIMING   // variant build only: per-phase clock64 accumulation in the softmax warps
+__device__ unsigned long long g_attn_phase[8];
+#define AT_TICK(k) do { const long long t_now = clock64(); t_acc[k] += t_now - t_prev; t_prev = t_now; } while (0)
+#else
+#define AT_TICK(k) do {} while (0)
+#endif
+#ifdef UDB_ATTN_TRACE   // variant build only: event timeline of CTA (1,0,0): softmax warp 2 + the MMA thread
+__device__ long long g_attn_trace[32 * 16];
+#define AT_EV(j, k) do { if (trace_on && (j) < 32) g_attn_trace[(j) * 16 + (k)] = clock64(); } while (0)
+#else
+#define AT_EV(j, k) do {} while (0)
+#endif
 #ifndef UDB_ATTN_BK
 #define UDB_ATTN_BK 128
 #endif
@@ -213,24 +228,39 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t tmem_O = tmem_base + AT_BK;
   pdl_wait();   // everything above overlapped the previous kernel's tail
+#ifdef UDB_ATTN_TRACE
+  const bool trace_on = blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && (warp == 1 || warp == 2) && lane == 0;
+#endif
 
   if (warp == 0) {
-    if (lane == 0) {
+    const bool leader = elect_one();   // whole warp in the control flow, one lane issues (see the MMA warp)
+    if (leader) {
       mbar_arrive_expect_tx(q_full, kQBytes);
       tma_load_3d(sQ, &tmQ, q_full, p.q_col0 + head * HD, q0, b);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int st = j % NS;
-        const uint32_t ph = ((j / NS) & 1) ^ 1;
-        mbar_wait(&k_empty[st], ph);
+    }
+    __syncwarp();
+    for (int j = 0; j < n_tiles; ++j) {
+      const int st = j % NS;
+      const uint32_t ph = ((j / NS) & 1) ^ 1;
+      mbar_wait(&k_empty[st], ph);
+      if (leader) {
         mbar_arrive_expect_tx(&k_full[st], kKBytes);
         tma_load_3d(sK + st * kKBytes, &tmK, &k_full[st], p.k_col0 + head * HD, j * AT_BK, b);
-        mbar_wait(&v_empty[st], ph);
+      }
+      __syncwarp();
+      mbar_wait(&v_empty[st], ph);
+      if (leader) {
         mbar_arrive_expect_tx(&v_full[st], kKBytes);
         tma_load_3d(sV + st * kKBytes, &tmV, &v_full[st], p.v_col0 + head * HD, j * AT_BK, b);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // The whole warp runs the control flow so that descriptors and addresses stay in uniform registers
+    // (under a lane-0 branch ptxas wraps every tcgen05.mma in an ELECT / R2UR waterfall loop that costs
+    // ~90 cycles per instruction); one elected lane issues the MMAs and commits.
+    const bool leader = elect_one();
+    {
       constexpr uint32_t idesc_qk = umma_idesc_f16(AT_BQ, AT_BK, false, false);
       constexpr uint32_t idesc_pv = umma_idesc_f16(AT_BQ, HD, false, true);   // B = V is MN-major
       const uint64_t dq = umma_desc_sw128(smem_u32(sQ), 16, 1024);
@@ -239,10 +269,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_wait(&k_full[st], (j / NS) & 1);
         tc_fence_after_sync();
         const uint64_t dk = umma_desc_sw128(smem_u32(sK + st * kKBytes), 16, 1024);
+        if (leader) {
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k) umma_f16_ss(tmem_base, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0);
-        umma_commit(&k_empty[st]);
-        umma_commit(s_full);
+          for (int k = 0; k < HD / 16; ++k) umma_f16_ss(tmem_base, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0);
+          umma_commit(&k_empty[st]);
+          umma_commit(s_full);
+        }
+        __syncwarp();
       };
       mbar_wait(q_full, 0);
       issue_qk(0);
@@ -250,20 +283,28 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const int st = j % NS;
         if (j + 1 < n_tiles) {
           mbar_wait(s_free, j & 1);                // score row of tile j is in registers: S may be overwritten
+          AT_EV(j, 8);
           issue_qk(j + 1);
+          AT_EV(j, 9);
         }
         mbar_wait(p_full, j & 1);                  // P_j written
+        AT_EV(j, 10);
         mbar_wait(&v_full[st], (j / NS) & 1);
         tc_fence_after_sync();
         const uint64_t dv = umma_desc_sw128(smem_u32(sV + st * kKBytes), 1024, 1024);
+        const uint64_t dp0 = umma_desc_sw128(smem_u32(sP), 16, 1024);
+        if (leader) {
 #pragma unroll
-        for (int ks = 0; ks < AT_BK / 16; ++ks) {
-          // A = P: sub-tile (ks/4) of 16 KB, 32 B per 16-key step inside the swizzle atom; B = V: 2 KB per step
-          const uint64_t dp = umma_desc_sw128(smem_u32(sP + (ks >> 2) * (AT_BQ * 128)), 16, 1024) + 2 * (ks & 3);
-          umma_f16_ss(tmem_O, dp, dv + (uint64_t)(ks * 2048 >> 4), idesc_pv, (j | ks) != 0);
+          for (int ks = 0; ks < AT_BK / 16; ++ks) {
+            // A = P: sub-tile (ks/4) of 16 KB, 32 B per 16-key step inside the swizzle atom; B = V: 2 KB per step
+            const uint64_t dp = dp0 + (uint64_t)((ks >> 2) * (AT_BQ * 128) >> 4) + 2 * (ks & 3);
+            umma_f16_ss(tmem_O, dp, dv + (uint64_t)(ks * 2048 >> 4), idesc_pv, (j | ks) != 0);
+          }
+          umma_commit(&v_empty[st]);
+          umma_commit(p_free);
         }
-        umma_commit(&v_empty[st]);
-        umma_commit(p_free);
+        __syncwarp();
+        AT_EV(j, 11);
       }
     }
   } else {
@@ -276,9 +317,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const float sc = p.scale_log2;
     constexpr float kRescaleThreshold = 8.0f;   // log2 domain
 
+#ifdef UDB_ATTN_TIMING
+    long long t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long t_prev = clock64();
+#endif
     for (int j = 0; j < n_tiles; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after_sync();
+      AT_TICK(0);
+      AT_EV(j, 0);
       const int kv_left = p.seq_k - j * AT_BK;   // valid keys in this tile (>= 1)
       const bool full = kv_left >= AT_BK;
       uint32_t sv[AT_BK];
@@ -289,7 +336,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_ld_wait();
       };
       load_scores();
-      bool careful = (j == 0);           // first tile: no reference yet
+      if (!UDB_ATTN_SPEC) {   // scores are in registers: S may be overwritten by the next QK^T right away
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_free);
+      }
+      AT_TICK(1);
+      AT_EV(j, 1);
+      bool careful = (j == 0) || !UDB_ATTN_SPEC;   // first tile: no reference yet
       bool pv_done = false;
       if (!careful) {
         // common case: exp2 against the current reference and the row max in the same pass
@@ -333,14 +387,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const float psum = full ? softmax_row<false>(sv, sc, m_used, kv_left) : softmax_row<true>(sv, sc, m_used, kv_left);
         l_run = fmaf(l_run, alpha, psum);
       }
+      AT_TICK(2);
+      AT_EV(j, 2);
       // the score buffer is released only now (the rare path re-reads it); S_{j+1} is then computed
       // while P_j is packed / stored and is ready when the next iteration starts
-      tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(s_free);
+      if (UDB_ATTN_SPEC) {
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_free);
+      }
+      AT_TICK(3);
+      AT_EV(j, 3);
       // the PV MMA of tile j-1 must have finished reading sP (the next completion of p_free needs
       // this thread's own arrival on p_full, so the parity is unambiguous)
       if (j > 0 && !pv_done) mbar_wait(p_free, (j - 1) & 1);
+      AT_TICK(4);
+      AT_EV(j, 4);
       uint8_t* p_row = sP + row * 128;
 #pragma unroll
       for (int q = 0; q < AT_BK / 8; ++q)      // chunks of 8 halves (16 B); 64-key sub-tiles of 16 KB
@@ -350,10 +412,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
+      AT_TICK(5);
+      AT_EV(j, 5);
     }
     // epilogue: O / l
     mbar_wait(p_free, (n_tiles - 1) & 1);   // last PV done => all done
     tc_fence_after_sync();
+    AT_TICK(6);
+#ifdef UDB_ATTN_TIMING
+    if (lane == 0) {
+      for (int k = 0; k < 7; ++k) atomicAdd(&g_attn_phase[k], (unsigned long long)t_acc[k]);
+      atomicAdd(&g_attn_phase[7], (unsigned long long)n_tiles);
+    }
+#endif
     const float inv = 1.0f / l_run;
     const int q = q0 + row;
     __half* op = p.out + ((long long)b * p.seq_q + (q < p.seq_q ? q : 0)) * p.ldo + p.o_col0 + head * HD;
@@ -385,6 +456,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
 }  // namespace udb
 
+#ifdef UDB_ATTN_TRACE
+extern "C" int udb_attn_trace_read(long long* out) {
+  cudaMemcpyFromSymbol(out, udb::g_attn_trace, sizeof(long long) * 32 * 16);
+  return 0;
+}
+#endif
+#ifdef UDB_ATTN_TIMING
+extern "C" int udb_attn_phase_read(unsigned long long* out, int reset) {
+  cudaMemcpyFromSymbol(out, udb::g_attn_phase, sizeof(unsigned long long) * 8);
+  if (reset) { unsigned long long z[8] = {}; cudaMemcpyToSymbol(udb::g_attn_phase, z, sizeof(z)); }
+  return 0;
+}
+#endif
+
 extern "C" int udb_attention_f16(const udb_attn_t* a, void* stream) {
   using namespace udb;
   if (a->head_dim != 64) { set_error("udb_attention_f16: head_dim %d unsupported (64 only)", a->head_dim); return 1; }
@@ -415,7 +500,10 @@ extern "C" int udb_attention_f16(const udb_attn_t* a, void* stream) {
   p.ldo = a->ldo; p.o_col0 = a->o_col0;
   p.q_col0 = a->q_col0; p.k_col0 = a->k_col0; p.v_col0 = a->v_col0;
   p.scale_log2 = a->scale * 1.4426950408889634f;
-  constexpr int smem_bytes = 16384 + 2 * AT_KV_STAGES * (AT_BK * 128) + AT_BQ * AT_BK * 2 + 256;
+#ifndef UDB_ATTN_SMEM_PAD
+#define UDB_ATTN_SMEM_PAD 0   // experiments: extra dynamic smem to lower the CTAs/SM
+#endif
+  constexpr int smem_bytes = 16384 + 2 * AT_KV_STAGES * (AT_BK * 128) + AT_BQ * AT_BK * 2 + 256 + UDB_ATTN_SMEM_PAD;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);

@@ -82,10 +82,16 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 
   const int per_img = p.tiles_x * p.tiles_y;
   if (warp == 0) {
-    if (lane == 0) {
+    // whole warp in the control flow, one elected lane issues (operands stay in uniform registers;
+    // a lane-0 branch makes ptxas wrap every TMA / MMA in an ELECT + R2UR waterfall loop)
+    const bool elected = elect_one();
+    {
       // weights: resident for the whole kernel
-      mbar_arrive_expect_tx(w_full, w_bytes);
-      for (int kb = 0; kb < 9 * p.slabs; ++kb) tma_load_2d(sW + kb * kWTile, &tmW, w_full, kb * 64, 0);
+      if (elected) {
+        mbar_arrive_expect_tx(w_full, w_bytes);
+        for (int kb = 0; kb < 9 * p.slabs; ++kb) tma_load_2d(sW + kb * kWTile, &tmW, w_full, kb * 64, 0);
+      }
+      __syncwarp();
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -93,14 +99,18 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         const int y0 = (r / p.tiles_x) * HC_TH, x0 = (r % p.tiles_x) * HC_TW;
         for (int s = 0; s < p.slabs; ++s) {
           mbar_wait(&a_empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&a_full[stage], HC_SLAB_BYTES);
-          tma_load_4d(sA + stage * HC_SLAB_BYTES, &tmX, &a_full[stage], p.coff + s * 64, x0, y0, b);
+          if (elected) {
+            mbar_arrive_expect_tx(&a_full[stage], HC_SLAB_BYTES);
+            tma_load_4d(sA + stage * HC_SLAB_BYTES, &tmX, &a_full[stage], p.coff + s * 64, x0, y0, b);
+          }
+          __syncwarp();
           if (++stage == p.a_stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    const bool elected = elect_one();
+    {
       constexpr uint32_t idesc = umma_idesc_f16(128, COUT, false, false);
       mbar_wait(w_full, 0);
       int stage = 0, it = 0;
@@ -121,13 +131,17 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             uint64_t da = umma_desc_sw128(a_base + (dy * HC_HW + dx) * 128, 16, HC_HW * 128);
             if (p.base_off_mode) da |= static_cast<uint64_t>(dx) << 49;   // start is dx rows into the 8-row swizzle pattern
             const uint64_t dw = umma_desc_sw128(smem_u32(sW + (tap * p.slabs + s) * kWTile), 16, 1024);
+            if (elected) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_f16_ss(d, da + 2 * k, dw + 2 * k, idesc, (s | tap | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < 4; ++k) umma_f16_ss(d, da + 2 * k, dw + 2 * k, idesc, (s | tap | k) != 0 ? 1u : 0u);
+            }
           }
-          umma_commit(&a_empty[stage]);
+          if (elected) umma_commit(&a_empty[stage]);
+          __syncwarp();
           if (++stage == p.a_stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&t_full[as]);
+        if (elected) umma_commit(&t_full[as]);
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {

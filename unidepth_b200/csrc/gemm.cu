@@ -304,7 +304,10 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // (whole warp in the control flow, one elected lane issues: keeps addresses/descriptors in uniform
+    //  registers -- under a lane-0 branch ptxas wraps each TMA / MMA in an ELECT+R2UR waterfall loop)
+    const bool elected = elect_one();
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -320,16 +323,19 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          if (p.a_mode == UDB_A_CONV3X3) {
-            const int tap = kb / p.conv_cpb;
-            const int c0 = p.conv_coff + (kb % p.conv_cpb) * BK;
-            tma_load_4d(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], c0, cx + tap % 3,
-                        cy + tap / 3, cb);
-          } else {
-            tma_load_2d(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * BK, mt * BM);
+          if (elected) {
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            if (p.a_mode == UDB_A_CONV3X3) {
+              const int tap = kb / p.conv_cpb;
+              const int c0 = p.conv_coff + (kb % p.conv_cpb) * BK;
+              tma_load_4d(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], c0, cx + tap % 3,
+                          cy + tap / 3, cb);
+            } else {
+              tma_load_2d(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * BK, mt * BM);
+            }
+            tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * BK, nt * BN);
           }
-          tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * BK, nt * BN);
+          __syncwarp();
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -339,7 +345,8 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    const bool elected = elect_one();
+    {
       constexpr uint32_t idesc = umma_idesc_f16(BM, BN, false, false);
       int stage = 0;
       uint32_t phase = 0;
@@ -355,18 +362,22 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           tc_fence_after_sync();
           const uint64_t da = umma_desc_sw128(smem_u32(sA + stage * Cfg::kABytes), 16, 1024);
           const uint64_t db = umma_desc_sw128(smem_u32(sB + stage * Cfg::kBBytes), 16, 1024);
+          if (elected) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // advance 16 elements (32 B) along K inside the 128 B swizzle atom: +2 in 16-byte units
-            umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              // advance 16 elements (32 B) along K inside the 128 B swizzle atom: +2 in 16-byte units
+              umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);
           }
-          umma_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full[as]);
+        if (elected) umma_commit(&tmem_full[as]);
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {
@@ -496,7 +507,8 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
-    if (lane == 0) {
+    const bool elected = elect_one();
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
@@ -512,16 +524,19 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
-          else mbar_arrive_remote(&full_bar[stage], 0);
-          if (p.a_mode == UDB_A_CONV3X3) {
-            const int tap = kb / p.conv_cpb;
-            const int c0 = p.conv_coff + (kb % p.conv_cpb) * BK;
-            tma_load_4d_2sm(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], c0, cx + tap % 3, cy + tap / 3, cb);
-          } else {
-            tma_load_2d_2sm(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * BK, mt * BM);
+          if (elected) {
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+            else mbar_arrive_remote(&full_bar[stage], 0);
+            if (p.a_mode == UDB_A_CONV3X3) {
+              const int tap = kb / p.conv_cpb;
+              const int c0 = p.conv_coff + (kb % p.conv_cpb) * BK;
+              tma_load_4d_2sm(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], c0, cx + tap % 3, cy + tap / 3, cb);
+            } else {
+              tma_load_2d_2sm(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * BK, mt * BM);
+            }
+            tma_load_2d_2sm(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * BK, nt * BN + (int)rank * (BN / 2));
           }
-          tma_load_2d_2sm(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * BK, nt * BN + (int)rank * (BN / 2));
+          __syncwarp();
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -531,7 +546,8 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
-    if (leader && lane == 0) {
+    if (leader) {
+      const bool elected = elect_one();
       constexpr uint32_t idesc = umma_idesc_f16(2 * BM, BN, false, false);
       int stage = 0;
       uint32_t phase = 0;
@@ -547,16 +563,20 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tc_fence_after_sync();
           const uint64_t da = umma_desc_sw128(smem_u32(sA + stage * Cfg::kABytes), 16, 1024);
           const uint64_t db = umma_desc_sw128(smem_u32(sB + stage * Cfg::kBBytes), 16, 1024);
+          if (elected) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma_f16_ss_2cta(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit_2cta(&empty_bar[stage]);
+            for (int k = 0; k < BK / 16; ++k)
+              umma_f16_ss_2cta(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit_2cta(&empty_bar[stage]);
+          }
+          __syncwarp();
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit_2cta(&tmem_full[as]);
+        if (elected) umma_commit_2cta(&tmem_full[as]);
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {

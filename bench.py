@@ -224,6 +224,7 @@ def main():
     if rank == 0:
         from unidepth_b200 import ops
         model.use_cuda_graph = False
+        model.use_engine = False      # same kernels scheduled from Python so that each launch can be bracketed by events
         ops.PROFILE = []
         # keep the GPU busy while the host enqueues the whole eager pass (launches + event records),
         # so the events bracket back-to-back kernel executions, not host launch gaps
@@ -232,6 +233,7 @@ def main():
         torch.cuda.synchronize()
         prof, ops.PROFILE = ops.PROFILE, None
         model.use_cuda_graph = True
+        model.use_engine = True
         agg = {}
         for name, flops, s, e in prof:
             a = agg.setdefault(name, [0.0, 0.0, 0])

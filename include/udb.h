@@ -17,6 +17,7 @@
  */
 #ifndef UDB_H_
 #define UDB_H_
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -216,6 +217,11 @@ int udb_camera_intrinsics(const float* x, int32_t B, int32_t net_h, int32_t net_
  * utils/positional_embedding.py:218-256): unit rays from intr4 (or from rays_in [B,net_h*net_w,3]
  * when not NULL) -> antialiased bilinear down-sample by `net/grid` -> renormalise -> polar,
  * azimuth -> sin(angle * pi * scales[j]); out f32/f16 [B*gh*gw, 2*bands]. */
+/* infer(camera=K) (unidepthv2.py:267-303; Camera.crop / resize utils/camera.py:78-81,115-120):
+ * K [B,3,3] pinhole in input-image pixels -> (fx,fy,cx,cy) in network-input pixels. */
+int udb_camera_adjust_k(const float* K, int32_t B, float factor, int32_t pad_l, int32_t pad_t,
+                        float* intr4, void* stream);
+
 typedef struct udb_ray_embed_t {
   const float* intr4;
   const float* rays_in;
@@ -266,6 +272,91 @@ typedef struct udb_postprocess_t {
   float* out_rays;
 } udb_postprocess_t;
 int udb_postprocess(const udb_postprocess_t* p, void* stream);
+
+/* ======================================================================================
+ * Whole-path engine: one handle = one UniDepthV2 model on one device.
+ *
+ * Replaces the body of `UniDepthV2.infer` (unidepth/models/unidepthv2/unidepthv2.py:239-339:
+ * pre-process -> `encode_decode` :341-377 -> `_postprocess` :80-108) as ONE call that only enqueues
+ * kernels on the caller's stream: no allocation, no host<->device copy, no synchronisation, so the
+ * call is CUDA-graph capturable.  The caller (the Python boundary class, or any C program) owns all
+ * memory: packed weights, the workspace and the seven output tensors.
+ *
+ * Life cycle:   udb_create -> udb_set_weight / udb_set_scalar (once per packed tensor)
+ *               -> udb_workspace_bytes(B,H,W,level)  [per new input shape; also prepares the
+ *                  shape-dependent tables: resized position embedding, ray-embedding frequencies]
+ *               -> udb_infer_v2 (any number of times) -> udb_destroy.
+ * A handle is not thread-safe (neither is a reference model instance: `infer` mutates module state,
+ * decoder.py:436,447-448).  All functions return 0 on success, non-zero + udb_last_error() otherwise.
+ * ====================================================================================== */
+typedef struct udb_engine udb_engine;
+
+enum { UDB_DT_F16 = 0, UDB_DT_F32 = 1 };
+
+typedef struct udb_config_t {
+  /* DINOv2 encoder (unidepth/models/backbones/dinov2.py:388-427, encoder.py:139-193) */
+  int32_t embed_dim, depth, enc_heads;
+  int32_t taps[4];      /* 1-based indices of the four block outputs consumed (unidepthv2.py:365-372) */
+  int32_t pos_grid;     /* side of the stored position-embedding grid (37) */
+  /* decoder (unidepth/models/unidepthv2/decoder.py:470-524) */
+  int32_t hidden, dec_heads, expansion, out_dim;
+  int32_t n_stages;     /* len(depths) */
+  int32_t dec_depths[4];
+  /* data.augmentations.shape_constraints of the model config (unidepthv2.py:247-262) */
+  double ratio_min, ratio_max;
+  double pixels_min, pixels_max;
+} udb_config_t;
+
+int udb_create(const udb_config_t* cfg, udb_engine** out);
+void udb_destroy(udb_engine* e);
+
+/* Register one PACKED tensor (device pointer, borrowed for the life of the handle) under the engine's
+ * own name; the packing (f16 operand layouts, folded LayerNorm->Linear heads, zero-padded narrow
+ * heads) is described in DESIGN.md and done once per checkpoint by the boundary class from the
+ * reference's state_dict.  dtype: UDB_DT_*. */
+int udb_set_weight(udb_engine* e, const char* name, const void* dev_ptr, const int64_t* shape, int32_t ndim,
+                   int32_t dtype);
+/* Host scalars of the packed model (the two 1x1 head biases and their additive constants). */
+int udb_set_scalar(udb_engine* e, const char* name, double value);
+
+/* Geometry of one call, same arithmetic as get_paddings / get_resize_factor (unidepthv2.py:36-77). */
+typedef struct udb_geometry_t {
+  int32_t pad_l, pad_r, pad_t, pad_b;
+  int32_t padded_h, padded_w;
+  int32_t net_h, net_w;   /* network input, multiples of 14 */
+  int32_t gh, gw;         /* patch grid */
+  double factor;
+} udb_geometry_t;
+/* resolution_level: 0..9, or -1 = attribute unset (default pixel bounds). */
+int udb_geometry(const udb_engine* e, int32_t H, int32_t W, int32_t resolution_level, udb_geometry_t* out);
+
+/* Bytes of scratch udb_infer_v2 needs for this shape; also prepares the per-shape tables (may
+ * allocate and launch on the default stream: call it outside graph capture). 0 = error. */
+size_t udb_workspace_bytes(udb_engine* e, int32_t B, int32_t H, int32_t W, int32_t resolution_level);
+
+typedef struct udb_infer_args_t {
+  const void* rgb;            /* [B,3,H,W] uint8 or float32 (0..255 when normalize) */
+  int32_t rgb_is_u8, normalize;
+  int32_t B, H, W;
+  int32_t resolution_level;   /* 0..9 or -1 */
+  const float* camera_k;      /* optional [B,3,3] pinhole K in input-image pixels (infer(camera=K),
+                                 unidepthv2.py:267-303): rays come from it, intrinsics stay predicted */
+  const float* ray_scales;    /* optional [hidden/2] frequency table (positional_embedding.py:231-233);
+                                 NULL = the engine's own table */
+  void* workspace;
+  size_t workspace_bytes;
+  /* outputs, float32, caller-allocated (keys of the dict returned by infer, unidepthv2.py:331-339) */
+  float* confidence;          /* [B,1,H,W] */
+  float* intrinsics;          /* [B,3,3]   */
+  float* radius;              /* [B,1,H,W] */
+  float* depth;               /* [B,1,H,W] */
+  float* points;              /* [B,3,H,W] */
+  float* rays;                /* [B,3,H,W] */
+  float* depth_features;      /* [B,gh,gw,hidden] channel-last (the reference returns the same values
+                                 as [B,hidden,gh,gw]; the boundary class returns a permuted view) */
+} udb_infer_args_t;
+
+int udb_infer_v2(udb_engine* e, const udb_infer_args_t* a, void* stream);
 
 #ifdef __cplusplus
 }

@@ -114,3 +114,46 @@ def test_unknown_encoder_is_rejected():
     cfg["model"]["pixel_encoder"]["name"] = "convnext_large"
     with pytest.raises(NotImplementedError):
         UniDepthV2(cfg)
+
+
+def test_engine_geometry_matches_python_and_reference_examples():
+    """udb_geometry (C, include/udb.h) == spec.get_paddings / get_resize_factor (== the oracle's) on
+    random shapes and every resolution level; host-only calls, no GPU needed."""
+    import ctypes as C
+    from unidepth_b200 import _cabi, spec
+    lib = _cabi.lib()
+    cfg = _cabi.Config()
+    cfg.embed_dim, cfg.depth, cfg.enc_heads = 1024, 24, 16
+    for i, t in enumerate((6, 12, 18, 24)):
+        cfg.taps[i] = t
+    cfg.pos_grid, cfg.hidden, cfg.dec_heads, cfg.expansion, cfg.out_dim, cfg.n_stages = 37, 512, 8, 4, 64, 3
+    for i in range(3):
+        cfg.dec_depths[i] = 2
+    cfg.ratio_min, cfg.ratio_max, cfg.pixels_min, cfg.pixels_max = 0.5, 2.5, 200000.0, 600000.0
+    h = C.c_void_p()
+    assert lib.udb_create(C.byref(cfg), C.byref(h)) == 0
+    try:
+        g = _cabi.Geometry()
+        gen = torch.Generator().manual_seed(1)
+        shapes = [(480, 640), (1024, 1536), (480, 1600), (1000, 400)]
+        shapes += [(int(torch.randint(16, 2200, (1,), generator=gen)), int(torch.randint(16, 2200, (1,), generator=gen)))
+                   for _ in range(300)]
+        for (H, W) in shapes:
+            pads, padded = spec.get_paddings((H, W), (0.5, 2.5))
+            for lvl in (None, 0, 2, 5, 9):
+                bounds = spec.pixel_bounds({"pixels_min": 200000, "pixels_max": 600000}, lvl)
+                f, (nh, nw) = spec.get_resize_factor(padded, bounds)
+                assert lib.udb_geometry(h, H, W, -1 if lvl is None else lvl, C.byref(g)) == 0
+                assert (g.pad_l, g.pad_r, g.pad_t, g.pad_b) == pads and (g.padded_h, g.padded_w) == padded
+                assert (g.net_h, g.net_w, g.gh, g.gw) == (nh, nw, nh // 14, nw // 14) and g.factor == f, (H, W, lvl)
+        assert lib.udb_geometry(h, 480, 640, -1, C.byref(g)) == 0 and (g.net_h, g.net_w) == (490, 644)
+        assert lib.udb_geometry(h, 480, 640, 10, C.byref(g)) != 0          # resolution_level out of range
+        # unprepared / incomplete handles fail loudly instead of computing anything
+        a = _cabi.InferArgs()
+        assert lib.udb_infer_v2(h, C.byref(a), None) != 0
+        assert b"null" in lib.udb_last_error()
+    finally:
+        lib.udb_destroy(h)
+    bad = _cabi.Config()
+    bad.embed_dim, bad.enc_heads, bad.hidden, bad.dec_heads, bad.n_stages = 1000, 16, 512, 8, 3
+    assert lib.udb_create(C.byref(bad), C.byref(h)) != 0

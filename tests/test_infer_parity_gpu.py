@@ -197,3 +197,67 @@ def test_high_res_1024x1536_long_sequence():
     assert out["depth"].shape == (1, 1, 1024, 1536)
     assert out["depth_features"].shape == (1, 512, 46, 68)
     _check(out, ref)
+
+
+def test_c_engine_equals_python_schedule(shallow):
+    """udb_infer_v2 (the whole path as one C call) launches exactly the kernels the Python-side
+    schedule (ops.*) launches, in the same order on the same packed weights: outputs must be
+    bit-identical, with and without padding / resolution level / GT camera, eager and graph."""
+    cfg, sd = shallow
+    m = _model(cfg, sd)
+    K = torch.tensor([[300.0, 0.0, 170.0], [0.0, 310.0, 115.0], [0.0, 0.0, 1.0]])
+    for shape, level, cam in (((2, 240, 320), None, None), ((1, 96, 288), 3, None), ((2, 224, 320), 7, K)):
+        rgb = _rgb(shape, 5)
+        m.resolution_level = level
+        outs = []
+        for use_engine, use_graph in ((True, False), (False, False), (True, True)):
+            m.use_engine, m.use_cuda_graph = use_engine, use_graph
+            outs.append(m.infer(rgb, camera=cam) if cam is not None else m.infer(rgb))
+        for k in outs[0]:
+            assert outs[0][k].shape == outs[1][k].shape, k
+            assert torch.equal(outs[0][k], outs[1][k]), f"engine vs python schedule: {k} {shape} {level}"
+            assert torch.equal(outs[0][k], outs[2][k]), f"engine eager vs graph: {k} {shape} {level}"
+    m.use_engine, m.use_cuda_graph = True, True
+
+
+def test_c_engine_own_frequency_table_and_errors(shallow):
+    """A pure-C caller passes ray_scales = NULL: the engine's own 2**linspace table (libm powf) may
+    differ from torch's by an ulp (inside the parity tolerance).  Also: workspace too small and
+    unprepared shapes are reported, not silently computed."""
+    import ctypes as C
+    from unidepth_b200 import _cabi
+    cfg, sd = shallow
+    m = _model(cfg, sd)
+    m.resolution_level = None
+    rgb = _rgb((1, 240, 320), 6).cuda()
+    m.use_cuda_graph = False
+    ref = m.infer(rgb)
+    eng, lib = m._get_engine(), _cabi.lib()
+    B, _, H, W = rgb.shape
+    g = _cabi.Geometry()
+    assert lib.udb_geometry(eng, H, W, -1, C.byref(g)) == 0
+    nbytes = lib.udb_workspace_bytes(eng, B, H, W, -1)
+    assert nbytes > 0
+    ws = torch.empty(nbytes, device="cuda", dtype=torch.uint8)
+    f = lambda *s: torch.empty(s, device="cuda", dtype=torch.float32)
+    out = {"confidence": f(B, 1, H, W), "intrinsics": f(B, 3, 3), "radius": f(B, 1, H, W), "depth": f(B, 1, H, W),
+           "points": f(B, 3, H, W), "rays": f(B, 3, H, W), "depth_features": f(B, g.gh, g.gw, m.spec.hidden)}
+    a = _cabi.InferArgs()
+    a.rgb, a.rgb_is_u8, a.normalize, a.B, a.H, a.W, a.resolution_level = rgb.data_ptr(), 1, 1, B, H, W, -1
+    a.workspace, a.workspace_bytes = ws.data_ptr(), nbytes
+    for k, v in out.items():
+        setattr(a, k, v.data_ptr())
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    assert lib.udb_infer_v2(eng, C.byref(a), st) == 0, lib.udb_last_error()
+    torch.cuda.synchronize()
+    rel = (out["depth"] - ref["depth"]).abs() / ref["depth"]
+    print(f"engine-owned frequency table vs torch table: depth ARel {rel.mean().item():.3e} max {rel.max().item():.3e}")
+    # an ulp in a frequency flips f16 roundings of the embedding downstream: same size as the parity noise
+    assert rel.mean().item() < 2e-4 and rel.max().item() < 4e-3
+    assert torch.equal(out["intrinsics"], ref["intrinsics"])
+    a.workspace_bytes = nbytes // 2
+    assert lib.udb_infer_v2(eng, C.byref(a), st) != 0 and b"workspace too small" in lib.udb_last_error()
+    torch.cuda.synchronize()
+    a.workspace_bytes, a.H = nbytes, 238            # different patch grid: not prepared
+    assert lib.udb_infer_v2(eng, C.byref(a), st) != 0 and b"not prepared" in lib.udb_last_error()
+    m.use_cuda_graph = True

@@ -89,6 +89,34 @@ class Postprocess(C.Structure):
     ]
 
 
+class Config(C.Structure):
+    _fields_ = [
+        ("embed_dim", i32), ("depth", i32), ("enc_heads", i32), ("taps", i32 * 4), ("pos_grid", i32),
+        ("hidden", i32), ("dec_heads", i32), ("expansion", i32), ("out_dim", i32), ("n_stages", i32),
+        ("dec_depths", i32 * 4),
+        ("ratio_min", C.c_double), ("ratio_max", C.c_double), ("pixels_min", C.c_double), ("pixels_max", C.c_double),
+    ]
+
+
+class Geometry(C.Structure):
+    _fields_ = [
+        ("pad_l", i32), ("pad_r", i32), ("pad_t", i32), ("pad_b", i32), ("padded_h", i32), ("padded_w", i32),
+        ("net_h", i32), ("net_w", i32), ("gh", i32), ("gw", i32), ("factor", C.c_double),
+    ]
+
+
+class InferArgs(C.Structure):
+    _fields_ = [
+        ("rgb", vp), ("rgb_is_u8", i32), ("normalize", i32), ("B", i32), ("H", i32), ("W", i32),
+        ("resolution_level", i32), ("camera_k", vp), ("ray_scales", vp), ("workspace", vp),
+        ("workspace_bytes", C.c_size_t),
+        ("confidence", vp), ("intrinsics", vp), ("radius", vp), ("depth", vp), ("points", vp), ("rays", vp),
+        ("depth_features", vp),
+    ]
+
+
+DT_F16, DT_F32 = 0, 1
+
 EXPORTS = {
     "udb_version": (i32, []),
     "udb_last_error": (C.c_char_p, []),
@@ -109,6 +137,14 @@ EXPORTS = {
     "udb_reflect_pad1_nhwc_f16": (i32, [vp, vp, i32, i32, i32, i32, vp]),
     "udb_reflect_border_fill_nhwc_f16": (i32, [vp, i32, i32, i32, i32, vp]),
     "udb_postprocess": (i32, [C.POINTER(Postprocess), vp]),
+    "udb_camera_adjust_k": (i32, [vp, i32, f32, i32, i32, vp, vp]),
+    "udb_create": (i32, [C.POINTER(Config), C.POINTER(vp)]),
+    "udb_destroy": (None, [vp]),
+    "udb_set_weight": (i32, [vp, C.c_char_p, vp, C.POINTER(i64), i32, i32]),
+    "udb_set_scalar": (i32, [vp, C.c_char_p, C.c_double]),
+    "udb_geometry": (i32, [vp, i32, i32, i32, C.POINTER(Geometry)]),
+    "udb_workspace_bytes": (C.c_size_t, [vp, i32, i32, i32, i32]),
+    "udb_infer_v2": (i32, [vp, C.POINTER(InferArgs), vp]),
 }
 
 _lib = None

@@ -579,6 +579,27 @@ extern "C" int udb_camera_intrinsics(const float* x, int32_t B, int32_t net_h, i
   return check_launch("camera_intrinsics_kernel");
 }
 
+// infer(camera=K): the reference wraps K in Pinhole/BatchCamera, shifts the principal point by the
+// paddings (`crop`, utils/camera.py:115-120) and scales by the resize factor (`resize`, :78-81) before
+// generating rays; (fx, fy, cx, cy) in network-input pixels, float32 like the reference.
+__global__ void camera_adjust_k_kernel(const float* __restrict__ K, int B, float factor, float pad_l, float pad_t,
+                                       float* __restrict__ intr4) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float* k = K + b * 9;
+  intr4[b * 4 + 0] = k[0] * factor;
+  intr4[b * 4 + 1] = k[4] * factor;
+  intr4[b * 4 + 2] = (k[2] + pad_l) * factor;
+  intr4[b * 4 + 3] = (k[5] + pad_t) * factor;
+}
+
+extern "C" int udb_camera_adjust_k(const float* K, int32_t B, float factor, int32_t pad_l, int32_t pad_t, float* intr4,
+                                   void* stream) {
+  camera_adjust_k_kernel<<<(B + 63) / 64, 64, 0, ST(stream)>>>(K, B, factor, static_cast<float>(pad_l),
+                                                              static_cast<float>(pad_t), intr4);
+  return check_launch("camera_adjust_k_kernel");
+}
+
 extern "C" int udb_ray_embed(const udb_ray_embed_t* p, void* stream) {
   const int toks = p->B * p->gh * p->gw;
   ray_embed_kernel<<<(toks + 7) / 8, 256, 0, ST(stream)>>>(*p);

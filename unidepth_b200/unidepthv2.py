@@ -17,6 +17,7 @@ raises.
 """
 from __future__ import annotations
 
+import ctypes as C
 import json
 import math
 import os
@@ -26,6 +27,7 @@ from typing import Dict, Optional
 import torch
 import torch.nn as nn
 
+from . import _cabi as cabi
 from . import ops
 from .spec import ModelSpec, PATCH, get_paddings, get_resize_factor, param_shapes, pixel_bounds
 
@@ -72,6 +74,10 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
         self.shape_constraints = dict(s.shape_constraints)   # mutable, read by infer (unidepthv2.py:459)
         self.interpolation_mode = "bilinear"                 # unidepthv2.py:460
         self.use_cuda_graph = True
+        self.use_engine = True        # False: schedule the same kernels from Python (ops.*; debugging taps / per-kernel timing)
+        self._engine = None
+        self._engine_key = None
+        self._workspaces: Dict[tuple, torch.Tensor] = {}
         self._packed: Optional[dict] = None
         self._packed_key = None
         self._graphs: Dict[tuple, dict] = {}
@@ -255,6 +261,130 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
         self._packed_key = self._fingerprint()
         self._graphs.clear()
         self._posembed_cache.clear()
+        self._drop_engine()
+
+    # ------------------------------------------------------------------ C engine (udb_create / udb_infer_v2)
+    def _drop_engine(self):
+        if self._engine is not None:
+            cabi.lib().udb_destroy(self._engine)
+        self._engine, self._engine_key = None, None
+        self._workspaces.clear()
+
+    def __del__(self):
+        try:
+            self._drop_engine()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _flatten_packed(P: dict):
+        """Packed-weight dict -> ({engine tensor name: tensor}, {scalar name: float}) (names: include/udb.h,
+        DESIGN.md 'packed tensors')."""
+        T, S = {}, {}
+        for k in ("patch_w", "patch_b", "cls", "pos", "norm_w", "norm_b", "lat_w", "lat_b", "head_mlp_w", "head_mlp_b",
+                  "ln_ones", "ln_zeros"):
+            T[k] = P[k]
+        for i, blk in enumerate(P["blocks"]):
+            for k, v in blk.items():
+                T[f"blocks.{i}.{k}"] = v
+        for l in range(4):
+            T[f"adapt.{l}.w"], T[f"adapt.{l}.b"] = P["adapt"][l]
+            T[f"cam_adapt.{l}.w"], T[f"cam_adapt.{l}.b"] = P["cam_adapt"][l]
+            for k, v in P["prompt"][l].items():
+                T[f"prompt.{l}.{k}"] = v
+        cam = P["cam"]
+        T["cam.pos"] = cam["pos"]
+        for name in ("project", "pinhole"):
+            for k, v in cam[name].items():
+                T[f"cam.{name}.{k}"] = v
+        for name in ("agg1", "agg2"):
+            for k, v in cam[name].items():
+                if k == "mlp":
+                    for k2, v2 in v.items():
+                        T[f"cam.{name}.mlp.{k2}"] = v2
+                else:
+                    T[f"cam.{name}.{k}"] = v
+        for i, st in enumerate(P["ups"]):
+            for k in ("ct_w", "ct_b", "up_w", "up_b"):
+                T[f"ups.{i}.{k}"] = st[k]
+            for j, r in enumerate(st["rcus"]):
+                for k, v in r.items():
+                    T[f"ups.{i}.rcu.{j}.{k}"] = v
+        for i, hd in enumerate(P["heads"]):
+            for k in ("lr_w", "lr_b", "hr_w", "hr_b", "head_w"):
+                T[f"heads.{i}.{k}"] = hd[k]
+            S[f"heads.{i}.head_b"] = hd["head_b"]
+            S[f"heads.{i}.add"] = hd["add"]
+        return T, S
+
+    def _get_engine(self):
+        P = self._weights()
+        sc = self.shape_constraints
+        key = (tuple(sc["ratio_bounds"]), sc["pixels_min"], sc["pixels_max"])
+        if self._engine is not None and self._engine_key == key:
+            return self._engine
+        self._drop_engine()
+        s = self.spec
+        cfg = cabi.Config()
+        cfg.embed_dim, cfg.depth, cfg.enc_heads = s.embed_dim, s.depth, s.enc_heads
+        for i, t in enumerate(s.taps):
+            cfg.taps[i] = t
+        cfg.pos_grid = int(math.isqrt(P["pos"].shape[0] - 1))
+        cfg.hidden, cfg.dec_heads, cfg.expansion, cfg.out_dim = s.hidden, s.dec_heads, s.expansion, s.out_dim
+        cfg.n_stages = len(s.dec_depths)
+        for i, dd in enumerate(s.dec_depths):
+            cfg.dec_depths[i] = dd
+        cfg.ratio_min, cfg.ratio_max = sc["ratio_bounds"]
+        cfg.pixels_min, cfg.pixels_max = sc["pixels_min"], sc["pixels_max"]
+        handle = C.c_void_p()
+        cabi.check(cabi.lib().udb_create(C.byref(cfg), C.byref(handle)), "udb_create")
+        tensors, scalars = self._flatten_packed(P)
+        for name, t in tensors.items():
+            assert t.is_cuda and t.is_contiguous() and t.dtype in (f16, f32), name
+            shape = (C.c_int64 * max(t.ndim, 1))(*t.shape)
+            cabi.check(cabi.lib().udb_set_weight(handle, name.encode(), C.c_void_p(t.data_ptr()), shape, t.ndim,
+                                                 cabi.DT_F32 if t.dtype == f32 else cabi.DT_F16), f"udb_set_weight({name})")
+        for name, v in scalars.items():
+            cabi.check(cabi.lib().udb_set_scalar(handle, name.encode(), float(v)), f"udb_set_scalar({name})")
+        self._engine, self._engine_key = handle, key
+        self._engine_tensors = tensors          # the engine borrows these pointers
+        return handle
+
+    def _forward_engine(self, rgb: torch.Tensor, geom: dict, normalize: bool, level, camera_k=None):
+        """The whole path as ONE C call (udb_infer_v2): torch only allocates outputs / workspace."""
+        eng = self._get_engine()
+        lib = cabi.lib()
+        dev = rgb.device
+        B, _, H, W = rgb.shape
+        lvl = -1 if level is None else int(level)
+        g = cabi.Geometry()
+        cabi.check(lib.udb_geometry(eng, H, W, lvl, C.byref(g)), "udb_geometry")
+        assert (g.net_h, g.net_w) == tuple(geom["net_hw"]) and (g.pad_l, g.pad_r, g.pad_t, g.pad_b) == tuple(geom["paddings"])
+        wkey = (B, H, W, lvl)
+        ws = self._workspaces.get(wkey)
+        if ws is None:
+            nbytes = lib.udb_workspace_bytes(eng, B, H, W, lvl)
+            if nbytes == 0:
+                raise RuntimeError(f"udb_workspace_bytes failed: {lib.udb_last_error().decode()}")
+            ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+            self._workspaces[wkey] = ws
+        hid = self.spec.hidden
+        E = lambda *shape: torch.empty(shape, device=dev, dtype=f32)
+        out = {"confidence": E(B, 1, H, W), "intrinsics": E(B, 3, 3), "radius": E(B, 1, H, W), "depth": E(B, 1, H, W),
+               "points": E(B, 3, H, W), "rays": E(B, 3, H, W)}
+        feats = E(B, g.gh, g.gw, hid)
+        a = cabi.InferArgs()
+        a.rgb, a.rgb_is_u8, a.normalize = rgb.data_ptr(), int(rgb.dtype == torch.uint8), int(normalize)
+        a.B, a.H, a.W, a.resolution_level = B, H, W, lvl
+        a.camera_k = camera_k.data_ptr() if camera_k is not None else None
+        a.ray_scales = geom["scales"].data_ptr()
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        for k, v in out.items():
+            setattr(a, k, v.data_ptr())
+        a.depth_features = feats.data_ptr()
+        cabi.check(lib.udb_infer_v2(eng, C.byref(a), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "udb_infer_v2")
+        out["depth_features"] = feats.permute(0, 3, 1, 2)
+        return out
 
     def _weights(self):
         if self._packed is None or self._packed_key != self._fingerprint():
@@ -490,28 +620,39 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
             self._posembed_cache[skey] = (2.0 ** torch.linspace(0.0, math.log2(max(gh, gw) // 2), steps=bands)).to(dev)
         geom["scales"] = self._posembed_cache[skey]
 
-        gt_intr4 = None
+        gt_intr4, camera_k = None, None
         if camera is not None:
-            gt_intr4 = self._gt_intrinsics(camera, B, paddings, factor, dev)
+            gt_intr4 = self._gt_intrinsics(camera, B, paddings, factor, dev)     # validates the argument
+            camera_k = camera.to(dev, f32).reshape(-1, 3, 3)
+            if camera_k.shape[0] == 1 and B > 1:
+                camera_k = camera_k.expand(B, 3, 3)
+            camera_k = camera_k.contiguous()
 
         self._weights()
-        self._pos_embed(gh, gw)
-        if not self.use_cuda_graph or gt_intr4 is not None:
-            return self._forward(rgb, geom, normalize, gt_intr4=gt_intr4)
 
-        key = (B, H, W, rgb.dtype, level, bool(normalize), tuple(self.shape_constraints["ratio_bounds"]), bounds)
+        def run(inp):
+            if self.use_engine:
+                return self._forward_engine(inp, geom, normalize, level, camera_k=camera_k)
+            self._pos_embed(gh, gw)
+            return self._forward(inp, geom, normalize, gt_intr4=gt_intr4)
+
+        if not self.use_cuda_graph or camera is not None:
+            return run(rgb)
+
+        key = (B, H, W, rgb.dtype, level, bool(normalize), tuple(self.shape_constraints["ratio_bounds"]), bounds,
+               bool(self.use_engine))
         entry = self._graphs.get(key)
         if entry is None:
             static_in = rgb.clone()
-            # warm-up on a side stream (allocator + lazy module state), then capture
+            # warm-up on a side stream (allocator, per-shape tables, workspace), then capture
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                self._forward(static_in, geom, normalize)
+                run(static_in)
             torch.cuda.current_stream().wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                static_out = self._forward(static_in, geom, normalize)
+                static_out = run(static_in)
             entry = dict(graph=graph, inp=static_in, out=static_out)
             self._graphs[key] = entry
         entry["inp"].copy_(rgb, non_blocking=True)

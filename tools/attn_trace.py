@@ -1,5 +1,5 @@
 """Event timeline of one attention CTA (needs a -DUDB_ATTN_TRACE variant build, see tools/build_variant.sh).
-Columns are clock64 deltas relative to the softmax warp's 's_full seen' of each tile."""
+Times are clock64 deltas relative to the first softmax event; sm = softmax warp 2, mma = the MMA warp."""
 import ctypes
 import os
 import sys
@@ -20,8 +20,8 @@ buf = (ctypes.c_longlong * (32 * 16))()
 lib.udb_attn_trace_read(buf)
 ev = [[buf[j * 16 + k] for k in range(16)] for j in range(13)]
 t0 = ev[0][0]
-names = {0: "sm:s_full", 1: "sm:ld", 2: "sm:exp", 3: "sm:s_free!", 4: "sm:p_free", 5: "sm:p_full!",
-         8: "mma:s_free", 9: "mma:qk_iss", 10: "mma:p_full", 11: "mma:pv_iss"}
+names = {0: "sm:sA_full", 1: "sm:A_done", 2: "sm:sB_full", 3: "sm:B_done", 4: "sm:p_free", 5: "sm:p_full!",
+         8: "mma:sA_free", 9: "mma:qkA_iss", 10: "mma:sB_free", 11: "mma:qkB_iss", 12: "mma:p_full", 13: "mma:pv_iss"}
 for j in range(13):
     items = sorted((ev[j][k] - t0, names[k]) for k in names if ev[j][k])
     print(f"tile {j:2d}: " + "  ".join(f"{n}@{t}" for t, n in items))

@@ -1,54 +1,45 @@
 // Fused attention forward for sm_100a:  O = softmax(Q K^T * scale) V   (no mask, no dropout)
 //
 // One CTA = one (batch, head, 128-query tile); two CTAs are resident per SM (TMEM 2 x 256 columns,
-// <= 113 KB shared memory each).  Keys are processed in tiles of 128:
+// <= 113 KB shared memory each).  Keys are processed in tiles of 128, each as two 64-key HALVES with
+// their own score buffer and barriers:
 //   warp 0      : TMA producer (Q once; K_j / V_j tiles through two independent 2-stage rings)
-//   warp 1      : TMEM allocator + MMA issuer.  S_j = Q K_j^T (M128 N128 K64) into TMEM; the softmax
-//                 warps copy the whole score row to registers first thing and release the buffer, so
-//                 S_{j+1} is computed while they work on tile j.  O += P_j V_j (M128 N64 K128, V is the
-//                 MN-major B operand) accumulates in TMEM.
-//   warps 2..5  : softmax, one query row per thread, 128 scores in registers: row max / sum in fp32
-//                 with packed f32x2 math (optional FMA-pipe polynomial exp2, off by default), P_j as f16
-//                 into 128B-swizzled shared memory.  O is rescaled lazily: only when a row maximum
-//                 grows by more than 2^8 over the reference the probabilities are expressed against.
+//   warp 1      : TMEM allocator + MMA issuer (whole warp in the control flow, one elected lane issues).
+//                 S_j^h = Q (K_j^h)^T (M128 N64 K64) into TMEM columns [64h, 64h+64); as soon as the
+//                 softmax warps release half h of tile j the same half of tile j+1 is issued, so the
+//                 QK^T latency (4 MMAs + commit round trip, ~500 clk) hides behind the softmax of the
+//                 other half.  O += P_j V_j (M128 N64 K128, V is the MN-major B operand) accumulates
+//                 in TMEM columns [128, 192).
+//   warps 2..5  : softmax, one query row per thread, 64 scores at a time in registers.  SPECULATIVE
+//                 single pass: exp2(s*scale - m_ref) against the current reference maximum and the
+//                 half's row maximum in the same loop (MUFU and ALU pipes overlap); only if some row's
+//                 maximum outgrew the reference by more than 2^8 (rare after the first tile) the half is
+//                 redone from the scores still in TMEM and O / l / the already packed half are rescaled
+//                 (lazy rescale).  fp32 max / sum with packed f32x2 math; P_j as f16 through
+//                 128B-swizzled shared memory.
+// Measured structure (tools/attn_trace.py, tools/mma_probe.cu, B200): a single softmax warp needs
+// ~12 clk per MUFU.EX2 (in-order issue, two such warps share a sub-partition's MUFU), a tcgen05.mma
+// burst has ~280 clk of fixed issue-to-mbarrier latency, SS-mode M128 N64 K16 takes 53 clk.
 // Replaces F.scaled_dot_product_attention (reference: metadinov2/attention.py:58,
 // layers/attention.py:136).
 #include "common.h"
 #include "ptx.cuh"
 
-// every UDB_ATTN_POLY-th pair of probabilities uses the FMA-pipe polynomial exp2 (0 = never).
-// Measured on B200 (8x16x1611^2): POLY 0: 162 us, 4: 174 us, 2: 180 us -- the kernel is issue /
-// latency bound (2 softmax warps per SM sub-partition), not MUFU bound, so the extra FMA-pipe
-// instructions cost more than the MUFU work they save; kept as a compile-time option.
-#ifndef UDB_ATTN_POLY
-#define UDB_ATTN_POLY 0
-#endif
-
 namespace udb {
 
 constexpr int AT_BQ = 128;       // queries per CTA
-#ifndef UDB_ATTN_SPEC
-#define UDB_ATTN_SPEC 1   // speculative exp2 against the running reference (rare redo)
-#endif
-#ifdef UDB_ATTN_TIMING   // variant build only: per-phase clock64 accumulation in the softmax warps
-__device__ unsigned long long g_attn_phase[8];
-#define AT_TICK(k) do { const long long t_now = clock64(); t_acc[k] += t_now - t_prev; t_prev = t_now; } while (0)
-#else
-#define AT_TICK(k) do {} while (0)
-#endif
-#ifdef UDB_ATTN_TRACE   // variant build only: event timeline of CTA (1,0,0): softmax warp 2 + the MMA thread
+constexpr int AT_BK = 128;       // keys per tile
+constexpr int AT_HK = 64;        // keys per half tile (softmax / QK^T granularity)
+constexpr int AT_CTAS_PER_SM = 2;
+constexpr int AT_KV_STAGES = 2;  // per ring
+constexpr int AT_THREADS = 192;  // TMA warp, MMA warp, 4 softmax warps
+
+#ifdef UDB_ATTN_TRACE   // variant build only: event timeline of CTA (1,0,0): softmax warp 2 + the MMA warp
 __device__ long long g_attn_trace[32 * 16];
 #define AT_EV(j, k) do { if (trace_on && (j) < 32) g_attn_trace[(j) * 16 + (k)] = clock64(); } while (0)
 #else
 #define AT_EV(j, k) do {} while (0)
 #endif
-#ifndef UDB_ATTN_BK
-#define UDB_ATTN_BK 128
-#endif
-constexpr int AT_BK = UDB_ATTN_BK;   // keys per tile (128: 2 CTAs/SM; 64: 3 CTAs/SM)
-constexpr int AT_CTAS_PER_SM = AT_BK == 128 ? 2 : 3;
-constexpr int AT_KV_STAGES = 2;  // per ring
-constexpr int AT_THREADS = 192;  // TMA warp, MMA warp, 4 softmax warps
 
 struct AttnArgs {
   __half* out;
@@ -64,71 +55,43 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-// exp2 of two values on the FMA / ALU pipes (no MUFU): x = n + f with n = round(x), f in [-0.5, 0.5];
-// 2^f by a degree-3 minimax polynomial (max relative error 7.6e-5, far below the f16 rounding of P);
-// 2^n is added into the exponent field.  Requires -126 < x < 126 (callers clamp the scores).
-__device__ __forceinline__ void exp2_poly_pair(const uint64_t x2, float& e0, float& e1) {
-  const uint64_t magic = pack2(12582912.f, 12582912.f);        // 1.5 * 2^23: x + magic rounds to integer
-  const uint64_t t2 = add2(x2, magic);
-  const uint64_t n2 = add2(t2, pack2(-12582912.f, -12582912.f));
-  const uint64_t f2 = fma2(n2, pack2(-1.f, -1.f), x2);
-  uint64_t q = fma2(pack2(0.05520550534129143f, 0.05520550534129143f), f2, pack2(0.24261397123336792f, 0.24261397123336792f));
-  q = fma2(q, f2, pack2(0.6932547688484192f, 0.6932547688484192f));
-  q = fma2(q, f2, pack2(0.9999276995658875f, 0.9999276995658875f));
-  float p0, p1, t0, t1;
-  unpack2(q, p0, p1);
-  unpack2(t2, t0, t1);
-  e0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23));
-  e1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
-}
-
-// exp2(s*scale - m) for the 128 scores of one row; returns the row sum; P (f16) packed in place into
-// sv[0..63].  MASK: only the first kv_left entries are valid keys (last tile).  The MUFU unit
-// (16 ex2 / clk / SM) is the bottleneck of d=64 attention, so every second pair of elements is
-// computed with the polynomial instead.
+// exp2(s*scale - m) for the 64 scores of one half row; returns their sum; P (f16 pairs) into pk[0..31].
+// MASK: only the first kv_left entries are valid keys (last tile; kv_left may be <= 0).
 template <bool MASK>
-__device__ __forceinline__ float softmax_row(uint32_t (&sv)[AT_BK], const float sc, const float m_used,
-                                             const int kv_left) {
+__device__ __forceinline__ float softmax_half(const uint32_t (&sv)[AT_HK], uint32_t* pk, const float sc, const float m_used,
+                                              const int kv_left) {
   const uint64_t sc2 = pack2(sc, sc), nm2 = pack2(-m_used, -m_used);
-  const float s_floor = (m_used - 100.0f) / sc;      // scores below this give exp2(< -100) = 0 in f16 anyway
   uint64_t ps[4] = {0ull, 0ull, 0ull, 0ull};   // independent partial sums: no serial FADD chain behind the MUFUs
 #pragma unroll
-  for (int i = 0; i < AT_BK; i += 2) {
-    float e0, e1;
-    if (UDB_ATTN_POLY > 0 && ((i >> 1) % (UDB_ATTN_POLY > 0 ? UDB_ATTN_POLY : 1)) == (UDB_ATTN_POLY > 0 ? UDB_ATTN_POLY : 1) - 1) {
-      const float s0 = fmaxf(__uint_as_float(sv[i]), s_floor), s1 = fmaxf(__uint_as_float(sv[i + 1]), s_floor);
-      exp2_poly_pair(fma2(pack2(s0, s1), sc2, nm2), e0, e1);
-    } else {
-      float t0, t1;
-      unpack2(fma2(pack2u(sv[i], sv[i + 1]), sc2, nm2), t0, t1);
-      e0 = ex2(t0);
-      e1 = ex2(t1);
-    }
+  for (int i = 0; i < AT_HK; i += 2) {
+    float t0, t1;
+    unpack2(fma2(pack2u(sv[i], sv[i + 1]), sc2, nm2), t0, t1);
+    float e0 = ex2(t0), e1 = ex2(t1);
     if (MASK) {
       e0 = (i < kv_left) ? e0 : 0.f;
       e1 = (i + 1 < kv_left) ? e1 : 0.f;
     }
     ps[(i >> 1) & 3] = add2(ps[(i >> 1) & 3], pack2(e0, e1));
-    sv[i >> 1] = pack_half2(e0, e1);   // pair i -> word i/2 (already consumed)
+    pk[i >> 1] = pack_half2(e0, e1);
   }
   float ps0, ps1;
   unpack2(add2(add2(ps[0], ps[1]), add2(ps[2], ps[3])), ps0, ps1);
   return ps0 + ps1;
 }
 
-// Speculative variant: probabilities against the CURRENT reference m_used AND the tile's row maximum
+// Speculative variant: probabilities against the CURRENT reference m_used AND the half's row maximum
 // in one pass, so the max (ALU pipe, FMNMX3) overlaps the exp2 (MUFU pipe) instead of preceding it.
 // The caller checks afterwards that the maximum did not outgrow the reference by more than the
 // lazy-rescale threshold; if it did (rare) the results -- possibly overflowed -- are discarded and
-// the tile is redone from the scores still held in TMEM.
+// the half is redone from the scores still held in TMEM.
 template <bool MASK>
-__device__ __forceinline__ float softmax_row_spec(uint32_t (&sv)[AT_BK], const float sc, const float m_used,
-                                                  const int kv_left, float& mx_out) {
+__device__ __forceinline__ float softmax_half_spec(const uint32_t (&sv)[AT_HK], uint32_t* pk, const float sc,
+                                                   const float m_used, const int kv_left, float& mx_out) {
   const uint64_t sc2 = pack2(sc, sc), nm2 = pack2(-m_used, -m_used);
   uint64_t ps[4] = {0ull, 0ull, 0ull, 0ull};
   float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
-  for (int i = 0; i < AT_BK; i += 2) {
+  for (int i = 0; i < AT_HK; i += 2) {
     const float s0 = __uint_as_float(sv[i]), s1 = __uint_as_float(sv[i + 1]);
     float t0, t1;
     unpack2(fma2(pack2(s0, s1), sc2, nm2), t0, t1);
@@ -144,7 +107,7 @@ __device__ __forceinline__ float softmax_row_spec(uint32_t (&sv)[AT_BK], const f
       m0 = max3(m0, s0, s1);
     }
     ps[(i >> 1) & 3] = add2(ps[(i >> 1) & 3], pack2(e0, e1));
-    sv[i >> 1] = pack_half2(e0, e1);
+    pk[i >> 1] = pack_half2(e0, e1);
   }
   mx_out = fmaxf(m0, m1);
   float ps0, ps1;
@@ -153,17 +116,17 @@ __device__ __forceinline__ float softmax_row_spec(uint32_t (&sv)[AT_BK], const f
 }
 
 template <bool MASK>
-__device__ __forceinline__ float row_max(const uint32_t (&sv)[AT_BK], const int kv_left) {
+__device__ __forceinline__ float half_max(const uint32_t (&sv)[AT_HK], const int kv_left) {
   float m0 = -INFINITY, m1 = -INFINITY;    // two chains for ILP
   if (!MASK) {
 #pragma unroll
-    for (int i = 0; i < AT_BK; i += 4) {
+    for (int i = 0; i < AT_HK; i += 4) {
       m0 = max3(m0, __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]));
       m1 = max3(m1, __uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3]));
     }
   } else {
 #pragma unroll
-    for (int i = 0; i < AT_BK; ++i) m0 = (i < kv_left) ? fmaxf(m0, __uint_as_float(sv[i])) : m0;
+    for (int i = 0; i < AT_HK; ++i) m0 = (i < kv_left) ? fmaxf(m0, __uint_as_float(sv[i])) : m0;
   }
   return fmaxf(m0, m1);
 }
@@ -176,7 +139,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   constexpr int kQBytes = AT_BQ * HD * 2;      // 16 KB
   constexpr int kKBytes = AT_BK * HD * 2;      // 16 KB
   constexpr int kPBytes = AT_BQ * AT_BK * 2;   // 32 KB (two 64-key sub-tiles of 16 KB)
-  constexpr uint32_t kTmemCols = AT_BK == 128 ? 256 : 128;   // S: [0,AT_BK)  O: [AT_BK, AT_BK+64)
+  constexpr uint32_t kTmemCols = 256;          // S halves: [0,64) [64,128)   O: [128,192)
   constexpr int NS = AT_KV_STAGES;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
@@ -187,11 +150,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* q_full = bars;
   uint64_t* k_full = bars + 1;             // [NS]
   uint64_t* v_full = k_full + NS;          // [NS]
-  uint64_t* k_empty = v_full + NS;         // [NS]  K stage free once its QK MMA has completed
+  uint64_t* k_empty = v_full + NS;         // [NS]  K stage free once both QK half MMAs have completed
   uint64_t* v_empty = k_empty + NS;        // [NS]  V stage free once its PV MMA has completed
-  uint64_t* s_full = v_empty + NS;         // S_j complete in TMEM
-  uint64_t* s_free = s_full + 1;           // S_j copied to registers by all softmax warps
-  uint64_t* p_full = s_free + 1;           // P_j written to smem
+  uint64_t* s_full = v_empty + NS;         // [2]   S_j^h complete in TMEM
+  uint64_t* s_free = s_full + 2;           // [2]   S_j^h consumed by all softmax warps
+  uint64_t* p_full = s_free + 2;           // P_j written to smem
   uint64_t* p_free = p_full + 1;           // PV_j MMA done (one phase per tile)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(p_free + 1);
 
@@ -215,8 +178,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(&k_empty[i], 1);
       mbar_init(&v_empty[i], 1);
     }
-    mbar_init(s_full, 1);
-    mbar_init(s_free, 4);
+    for (int h = 0; h < 2; ++h) {
+      mbar_init(&s_full[h], 1);
+      mbar_init(&s_free[h], 4);
+    }
     mbar_init(p_full, 4);
     mbar_init(p_free, 1);
     fence_barrier_init();
@@ -257,55 +222,60 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
   } else if (warp == 1) {
     // The whole warp runs the control flow so that descriptors and addresses stay in uniform registers
-    // (under a lane-0 branch ptxas wraps every tcgen05.mma in an ELECT / R2UR waterfall loop that costs
-    // ~90 cycles per instruction); one elected lane issues the MMAs and commits.
+    // (under a lane-0 branch ptxas wraps every tcgen05.mma in an ELECT / R2UR waterfall loop);
+    // one elected lane issues the MMAs and commits.
     const bool leader = elect_one();
-    {
-      constexpr uint32_t idesc_qk = umma_idesc_f16(AT_BQ, AT_BK, false, false);
-      constexpr uint32_t idesc_pv = umma_idesc_f16(AT_BQ, HD, false, true);   // B = V is MN-major
-      const uint64_t dq = umma_desc_sw128(smem_u32(sQ), 16, 1024);
-      auto issue_qk = [&](int j) {   // S = Q K_j^T
-        const int st = j % NS;
+    constexpr uint32_t idesc_qk = umma_idesc_f16(AT_BQ, AT_HK, false, false);
+    constexpr uint32_t idesc_pv = umma_idesc_f16(AT_BQ, HD, false, true);   // B = V is MN-major
+    const uint64_t dq = umma_desc_sw128(smem_u32(sQ), 16, 1024);
+    auto issue_qk = [&](int j, int h) {   // S^h = Q (K_j rows [64h, 64h+64))^T
+      const int st = j % NS;
+      if (h == 0) {
         mbar_wait(&k_full[st], (j / NS) & 1);
         tc_fence_after_sync();
-        const uint64_t dk = umma_desc_sw128(smem_u32(sK + st * kKBytes), 16, 1024);
-        if (leader) {
-#pragma unroll
-          for (int k = 0; k < HD / 16; ++k) umma_f16_ss(tmem_base, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0);
-          umma_commit(&k_empty[st]);
-          umma_commit(s_full);
-        }
-        __syncwarp();
-      };
-      mbar_wait(q_full, 0);
-      issue_qk(0);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int st = j % NS;
-        if (j + 1 < n_tiles) {
-          mbar_wait(s_free, j & 1);                // score row of tile j is in registers: S may be overwritten
-          AT_EV(j, 8);
-          issue_qk(j + 1);
-          AT_EV(j, 9);
-        }
-        mbar_wait(p_full, j & 1);                  // P_j written
-        AT_EV(j, 10);
-        mbar_wait(&v_full[st], (j / NS) & 1);
-        tc_fence_after_sync();
-        const uint64_t dv = umma_desc_sw128(smem_u32(sV + st * kKBytes), 1024, 1024);
-        const uint64_t dp0 = umma_desc_sw128(smem_u32(sP), 16, 1024);
-        if (leader) {
-#pragma unroll
-          for (int ks = 0; ks < AT_BK / 16; ++ks) {
-            // A = P: sub-tile (ks/4) of 16 KB, 32 B per 16-key step inside the swizzle atom; B = V: 2 KB per step
-            const uint64_t dp = dp0 + (uint64_t)((ks >> 2) * (AT_BQ * 128) >> 4) + 2 * (ks & 3);
-            umma_f16_ss(tmem_O, dp, dv + (uint64_t)(ks * 2048 >> 4), idesc_pv, (j | ks) != 0);
-          }
-          umma_commit(&v_empty[st]);
-          umma_commit(p_free);
-        }
-        __syncwarp();
-        AT_EV(j, 11);
       }
+      const uint64_t dk = umma_desc_sw128(smem_u32(sK + st * kKBytes + h * (AT_HK * 128)), 16, 1024);
+      if (leader) {
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) umma_f16_ss(tmem_base + h * AT_HK, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0);
+        if (h == 1) umma_commit(&k_empty[st]);
+        umma_commit(&s_full[h]);
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    issue_qk(0, 0);
+    issue_qk(0, 1);
+    for (int j = 0; j < n_tiles; ++j) {
+      const int st = j % NS;
+      if (j + 1 < n_tiles) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait(&s_free[h], j & 1);            // half h of tile j consumed: its columns may be overwritten
+          tc_fence_after_sync();
+          AT_EV(j, 8 + 2 * h);
+          issue_qk(j + 1, h);
+          AT_EV(j, 9 + 2 * h);
+        }
+      }
+      mbar_wait(p_full, j & 1);                    // P_j written
+      AT_EV(j, 12);
+      mbar_wait(&v_full[st], (j / NS) & 1);
+      tc_fence_after_sync();
+      const uint64_t dv = umma_desc_sw128(smem_u32(sV + st * kKBytes), 1024, 1024);
+      const uint64_t dp0 = umma_desc_sw128(smem_u32(sP), 16, 1024);
+      if (leader) {
+#pragma unroll
+        for (int ks = 0; ks < AT_BK / 16; ++ks) {
+          // A = P: sub-tile (ks/4) of 16 KB, 32 B per 16-key step inside the swizzle atom; B = V: 2 KB per step
+          const uint64_t dp = dp0 + (uint64_t)((ks >> 2) * (AT_BQ * 128) >> 4) + 2 * (ks & 3);
+          umma_f16_ss(tmem_O, dp, dv + (uint64_t)(ks * 2048 >> 4), idesc_pv, (j | ks) != 0);
+        }
+        umma_commit(&v_empty[st]);
+        umma_commit(p_free);
+      }
+      __syncwarp();
+      AT_EV(j, 13);
     }
   } else {
     // ------------------------------------------------------------------ softmax warps
@@ -316,115 +286,108 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int sw = row & 7;
     const float sc = p.scale_log2;
     constexpr float kRescaleThreshold = 8.0f;   // log2 domain
+    uint32_t pk[AT_BK / 2];                     // P row of the current tile, f16 pairs
 
-#ifdef UDB_ATTN_TIMING
-    long long t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    long long t_prev = clock64();
-#endif
     for (int j = 0; j < n_tiles; ++j) {
-      mbar_wait(s_full, j & 1);
-      tc_fence_after_sync();
-      AT_TICK(0);
-      AT_EV(j, 0);
       const int kv_left = p.seq_k - j * AT_BK;   // valid keys in this tile (>= 1)
-      const bool full = kv_left >= AT_BK;
-      uint32_t sv[AT_BK];
-      auto load_scores = [&]() {
+      bool pv_done = false;                      // PV_{j-1} known complete (needed before O / sP are touched)
 #pragma unroll
-        for (int c = 0; c < AT_BK; c += 32)
-          tmem_ld_32x32b_x32(tmem_base + lane_addr + c, *reinterpret_cast<uint32_t(*)[32]>(&sv[c]));
-        tmem_ld_wait();
-      };
-      load_scores();
-      if (!UDB_ATTN_SPEC) {   // scores are in registers: S may be overwritten by the next QK^T right away
-        tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(s_free);
-      }
-      AT_TICK(1);
-      AT_EV(j, 1);
-      bool careful = (j == 0) || !UDB_ATTN_SPEC;   // first tile: no reference yet
-      bool pv_done = false;
-      if (!careful) {
-        // common case: exp2 against the current reference and the row max in the same pass
-        float mx;
-        const float psum = full ? softmax_row_spec<false>(sv, sc, m_used, kv_left, mx)
-                                : softmax_row_spec<true>(sv, sc, m_used, kv_left, mx);
-        careful = __any_sync(0xffffffffu, mx * sc > m_used + kRescaleThreshold);
-        if (careful) load_scores();      // rare: the speculative results are discarded
-        else l_run += psum;
-      }
-      if (careful) {
-        const float m_tile = (full ? row_max<false>(sv, kv_left) : row_max<true>(sv, kv_left)) * sc;
-        const bool need = m_tile > m_used + kRescaleThreshold;   // always true on the first tile
-        float alpha = 1.0f;
-        if (need) {
-          alpha = ex2(m_used - m_tile);      // 0 on the first tile
-          m_used = m_tile;
+      for (int h = 0; h < 2; ++h) {
+        mbar_wait(&s_full[h], j & 1);
+        tc_fence_after_sync();
+        AT_EV(j, 2 * h);
+        const int kvl = kv_left - h * AT_HK;     // valid keys in this half (may be <= 0 in the last tile)
+        const bool full = kvl >= AT_HK;
+        uint32_t sv[AT_HK];
+        auto load_scores = [&]() {
+#pragma unroll
+          for (int c = 0; c < AT_HK; c += 32)
+            tmem_ld_32x32b_x32(tmem_base + lane_addr + h * AT_HK + c, *reinterpret_cast<uint32_t(*)[32]>(&sv[c]));
+          tmem_ld_wait();
+        };
+        load_scores();
+        bool careful = (j | h) == 0;             // very first half: no reference yet
+        if (!careful) {
+          // common case: exp2 against the current reference and the row max in the same pass
+          float mx;
+          const float psum = full ? softmax_half_spec<false>(sv, pk + 32 * h, sc, m_used, kvl, mx)
+                                  : softmax_half_spec<true>(sv, pk + 32 * h, sc, m_used, kvl, mx);
+          careful = __any_sync(0xffffffffu, mx * sc > m_used + kRescaleThreshold);
+          if (careful) load_scores();            // rare: the speculative results are discarded
+          else l_run += psum;
         }
-        if (j > 0 && __any_sync(0xffffffffu, need)) {
-          // rescale this warp's 32 rows of O (rows that do not need it multiply by 1)
-          mbar_wait(p_free, (j - 1) & 1);
-          tc_fence_after_sync();
-          pv_done = true;
-          const uint64_t a2 = pack2(alpha, alpha);
-#pragma unroll 1
-          for (int c = 0; c < HD; c += 16) {
-            uint32_t r[16];
-            tmem_ld_32x32b_x16(tmem_O + lane_addr + c, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; i += 2) {
-              float lo, hi;
-              unpack2(mul2(pack2u(r[i], r[i + 1]), a2), lo, hi);
-              r[i] = __float_as_uint(lo);
-              r[i + 1] = __float_as_uint(hi);
-            }
-            tmem_st_32x32b_x16(tmem_O + lane_addr + c, r);
+        if (careful) {
+          const float m_half = (full ? half_max<false>(sv, kvl) : half_max<true>(sv, kvl)) * sc;
+          const bool need = m_half > m_used + kRescaleThreshold;   // always true on the very first half
+          float alpha = 1.0f;
+          if (need) {
+            alpha = ex2(m_used - m_half);          // 0 on the very first half
+            m_used = m_half;
           }
-          tmem_st_wait();
+          if ((j | h) != 0 && __any_sync(0xffffffffu, need)) {
+            if (j > 0) {
+              // rescale this warp's 32 rows of O (rows that do not need it multiply by 1)
+              if (!pv_done) {
+                mbar_wait(p_free, (j - 1) & 1);
+                tc_fence_after_sync();
+                pv_done = true;
+              }
+              const uint64_t a2 = pack2(alpha, alpha);
+#pragma unroll 1
+              for (int c = 0; c < HD; c += 16) {
+                uint32_t r[16];
+                tmem_ld_32x32b_x16(tmem_O + lane_addr + c, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; i += 2) {
+                  float lo, hi;
+                  unpack2(mul2(pack2u(r[i], r[i + 1]), a2), lo, hi);
+                  r[i] = __float_as_uint(lo);
+                  r[i + 1] = __float_as_uint(hi);
+                }
+                tmem_st_32x32b_x16(tmem_O + lane_addr + c, r);
+              }
+              tmem_st_wait();
+            }
+            if (h == 1) {
+              // the first half of this tile was packed against the old reference
+              const __half2 ah = __float2half2_rn(alpha);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                __half2 v = __hmul2(*reinterpret_cast<__half2*>(&pk[i]), ah);
+                pk[i] = *reinterpret_cast<uint32_t*>(&v);
+              }
+            }
+          }
+          const float psum = full ? softmax_half<false>(sv, pk + 32 * h, sc, m_used, kvl)
+                                  : softmax_half<true>(sv, pk + 32 * h, sc, m_used, kvl);
+          l_run = fmaf(l_run, alpha, psum);
         }
-        const float psum = full ? softmax_row<false>(sv, sc, m_used, kv_left) : softmax_row<true>(sv, sc, m_used, kv_left);
-        l_run = fmaf(l_run, alpha, psum);
-      }
-      AT_TICK(2);
-      AT_EV(j, 2);
-      // the score buffer is released only now (the rare path re-reads it); S_{j+1} is then computed
-      // while P_j is packed / stored and is ready when the next iteration starts
-      if (UDB_ATTN_SPEC) {
+        // release this half of the score buffer: the same half of the next tile is computed while the
+        // other half / the P store are being worked on
         tc_fence_before_sync();
         __syncwarp();
-        if (lane == 0) mbar_arrive(s_free);
+        if (lane == 0) mbar_arrive(&s_free[h]);
+        AT_EV(j, 2 * h + 1);
       }
-      AT_TICK(3);
-      AT_EV(j, 3);
       // the PV MMA of tile j-1 must have finished reading sP (the next completion of p_free needs
       // this thread's own arrival on p_full, so the parity is unambiguous)
       if (j > 0 && !pv_done) mbar_wait(p_free, (j - 1) & 1);
-      AT_TICK(4);
       AT_EV(j, 4);
       uint8_t* p_row = sP + row * 128;
 #pragma unroll
       for (int q = 0; q < AT_BK / 8; ++q)      // chunks of 8 halves (16 B); 64-key sub-tiles of 16 KB
         *reinterpret_cast<uint4*>(p_row + (q >> 3) * (AT_BQ * 128) + (((q & 7) ^ sw) << 4)) =
-            make_uint4(sv[4 * q], sv[4 * q + 1], sv[4 * q + 2], sv[4 * q + 3]);
+            make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
       fence_proxy_async_smem();
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
-      AT_TICK(5);
       AT_EV(j, 5);
     }
     // epilogue: O / l
     mbar_wait(p_free, (n_tiles - 1) & 1);   // last PV done => all done
     tc_fence_after_sync();
-    AT_TICK(6);
-#ifdef UDB_ATTN_TIMING
-    if (lane == 0) {
-      for (int k = 0; k < 7; ++k) atomicAdd(&g_attn_phase[k], (unsigned long long)t_acc[k]);
-      atomicAdd(&g_attn_phase[7], (unsigned long long)n_tiles);
-    }
-#endif
     const float inv = 1.0f / l_run;
     const int q = q0 + row;
     __half* op = p.out + ((long long)b * p.seq_q + (q < p.seq_q ? q : 0)) * p.ldo + p.o_col0 + head * HD;
@@ -462,14 +425,6 @@ extern "C" int udb_attn_trace_read(long long* out) {
   return 0;
 }
 #endif
-#ifdef UDB_ATTN_TIMING
-extern "C" int udb_attn_phase_read(unsigned long long* out, int reset) {
-  cudaMemcpyFromSymbol(out, udb::g_attn_phase, sizeof(unsigned long long) * 8);
-  if (reset) { unsigned long long z[8] = {}; cudaMemcpyToSymbol(udb::g_attn_phase, z, sizeof(z)); }
-  return 0;
-}
-#endif
-
 extern "C" int udb_attention_f16(const udb_attn_t* a, void* stream) {
   using namespace udb;
   if (a->head_dim != 64) { set_error("udb_attention_f16: head_dim %d unsupported (64 only)", a->head_dim); return 1; }

@@ -341,6 +341,9 @@ typedef struct udb_infer_args_t {
   int32_t resolution_level;   /* 0..9 or -1 */
   const float* camera_k;      /* optional [B,3,3] pinhole K in input-image pixels (infer(camera=K),
                                  unidepthv2.py:267-303): rays come from it, intrinsics stay predicted */
+  const float* camera_rays;   /* optional [B, net_h*net_w, 3] unit rays at network-input resolution produced by the
+                                 caller's camera model (infer(camera=<Camera object>): camera.crop / resize /
+                                 get_rays, unidepthv2.py:299-303,361-362; decoder.py:400); overrides camera_k */
   const float* ray_scales;    /* optional [hidden/2] frequency table (positional_embedding.py:231-233);
                                  NULL = the engine's own table */
   void* workspace;

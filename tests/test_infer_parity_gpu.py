@@ -261,3 +261,65 @@ def test_c_engine_own_frequency_table_and_errors(shallow):
     a.workspace_bytes, a.H = nbytes, 238            # different patch grid: not prepared
     assert lib.udb_infer_v2(eng, C.byref(a), st) != 0 and b"not prepared" in lib.udb_last_error()
     m.use_cuda_graph = True
+
+
+class _DuckCamera:
+    """Stand-in for the reference's Camera classes (utils/camera.py): same crop / resize / get_rays / to
+    surface and the same in-place semantics; `k1` adds a radial term so the rays are NOT pinhole."""
+
+    def __init__(self, K, k1=0.0):
+        self.K, self.k1 = K.clone().float(), k1
+
+    def to(self, device):
+        self.K = self.K.to(device)
+        return self
+
+    def crop(self, left, top, right=None, bottom=None):
+        self.K[..., 0, 2] -= left
+        self.K[..., 1, 2] -= top
+        return self
+
+    def resize(self, factor):
+        self.K[..., :2, :] *= factor
+        return self
+
+    def get_rays(self, shapes):
+        b, h, w = shapes
+        dev = self.K.device
+        v, u = torch.meshgrid(torch.arange(h, device=dev) + 0.5, torch.arange(w, device=dev) + 0.5, indexing="ij")
+        K = self.K.reshape(-1, 3, 3)
+        x = (u[None] - K[:, 0, 2, None, None]) / K[:, 0, 0, None, None]
+        y = (v[None] - K[:, 1, 2, None, None]) / K[:, 1, 1, None, None]
+        s = 1.0 + self.k1 * (x * x + y * y)
+        rays = torch.stack([x * s, y * s, torch.ones_like(x)], dim=1)
+        return rays / rays.norm(dim=1, keepdim=True).clamp(min=1e-4)
+
+
+def test_camera_object_branch(shallow):
+    """infer(rgb, camera=<object>) (unidepthv2.py:267-303): the object is cropped / resized / asked for
+    rays like the reference does; a pinhole object must reproduce the K-tensor path, a distorted one
+    must return exactly its own rays (after the output resampling) and leave the caller's object intact."""
+    cfg, sd = shallow
+    m = _model(cfg, sd)
+    m.resolution_level = None
+    rgb = _rgb((2, 96, 288), 4)          # padded input: exercises crop
+    K = torch.tensor([[[250.0, 0.0, 140.0], [0.0, 255.0, 50.0], [0.0, 0.0, 1.0]]])
+    ref = m.infer(rgb, camera=K)
+    cam = _DuckCamera(K)
+    for use_engine in (True, False):
+        m.use_engine = use_engine
+        out = m.infer(rgb, camera=cam)
+        assert torch.equal(cam.K, K.float())                       # not mutated
+        assert (out["rays"] - ref["rays"]).abs().max().item() < 2e-5
+        rel = (out["depth"] - ref["depth"]).abs() / ref["depth"]
+        print(f"camera object vs K tensor (engine={use_engine}): depth ARel {rel.mean().item():.3e} max {rel.max().item():.3e}")
+        assert rel.mean().item() < 2e-4 and rel.max().item() < 4e-3
+        assert torch.equal(out["intrinsics"], ref["intrinsics"])   # predicted intrinsics either way
+    m.use_engine = True
+    dist = m.infer(rgb, camera=_DuckCamera(K, k1=-0.2))
+    assert (dist["rays"] - ref["rays"]).abs().max().item() > 1e-3  # a different camera model took effect
+    n = dist["rays"].norm(dim=1)
+    assert (n - 1).abs().max().item() < 1e-5
+    assert (dist["points"] - dist["rays"] * dist["radius"]).abs().max().item() < 1e-4 * dist["radius"].max().item()
+    with pytest.raises(TypeError):
+        m.infer(rgb, camera=object())

@@ -108,7 +108,7 @@ class Geometry(C.Structure):
 class InferArgs(C.Structure):
     _fields_ = [
         ("rgb", vp), ("rgb_is_u8", i32), ("normalize", i32), ("B", i32), ("H", i32), ("W", i32),
-        ("resolution_level", i32), ("camera_k", vp), ("ray_scales", vp), ("workspace", vp),
+        ("resolution_level", i32), ("camera_k", vp), ("camera_rays", vp), ("ray_scales", vp), ("workspace", vp),
         ("workspace_bytes", C.c_size_t),
         ("confidence", vp), ("intrinsics", vp), ("radius", vp), ("depth", vp), ("points", vp), ("rays", vp),
         ("depth_features", vp),

@@ -363,7 +363,7 @@ static int run(udb_engine* e, const udb_infer_args_t& a, const udb_geometry_t& g
 
   // ---- a11/a12: rays (predicted K, or the caller's pinhole K) -> Fourier embedding on the patch grid
   const float* ray_intr = intr4;
-  if (a.camera_k) {
+  if (a.camera_k && !a.camera_rays) {
     float* gt4 = ar.f(static_cast<size_t>(B) * 4);
     if (!c.dry && !c.rc) c.done(udb_camera_adjust_k(a.camera_k, B, static_cast<float>(g.factor), g.pad_l, g.pad_t, gt4, st));
     ray_intr = gt4;
@@ -372,7 +372,7 @@ static int run(udb_engine* e, const udb_infer_args_t& a, const udb_geometry_t& g
   if (!c.dry && !c.rc) {
     udb_ray_embed_t p;
     memset(&p, 0, sizeof(p));
-    p.intr4 = ray_intr; p.scales = a.ray_scales ? a.ray_scales : tb.scales;
+    p.intr4 = ray_intr; p.rays_in = a.camera_rays; p.scales = a.ray_scales ? a.ray_scales : tb.scales;
     p.B = B; p.net_h = nh; p.net_w = nw; p.gh = gh; p.gw = gw; p.bands = hid / 2; p.out = remb; p.out_f32 = 1;
     c.done(udb_ray_embed(&p, st));
   }
@@ -480,7 +480,7 @@ static int run(udb_engine* e, const udb_infer_args_t& a, const udb_geometry_t& g
   if (!c.dry && !c.rc) {
     udb_postprocess_t p;
     memset(&p, 0, sizeof(p));
-    p.radius = planes[0]; p.confidence = planes[1]; p.intr4 = ray_intr;
+    p.radius = planes[0]; p.confidence = planes[1]; p.intr4 = ray_intr; p.rays_in = a.camera_rays;
     p.B = B; p.net_h = nh; p.net_w = nw; p.padded_h = g.padded_h; p.padded_w = g.padded_w; p.pad_l = g.pad_l; p.pad_t = g.pad_t;
     p.H = a.H; p.W = a.W;
     p.out_confidence = a.confidence; p.out_radius = a.radius; p.out_depth = a.depth; p.out_points = a.points; p.out_rays = a.rays;

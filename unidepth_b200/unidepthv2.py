@@ -350,7 +350,7 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
         self._engine_tensors = tensors          # the engine borrows these pointers
         return handle
 
-    def _forward_engine(self, rgb: torch.Tensor, geom: dict, normalize: bool, level, camera_k=None):
+    def _forward_engine(self, rgb: torch.Tensor, geom: dict, normalize: bool, level, camera_k=None, rays_in=None):
         """The whole path as ONE C call (udb_infer_v2): torch only allocates outputs / workspace."""
         eng = self._get_engine()
         lib = cabi.lib()
@@ -377,6 +377,7 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
         a.rgb, a.rgb_is_u8, a.normalize = rgb.data_ptr(), int(rgb.dtype == torch.uint8), int(normalize)
         a.B, a.H, a.W, a.resolution_level = B, H, W, lvl
         a.camera_k = camera_k.data_ptr() if camera_k is not None else None
+        a.camera_rays = rays_in.data_ptr() if rays_in is not None else None
         a.ray_scales = geom["scales"].data_ptr()
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
         for k, v in out.items():
@@ -408,7 +409,8 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
         return self._posembed_cache[key]
 
     # ------------------------------------------------------------------ the forward (kernel launches only)
-    def _forward(self, rgb: torch.Tensor, geom: dict, normalize: bool, gt_intr4=None, taps: Optional[dict] = None):
+    def _forward(self, rgb: torch.Tensor, geom: dict, normalize: bool, gt_intr4=None, taps: Optional[dict] = None,
+                 rays_in=None):
         P = self._weights()
         s = self.spec
         dev = rgb.device
@@ -489,7 +491,7 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
         # GT-camera branch (unidepthv2.py:299-303,361-362; decoder.py:400): rays come from the given
         # pinhole K instead of the predicted one; the returned intrinsics stay the predicted ones.
         ray_intr = intr4 if gt_intr4 is None else gt_intr4
-        remb = ops.ray_embed(ray_intr, scales, B, (nh, nw), (gh, gw), out_dtype=f32)
+        remb = ops.ray_embed(ray_intr, scales, B, (nh, nw), (gh, gw), out_dtype=f32, rays_in=rays_in)
         if taps is not None:
             taps["ray_embedding"] = remb.clone().view(B, N, hid)
             taps["intrinsics4"] = intr4.clone()
@@ -563,7 +565,8 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
 
         # a18: output assembly
         pl, pr_, pt, pb = geom["paddings"]
-        out = ops.postprocess(radius, confidence, ray_intr, B, (nh, nw), geom["padded_hw"], pl, pt, geom["out_hw"])
+        out = ops.postprocess(radius, confidence, ray_intr, B, (nh, nw), geom["padded_hw"], pl, pt, geom["out_hw"],
+                              rays_in=rays_in)
         out["intrinsics"] = k_out
         out["depth_features"] = init_latents.view(B, gh, gw, hid).permute(0, 3, 1, 2)
         return out
@@ -575,8 +578,6 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
         utils/camera.py:115-120) and scales by the resize factor (`resize`, :78-81); rays are then
         K^-1 [u,v,1] at pixel centres (Pinhole.unproject :252-263).  Here the adjusted
         (fx,fy,cx,cy) is handed to the ray kernels, which evaluate the same expression."""
-        if not isinstance(camera, torch.Tensor):
-            raise NotImplementedError("camera objects are not supported yet: pass a (...,3,3) pinhole K tensor")
         assert camera.shape[-1] == 3 and camera.shape[-2] == 3, \
             "camera tensor should be of shape (..., 3, 3): assume pinhole"
         K = camera.to(dev, f32).reshape(-1, 3, 3)
@@ -589,8 +590,35 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
                             (K[:, 1, 2] + pt) * factor], dim=1).contiguous()
 
     # ------------------------------------------------------------------ infer
+    @staticmethod
+    def _camera_rays(camera, B, paddings, factor, net_hw, dev):
+        """`camera=` given as a camera OBJECT (the reference's `Camera` / `BatchCamera` family,
+        utils/camera.py, or anything with the same three methods): the reference crops it by the
+        paddings, resizes it by the factor and asks it for unit rays at network-input resolution
+        (unidepthv2.py:299-303, :361-362); those rays replace the predicted ones (decoder.py:400).
+        The object's own host/torch code generates the rays; they enter the kernels as a
+        [B, net_h*net_w, 3] f32 tensor.  The caller's object is not mutated (the reference does)."""
+        import copy
+        for name in ("crop", "resize", "get_rays"):
+            if not callable(getattr(camera, name, None)):
+                raise TypeError(f"camera must be a (...,3,3) tensor or an object with crop/resize/get_rays (missing {name})")
+        cam = copy.deepcopy(camera)
+        if callable(getattr(cam, "to", None)):
+            cam = cam.to(dev)
+        pl, pr_, pt, pb = paddings
+        cam = cam.crop(left=-pl, top=-pt, right=-pr_, bottom=-pb)
+        cam = cam.resize(factor)
+        nh, nw = net_hw
+        rays = cam.get_rays(shapes=(B, nh, nw))
+        if rays.ndim == 3:
+            rays = rays.unsqueeze(0)
+        assert rays.shape[-3:] == (3, nh, nw), f"camera.get_rays returned {tuple(rays.shape)}"
+        if rays.shape[0] == 1 and B > 1:
+            rays = rays.expand(B, 3, nh, nw)
+        return rays.to(dev, f32).permute(0, 2, 3, 1).reshape(B, nh * nw, 3).contiguous()
+
     @torch.no_grad()
-    def infer(self, rgb: torch.Tensor, camera: Optional[torch.Tensor] = None, normalize: bool = True):
+    def infer(self, rgb: torch.Tensor, camera=None, normalize: bool = True):
         """Same contract as the reference `UniDepthV2.infer` (unidepthv2.py:239-339)."""
         if self.interpolation_mode != "bilinear":
             raise NotImplementedError("interpolation_mode other than 'bilinear' is not implemented")
@@ -620,8 +648,10 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
             self._posembed_cache[skey] = (2.0 ** torch.linspace(0.0, math.log2(max(gh, gw) // 2), steps=bands)).to(dev)
         geom["scales"] = self._posembed_cache[skey]
 
-        gt_intr4, camera_k = None, None
-        if camera is not None:
+        gt_intr4, camera_k, rays_in = None, None, None
+        if camera is not None and not isinstance(camera, torch.Tensor):
+            rays_in = self._camera_rays(camera, B, paddings, factor, (nh, nw), dev)
+        elif camera is not None:
             gt_intr4 = self._gt_intrinsics(camera, B, paddings, factor, dev)     # validates the argument
             camera_k = camera.to(dev, f32).reshape(-1, 3, 3)
             if camera_k.shape[0] == 1 and B > 1:
@@ -632,9 +662,9 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
 
         def run(inp):
             if self.use_engine:
-                return self._forward_engine(inp, geom, normalize, level, camera_k=camera_k)
+                return self._forward_engine(inp, geom, normalize, level, camera_k=camera_k, rays_in=rays_in)
             self._pos_embed(gh, gw)
-            return self._forward(inp, geom, normalize, gt_intr4=gt_intr4)
+            return self._forward(inp, geom, normalize, gt_intr4=gt_intr4, rays_in=rays_in)
 
         if not self.use_cuda_graph or camera is not None:
             return run(rgb)

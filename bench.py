@@ -165,24 +165,46 @@ def main():
     import warnings
     warnings.simplefilter("ignore")
 
+    # N > 1: the all-gather of step i is left in flight while step i+1 computes (depth-1 pipeline, what a
+    # serving loop does); every gather is waited for inside the timed region (flush()).
+    pending = {"dev": None, "e2e": None}
+
     def step_device():
         out = model.infer(rgb_dev)
         if world > 1:
-            out = gather_outputs(out, world)
+            nxt = gather_outputs(out, world, async_op=True)
+            if pending["dev"] is not None:
+                pending["dev"].wait()
+            pending["dev"] = nxt
         return out
 
     depth_host = torch.empty((B, 1, 480, 640), dtype=torch.float32).pin_memory()
     k_host = torch.empty((B, 3, 3), dtype=torch.float32).pin_memory()
 
+    def _d2h(out):
+        lo = rank * B if world > 1 else 0
+        depth_host.copy_(out["depth"][lo:lo + B], non_blocking=True)
+        k_host.copy_(out["intrinsics"][lo:lo + B], non_blocking=True)
+
     def step_e2e():
         x = rgb_host.to(dev, non_blocking=True)
         out = model.infer(x)
         if world > 1:
-            out = gather_outputs(out, world)
-        lo = rank * B if world > 1 else 0
-        depth_host.copy_(out["depth"][lo:lo + B], non_blocking=True)
-        k_host.copy_(out["intrinsics"][lo:lo + B], non_blocking=True)
+            nxt = gather_outputs(out, world, async_op=True)
+            if pending["e2e"] is not None:
+                _d2h(pending["e2e"].wait())
+            pending["e2e"] = nxt
+        else:
+            _d2h(out)
         return out
+
+    def flush():
+        if pending["dev"] is not None:
+            pending["dev"].wait()
+            pending["dev"] = None
+        if pending["e2e"] is not None:
+            _d2h(pending["e2e"].wait())
+            pending["e2e"] = None
 
     def barrier():
         if world > 1:
@@ -195,6 +217,7 @@ def main():
         s.record()
         for _ in range(steps):
             fn()
+        flush()
         e.record()
         barrier()
         ms = torch.tensor([s.elapsed_time(e)], device=dev)
@@ -289,7 +312,10 @@ def main():
             "dtype": "f16 operands, f32 accumulate/residual", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": B * world, "parallelism": f"dp{world}",
                        "l2": "per-step working set (weights 0.7 GB + activations > 4 GB) exceeds the 126 MB L2",
-                       "cuda_graph": True},
+                       "cuda_graph": True, "engine": "udb_infer_v2 (one C call per infer)",
+                       **({"collective": "one packed NCCL all-gather per step, left in flight under the next step's "
+                                         "compute (depth-1 pipeline); all gathers complete inside the timed region"}
+                          if world > 1 else {})},
             "e2e": {"value": total_images / (ms_e2e / 1000.0), "unit": "images/s",
                     "h2d_bytes_per_step": rgb_host.numel(), "d2h_bytes_per_step": depth_host.numel() * 4 + k_host.numel() * 4},
             "gpu_launches": int(launches_per_step * args.steps),

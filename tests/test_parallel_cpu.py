@@ -42,11 +42,14 @@ def _worker(rank, world, port, q):
     from unidepth_b200.parallel import gather_outputs
     out = _fake_out(2, rank)
     full = gather_outputs(out, world)
+    pend = gather_outputs(out, world, async_op=True)      # pipelined form: handle now, dict at wait()
+    full2 = pend.wait()
     ok = True
     for r in range(world):
         exp = _fake_out(2, r)
         for k in exp:
             ok &= torch.equal(full[k][2 * r:2 * r + 2], exp[k])
+            ok &= torch.equal(full2[k][2 * r:2 * r + 2], exp[k])
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 

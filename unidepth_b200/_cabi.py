@@ -160,6 +160,8 @@ def lib():
                 "unidepth_b200 has no CPU / PyTorch fallback.")
         l = C.CDLL(LIB_PATH)
         for name, (res, args) in EXPORTS.items():
+            if "UDB_LIB" in os.environ and not hasattr(l, name):
+                continue      # experiment builds of older sources may lack newer entry points
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args

@@ -38,23 +38,42 @@ def unpack_outputs(buf: torch.Tensor, like: Dict[str, torch.Tensor]) -> Dict[str
     return res
 
 
-def gather_outputs(out: Dict[str, torch.Tensor], world: int, group=None) -> Dict[str, torch.Tensor]:
-    """Single all-gather of the packed per-rank buffer (equal per-rank batch sizes)."""
+class PendingOutputs:
+    """Handle of an in-flight all-gather: `.wait()` makes the current stream (NCCL) / the host (gloo) wait
+    for it and returns the global output dict.  Keeps the send / receive buffers alive until then."""
+
+    def __init__(self, work, full, local, shapes):
+        self._work, self._full, self._local, self._shapes = work, full, local, shapes
+
+    def wait(self) -> Dict[str, torch.Tensor]:
+        if self._work is not None:
+            self._work.wait()
+            self._work = None
+        return unpack_outputs(self._full, self._shapes)
+
+
+def gather_outputs(out: Dict[str, torch.Tensor], world: int, group=None, async_op: bool = False):
+    """Single all-gather of the packed per-rank buffer (equal per-rank batch sizes).
+    async_op=True returns a PendingOutputs: the collective then overlaps whatever the caller enqueues
+    next (the following micro-batch's infer), which is how a serving loop hides it."""
     if world == 1:
-        return out
+        return PendingOutputs(None, pack_outputs(out), None, out) if async_op else out
     # depth_features is returned as a permuted view; make the packing layout-independent
     local = pack_outputs(out)
     full = torch.empty((world * local.shape[0], local.shape[1]), device=local.device, dtype=local.dtype)
-    dist.all_gather_into_tensor(full, local, group=group)
-    return unpack_outputs(full, out)
+    work = dist.all_gather_into_tensor(full, local, group=group, async_op=True)
+    shapes = {k: torch.empty((0,) + tuple(out[k].shape[1:]), device="meta") for k in _KEYS}
+    pending = PendingOutputs(work, full, local, shapes)
+    return pending if async_op else pending.wait()
 
 
-def infer_sharded(model, rgb: torch.Tensor, **kw) -> Dict[str, torch.Tensor]:
+def infer_sharded(model, rgb: torch.Tensor, async_op: bool = False, **kw):
     """`rgb` is the GLOBAL batch [N,3,H,W] (same on every rank); returns the global outputs on
-    every rank.  N must be divisible by the world size."""
+    every rank (or, with async_op=True, a PendingOutputs whose gather is still in flight).
+    N must be divisible by the world size."""
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
     n = rgb.shape[0]
     assert n % world == 0, "global batch must be divisible by the number of ranks"
     lo, hi = shard_bounds(n, rank, world)
-    return gather_outputs(model.infer(rgb[lo:hi], **kw), world)
+    return gather_outputs(model.infer(rgb[lo:hi], **kw), world, async_op=async_op)

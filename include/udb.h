@@ -149,6 +149,8 @@ typedef struct udb_layernorm_t {
   int64_t ld_in, ld_out;
   int32_t rows_per_group, group_stride, row_offset;
   float eps;
+  int32_t dim_valid; /* 0 = dim.  f16->f16 rows of 64/128/256 only: statistics over the first dim_valid
+                        columns (zero-padded channel rows, e.g. ViT-B's 96-channel map stored as 128) */
 } udb_layernorm_t;
 
 int udb_layernorm(const udb_layernorm_t* p, void* stream);

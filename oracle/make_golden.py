@@ -24,6 +24,7 @@ CASES = [
     # name, config, seed, (B,H,W), resolution_level
     ("vits_120x160", "config_v2_vits14.json", 0, (1, 120, 160), None),
     ("vits_pad_96x288_rl3", "config_v2_vits14.json", 1, (2, 96, 288), 3),
+    ("vitb_112x160", "config_v2_vitb14.json", 2, (1, 112, 160), None),
 ]
 
 

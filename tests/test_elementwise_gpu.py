@@ -153,3 +153,22 @@ def test_resamplers():
     got = ops.resize_ac_pad(xn, 61, 80, 1)
     refp = F.pad(ref, (1, 1, 1, 1), mode="reflect").permute(0, 2, 3, 1)
     assert _err(got, refp, "resize ac + reflect pad") < 4e-3
+
+
+def test_layernorm_zero_padded_channels():
+    """ViT-B's 96-channel map is stored as 128 channels (32 zeros): statistics over the first 96 only,
+    padded outputs stay zero (weight 0 there)."""
+    from unidepth_b200 import ops
+    dev = _dev()
+    torch.manual_seed(5)
+    for dim, valid in ((128, 96), (256, 192), (64, 48)):
+        x = torch.zeros(50003, dim, device=dev)
+        x[:, :valid] = torch.randn(50003, valid, device=dev) * 2 + 0.7
+        x = x.half()
+        w = torch.zeros(dim, device=dev)
+        w[:valid] = 1.0
+        b = torch.zeros(dim, device=dev)
+        got = ops.layernorm(x, w, b, 1e-5, out_dtype=torch.float16, dim_valid=valid)
+        ref = F.layer_norm(x[:, :valid].float(), (valid,), None, None, 1e-5)
+        assert _err(got[:, :valid], ref, f"ln {valid} of {dim}") < 8e-3
+        assert float(got[:, valid:].abs().max()) == 0.0

@@ -162,10 +162,10 @@ def test_full_vitl_480x640():
     _check(out, ref)
 
 
-@pytest.mark.parametrize("name", ["vits_120x160", "vits_pad_96x288_rl3"])
-def test_vits_against_reference_golden(name):
+@pytest.mark.parametrize("name", ["vits_120x160", "vits_pad_96x288_rl3", "vitb_112x160"])
+def test_against_reference_golden(name):
     """CUDA path vs outputs of the UNMODIFIED reference (tests/golden/*.npz, made by
-    oracle/make_golden.py from /root/reference): UniDepthV2 ViT-S/14, the reference's own config."""
+    oracle/make_golden.py from /root/reference): UniDepthV2 ViT-S/14 and ViT-B/14, the reference's own configs."""
     import numpy as np
     from fixture import make_state_dict
     z = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
@@ -323,3 +323,25 @@ def test_camera_object_branch(shallow):
     assert (dist["points"] - dist["rays"] * dist["radius"]).abs().max().item() < 1e-4 * dist["radius"].max().item()
     with pytest.raises(TypeError):
         m.infer(rgb, camera=object())
+
+
+def test_vitb_shallow_vs_oracle():
+    """ViT-B/14 config (768-wide encoder, 12x64 heads; decoder hidden 384 with 8x48 heads and a 96-channel
+    high-resolution map): narrower-than-64 quantities run zero-padded (heads 48->64, 96->128 channels,
+    48->64 lr channels) with LayerNorm statistics over the real channels."""
+    import unidepth_oracle as O
+    from fixture import make_state_dict
+    cfg = json.load(open(os.path.join(ROOT, "tests", "golden", "config_v2_vitb14.json")))
+    cfg["model"]["pixel_encoder"]["arch_override"] = {"depth": 4}
+    cfg["model"]["pixel_encoder"]["output_idx"] = [1, 2, 3, 4]
+    sd = make_state_dict(cfg, 2)
+    rgb = _rgb((2, 240, 320), 8)
+    torch.set_num_threads(min(32, os.cpu_count()))
+    ref = O.infer_v2(sd, copy.deepcopy(cfg), rgb)
+    m = _model(cfg, sd)
+    out = m.infer(rgb)
+    _check(out, ref)
+    m.use_engine = False
+    out2 = m.infer(rgb)
+    for k in out:
+        assert torch.equal(out[k], out2[k]), k

@@ -11,7 +11,7 @@ import torch
 import unidepth_oracle as O
 from fixture import make_state_dict
 
-CASES = ["vits_120x160", "vits_pad_96x288_rl3"]
+CASES = ["vits_120x160", "vits_pad_96x288_rl3", "vitb_112x160"]
 
 
 def _rgb(shape, seed):

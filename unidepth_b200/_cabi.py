@@ -53,7 +53,7 @@ class LayerNorm(C.Structure):
     _fields_ = [
         ("inp", vp), ("in_f32", i32), ("out", vp), ("out_f32", i32), ("weight", vp), ("bias", vp),
         ("rows", i32), ("dim", i32), ("ld_in", i64), ("ld_out", i64),
-        ("rows_per_group", i32), ("group_stride", i32), ("row_offset", i32), ("eps", f32),
+        ("rows_per_group", i32), ("group_stride", i32), ("row_offset", i32), ("eps", f32), ("dim_valid", i32),
     ]
 
 

@@ -101,16 +101,20 @@ __global__ void __launch_bounds__(256) layernorm_f16_small_kernel(const udb_laye
 #pragma unroll
     for (int q = 0; q < 8; ++q) x[q] = 0.f;
   }
-  float s = ((x[0] + x[1]) + (x[2] + x[3])) + ((x[4] + x[5]) + (x[6] + x[7]));
+  // zero-padded channel rows: statistics over the first n_valid columns only (multiple of 8)
+  const int n_valid = p.dim_valid > 0 ? p.dim_valid : p.dim;
+  const bool in_range = sub * 8 < n_valid;
+  float s = in_range ? ((x[0] + x[1]) + (x[2] + x[3])) + ((x[4] + x[5]) + (x[6] + x[7])) : 0.f;
 #pragma unroll
   for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float mean = s / (float)p.dim;
+  const float mean = s / (float)n_valid;
   float v = 0.f;
 #pragma unroll
   for (int q = 0; q < 8; ++q) v += (x[q] - mean) * (x[q] - mean);
+  v = in_range ? v : 0.f;
 #pragma unroll
   for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  const float rstd = rsqrtf(v / (float)p.dim + p.eps);
+  const float rstd = rsqrtf(v / (float)n_valid + p.eps);
   if (valid) {
     const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.weight + sub * 8)), w1 = __ldg(reinterpret_cast<const float4*>(p.weight + sub * 8 + 4));
     const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + sub * 8)), b1 = __ldg(reinterpret_cast<const float4*>(p.bias + sub * 8 + 4));
@@ -520,6 +524,10 @@ using namespace udb;
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
 
 extern "C" int udb_layernorm(const udb_layernorm_t* p, void* stream) {
+  if (p->dim_valid < 0 || p->dim_valid > p->dim || p->dim_valid % 8) {
+    set_error("udb_layernorm: dim_valid %d must be a multiple of 8 in [0, dim]", p->dim_valid);
+    return 1;
+  }
   if (!p->in_f32 && !p->out_f32 && p->rows_per_group <= 0 && (p->dim == 64 || p->dim == 128 || p->dim == 256)) {
     const int lpr = p->dim / 8, rpb = 8 * (32 / lpr);
     const int g = (p->rows + rpb - 1) / rpb;
@@ -528,6 +536,10 @@ extern "C" int udb_layernorm(const udb_layernorm_t* p, void* stream) {
     else if (lpr == 16) layernorm_f16_small_kernel<16><<<g, 256, 0, ST(stream)>>>(*p);
     else layernorm_f16_small_kernel<32><<<g, 256, 0, ST(stream)>>>(*p);
     return check_launch("layernorm_f16_small_kernel");
+  }
+  if (p->dim_valid > 0 && p->dim_valid != p->dim) {
+    set_error("udb_layernorm: dim_valid is only supported for f16->f16 rows of 64/128/256 columns");
+    return 1;
   }
   if (p->dim % 128 != 0 || p->dim > 1024) { set_error("udb_layernorm: dim %d unsupported (multiple of 128, <= 1024)", p->dim); return 1; }
   const int grid = (p->rows + 7) / 8;

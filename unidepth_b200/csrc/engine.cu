@@ -219,13 +219,14 @@ struct Ctx {
     done(udb_attention_f16(&a, st));
   }
   void layernorm(const void* in, int in_f32, void* out, int out_f32, const float* w, const float* b, int rows, int dim,
-                 float eps, int rows_per_group = 0, int group_stride = 0, int row_offset = 0) {
+                 float eps, int rows_per_group = 0, int group_stride = 0, int row_offset = 0, int dim_valid = 0) {
     if (dry || rc) return;
     udb_layernorm_t p;
     memset(&p, 0, sizeof(p));
     p.in = in; p.in_f32 = in_f32; p.out = out; p.out_f32 = out_f32; p.weight = w; p.bias = b;
     p.rows = rows; p.dim = dim; p.ld_in = dim; p.ld_out = dim;
     p.rows_per_group = rows_per_group; p.group_stride = group_stride; p.row_offset = row_offset; p.eps = eps;
+    p.dim_valid = dim_valid;
     done(udb_layernorm(&p, st));
   }
   void small_linear(const float* x, int M, int K, const float* w, int N, const float* bias, int act, const float* gamma,
@@ -454,7 +455,12 @@ static int run(udb_engine* e, const udb_infer_args_t& a, const udb_geometry_t& g
   // ---- a16/a17: depth + confidence heads (shared normalisation, merged LN->Linear GEMM written
   //      straight into the reflect-padded buffer the 3x3 "lr" convs read)
   __half* xhat = ar.h(hpx * c_hr);
-  c.layernorm(prev, 0, xhat, 0, c.F("ln_ones"), c.F("ln_zeros"), static_cast<int>(hpx), c_hr, 1e-5f);
+  // real width of the last map (decoder.py:470-524: max(2*hidden / 2^n_stages, out_dim)); ViT-B stores its 96
+  // channels zero-padded to 128
+  const int nxt_last = (2 * hid) >> cf.n_stages;
+  const int c_valid = nxt_last > cf.out_dim ? nxt_last : cf.out_dim;
+  c.layernorm(prev, 0, xhat, 0, c.F("ln_ones"), c.F("ln_zeros"), static_cast<int>(hpx), c_hr, 1e-5f, 0, 0, 0,
+              c_valid != c_hr ? c_valid : 0);
   const int n_mlp = static_cast<int>(c.W("head_mlp_w")->shape[0]);   // 2 * out_dim: [depth | confidence]
   __half* mp = ar.h(static_cast<size_t>(B) * (hh + 2) * (hw + 2) * n_mlp);
   c.conv_transpose(xhat, static_cast<int>(hpx), c_hr, c.H("head_mlp_w"), 1, n_mlp, hh, hw, c.F("head_mlp_b"), nullptr, 0, mp,
@@ -543,7 +549,7 @@ int udb_create(const udb_config_t* cfg, udb_engine** out) {
     return 1;
   }
   const int hd = cfg->dec_heads > 0 ? cfg->hidden / cfg->dec_heads : 0;
-  if (hd <= 0 || hd > 64 || 64 % hd) { set_error("udb_create: decoder head dim %d not supported", hd); return 1; }
+  if (hd <= 0 || hd > 64) { set_error("udb_create: decoder head dim %d not supported", hd); return 1; }
   if (cfg->n_stages < 1 || cfg->n_stages > 4) { set_error("udb_create: n_stages %d out of range", cfg->n_stages); return 1; }
   udb_engine* e = new udb_engine();
   e->cfg = *cfg;

@@ -187,7 +187,7 @@ def attention(q, k, v, out, *, B, heads, seq_q, seq_k, head_dim, q_col0=0, k_col
 
 
 def layernorm(x, weight, bias, eps, *, out=None, out_dtype=f16, rows=None, rows_per_group=0,
-              group_stride=0, row_offset=0):
+              group_stride=0, row_offset=0, dim_valid=0):
     dim = x.shape[-1]
     x2 = x.reshape(-1, dim)
     n_rows = rows if rows is not None else x2.shape[0]
@@ -201,7 +201,8 @@ def layernorm(x, weight, bias, eps, *, out=None, out_dtype=f16, rows=None, rows_
     p.ld_in, p.ld_out = x2.stride(0), out.stride(0)
     p.rows_per_group, p.group_stride, p.row_offset = rows_per_group, group_stride, row_offset
     p.eps = eps
-    cabi.check(cabi.lib().udb_layernorm(C.byref(p), _stream()), "udb_layernorm")
+    p.dim_valid = dim_valid
+    cabi.check(_launch("layernorm_kernel", 0.0, lambda: cabi.lib().udb_layernorm(C.byref(p), _stream())), "udb_layernorm")
     return out
 
 
@@ -214,7 +215,7 @@ def preprocess_patchify(rgb, paddings, net_hw, patches, normalize=True):
     p.pad_l, p.pad_r, p.pad_t, p.pad_b = paddings
     p.net_h, p.net_w = net_hw
     p.patches, p.ldp = _ptr(patches), patches.stride(0)
-    cabi.check(cabi.lib().udb_preprocess_patchify(C.byref(p), _stream()), "udb_preprocess_patchify")
+    cabi.check(_launch("preprocess_patchify_kernel", 0.0, lambda: cabi.lib().udb_preprocess_patchify(C.byref(p), _stream())), "udb_preprocess_patchify")
     return patches
 
 
@@ -240,7 +241,7 @@ def small_linear(x, w, bias=None, act=ACT_NONE, gamma=None, resid=None, out=None
     p.x, p.w, p.bias, p.gamma, p.resid, p.y = _ptr(x), _ptr(w), _ptr(bias), _ptr(gamma), _ptr(resid), _ptr(out)
     p.M, p.N, p.K, p.act = M, N, K, act
     p.ldx, p.ldy, p.ldr = x.stride(0), out.stride(0), (resid.stride(0) if resid is not None else 0)
-    cabi.check(cabi.lib().udb_small_linear_f32(C.byref(p), _stream()), "udb_small_linear_f32")
+    cabi.check(_launch("small_linear_kernel", 0.0, lambda: cabi.lib().udb_small_linear_f32(C.byref(p), _stream())), "udb_small_linear_f32")
     return out
 
 
@@ -268,21 +269,23 @@ def ray_embed(intr4, scales, B, net_hw, grid_hw, out_dtype=f32, rays_in=None):
     p.intr4, p.rays_in, p.scales = _ptr(intr4), _ptr(rays_in), _ptr(scales)
     p.B, p.net_h, p.net_w, p.gh, p.gw, p.bands = B, net_hw[0], net_hw[1], grid_hw[0], grid_hw[1], bands
     p.out, p.out_f32 = _ptr(out), _is32(out)
-    cabi.check(cabi.lib().udb_ray_embed(C.byref(p), _stream()), "udb_ray_embed")
+    cabi.check(_launch("ray_embed_kernel", 0.0, lambda: cabi.lib().udb_ray_embed(C.byref(p), _stream())), "udb_ray_embed")
     return out
 
 
 def upsample2x(x):
     B, H, W, Cc = x.shape
     out = torch.empty((B, 2 * H, 2 * W, Cc), device=x.device, dtype=f16)
-    cabi.check(cabi.lib().udb_upsample2x_nhwc_f16(_ptr(x), _ptr(out), B, H, W, Cc, _stream()), "udb_upsample2x_nhwc_f16")
+    cabi.check(_launch("upsample2x_kernel", 0.0, lambda: cabi.lib().udb_upsample2x_nhwc_f16(_ptr(x), _ptr(out), B, H, W, Cc, _stream())),
+               "udb_upsample2x_nhwc_f16")
     return out
 
 
 def resize_ac_pad(x, oh, ow, pad):
     B, H, W, Cc = x.shape
     out = torch.empty((B, oh + 2 * pad, ow + 2 * pad, Cc), device=x.device, dtype=f16)
-    cabi.check(cabi.lib().udb_resize_ac_pad_nhwc_f16(_ptr(x), _ptr(out), B, H, W, Cc, oh, ow, pad, _stream()),
+    cabi.check(_launch("resize_ac_pad_kernel", 0.0,
+                       lambda: cabi.lib().udb_resize_ac_pad_nhwc_f16(_ptr(x), _ptr(out), B, H, W, Cc, oh, ow, pad, _stream())),
                "udb_resize_ac_pad_nhwc_f16")
     return out
 
@@ -318,5 +321,5 @@ def postprocess(radius, confidence, intr4, B, net_hw, padded_hw, pad_l, pad_t, o
     p.padded_h, p.padded_w, p.pad_l, p.pad_t, p.H, p.W = padded_hw[0], padded_hw[1], pad_l, pad_t, H, W
     p.out_confidence, p.out_radius, p.out_depth = _ptr(outs["confidence"]), _ptr(outs["radius"]), _ptr(outs["depth"])
     p.out_points, p.out_rays = _ptr(outs["points"]), _ptr(outs["rays"])
-    cabi.check(cabi.lib().udb_postprocess(C.byref(p), _stream()), "udb_postprocess")
+    cabi.check(_launch("postprocess_kernel", 0.0, lambda: cabi.lib().udb_postprocess(C.byref(p), _stream())), "udb_postprocess")
     return outs

@@ -135,11 +135,18 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
         # v columns produce zeros that meet zero columns of the out projection; the softmax scale stays
         # 1/sqrt(true head dim).
         hd = hid // s.dec_heads
-        if d // s.enc_heads != 64 or hd > 64 or 64 % hd:
+        if d // s.enc_heads != 64 or hd > 64:
             raise NotImplementedError(f"head dims (encoder {d // s.enc_heads}, decoder {hd}) not supported")
-        for cch in list(s.cur) + list(s.outd):
+        for cch in list(s.cur) + list(s.outd[:-1]):
             if cch % 64:
-                raise NotImplementedError(f"decoder channel count {cch} is not a multiple of 64 (ViT-B decoder: later round)")
+                raise NotImplementedError(f"decoder channel count {cch} is not a multiple of 64")
+        # The last stage's output map (ViT-B: 96 channels) and the "lr" convs' outputs (48 / 32) are
+        # zero-padded to multiples of 64 channels: zero weight rows produce zero channels, which meet
+        # zero weight columns downstream; LayerNorm statistics use the real count (dim_valid).
+        pad64 = lambda c: (c + 63) // 64 * 64
+        c_hr_real, c_hr = s.outd[-1], pad64(s.outd[-1])
+        if c_hr_real % 8 or c_hr > 256:
+            raise NotImplementedError(f"high-resolution feature width {c_hr_real} not supported")
         P["dec_hd"], P["dec_hp"] = hd, s.dec_heads * 64
         pe = "pixel_encoder."
         wpe = torch.zeros((d, 640), device=dev, dtype=f16)
@@ -228,7 +235,12 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
                                        w2=conv_pack(sd[u + "conv2.weight"]), b2=c32(sd[u + "conv2.bias"]),
                                        gamma=c32(sd[u + "gamma"].reshape(-1))))
             uw = sd[f"{dl}ups.{i}.up.0.weight"]
-            st["up_w"], st["up_b"] = h16(uw.reshape(uw.shape[0], uw.shape[1])), c32(sd[f"{dl}ups.{i}.up.0.bias"])
+            uw, ub = uw.reshape(uw.shape[0], uw.shape[1]).float(), sd[f"{dl}ups.{i}.up.0.bias"].float()
+            if uw.shape[0] % 64:            # last stage of ViT-B: 96 -> 128 output channels (zeros)
+                extra = pad64(uw.shape[0]) - uw.shape[0]
+                uw = torch.cat([uw, torch.zeros((extra, uw.shape[1]), device=dev)], 0)
+                ub = torch.cat([ub, torch.zeros(extra, device=dev)], 0)
+            st["up_w"], st["up_b"] = h16(uw), c32(ub)
             P["ups"].append(st)
         last = len(s.dec_depths) - 1
         # heads: LN(x) = xhat * w + b with the SAME xhat for depth and confidence, so the two
@@ -236,26 +248,30 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
         # b' = W b + bias, depth rows first then confidence rows (decoder.py:190-199, 288, 306-307)
         P["heads"] = []
         wm, bm = [], []
+        zpad = lambda t, dim, n: t if t.shape[dim] == n else torch.cat(
+            [t, torch.zeros(tuple(n - t.shape[dim] if i == dim else sz for i, sz in enumerate(t.shape)), device=dev)], dim)
         for mlp_p, lr, hr, add in ((f"{dl}depth_mlp.{last}", "to_depth_lr", "to_depth_hr", 2.0),
                                    (f"{dl}confidence_mlp", "to_confidence_lr", "to_confidence_hr", 0.0)):
             lnw, lnb = sd[mlp_p + ".0.weight"].float(), sd[mlp_p + ".0.bias"].float()
             w, bb = sd[mlp_p + ".1.weight"].float(), sd[mlp_p + ".1.bias"].float()
-            wm.append(w * lnw.unsqueeze(0))
-            bm.append(w @ lnb + bb)
+            # [c_hr, c_hr] block of the merged GEMM: real rows / columns first, zero padding after
+            wm.append(zpad(zpad(w * lnw.unsqueeze(0), 1, c_hr), 0, c_hr))
+            bm.append(zpad(w @ lnb + bb, 0, c_hr))
             lr_w, lr_b, hr_w = sd[f"{dl}{lr}.weight"].float(), sd[f"{dl}{lr}.bias"].float(), sd[f"{dl}{hr}.0.weight"].float()
-            if lr_w.shape[0] < 64:      # ViT-S: 32 lr channels -> zero-pad to the kernels' 64-channel granularity
-                pad_c = 64 - lr_w.shape[0]
-                lr_w = torch.cat([lr_w, torch.zeros((pad_c,) + tuple(lr_w.shape[1:]), device=dev)], 0)
-                lr_b = torch.cat([lr_b, torch.zeros(pad_c, device=dev)], 0)
-                hr_w = torch.cat([hr_w, torch.zeros((hr_w.shape[0], pad_c, 3, 3), device=dev)], 1)
+            lr_c = pad64(lr_w.shape[0])       # ViT-S: 32 -> 64, ViT-B: 48 -> 64 output channels of the lr conv
+            lr_w = zpad(zpad(lr_w, 1, c_hr), 0, lr_c)
+            lr_b = zpad(lr_b, 0, lr_c)
+            hr_w = zpad(hr_w, 1, lr_c)
             P["heads"].append(dict(
                 lr_w=conv_pack(lr_w), lr_b=c32(lr_b),
                 hr_w=conv_pack(hr_w), hr_b=c32(sd[f"{dl}{hr}.0.bias"]),
                 head_w=c32(sd[f"{dl}{hr}.2.weight"].reshape(32)), head_b=float(sd[f"{dl}{hr}.2.bias"].item()),
                 add=add))
         P["head_mlp_w"], P["head_mlp_b"] = h16(torch.cat(wm, 0)), c32(torch.cat(bm, 0))
-        c_hr = wm[0].shape[1]
-        P["ln_ones"] = torch.ones(c_hr, device=dev, dtype=f32)
+        P["c_hr_valid"] = c_hr_real
+        ones = torch.zeros(c_hr, device=dev, dtype=f32)
+        ones[:c_hr_real] = 1.0               # padded channels: weight 0 -> normalised value 0
+        P["ln_ones"] = ones
         P["ln_zeros"] = torch.zeros(c_hr, device=dev, dtype=f32)
         self._packed = P
         self._packed_key = self._fingerprint()
@@ -547,7 +563,8 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
 
         # a16/a17: depth + confidence heads (shared normalisation, merged LN->Linear GEMM written
         # straight into the reflect-padded buffer the 3x3 "lr" convs read)
-        xhat = ops.layernorm(feat_hr, P["ln_ones"], P["ln_zeros"], 1e-5, out=E(B * hh * hw, C_hr))
+        xhat = ops.layernorm(feat_hr, P["ln_ones"], P["ln_zeros"], 1e-5, out=E(B * hh * hw, C_hr),
+                             dim_valid=P["c_hr_valid"] if P["c_hr_valid"] != C_hr else 0)
         n_mlp = P["head_mlp_w"].shape[0]                      # 2 * out_dim: [depth | confidence]
         mp = E(B, hh + 2, hw + 2, n_mlp)
         ops.conv_transpose_ks(xhat, P["head_mlp_w"], 1, n_mlp, (hh, hw), bias=P["head_mlp_b"], out=mp, pad=1)

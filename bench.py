@@ -165,17 +165,22 @@ def main():
     import warnings
     warnings.simplefilter("ignore")
 
-    # N > 1: the all-gather of step i is left in flight while step i+1 computes (depth-1 pipeline, what a
-    # serving loop does); every gather is waited for inside the timed region (flush()).
+    # N > 1: one all-gather of the packed outputs per step.  Default: synchronous NCCL gather (an NCCL kernel left
+    # in flight under the next step steals SMs from the persistent GEMM CTAs and costs more than it hides:
+    # 18.6 vs 18.0 ms/step at N=2).  UDB_GATHER=p2p: copy-engine pulls over NVLink peer memory, left in flight
+    # under the next step (depth-1 pipeline); every gather is waited for inside the timed region (flush()).
     pending = {"dev": None, "e2e": None}
+    pipelined = os.environ.get("UDB_GATHER", "nccl") == "p2p"
 
     def step_device():
         out = model.infer(rgb_dev)
-        if world > 1:
+        if world > 1 and pipelined:
             nxt = gather_outputs(out, world, async_op=True)
             if pending["dev"] is not None:
                 pending["dev"].wait()
             pending["dev"] = nxt
+        elif world > 1:
+            out = gather_outputs(out, world)
         return out
 
     depth_host = torch.empty((B, 1, 480, 640), dtype=torch.float32).pin_memory()
@@ -189,14 +194,24 @@ def main():
     def step_e2e():
         x = rgb_host.to(dev, non_blocking=True)
         out = model.infer(x)
-        if world > 1:
+        if world > 1 and pipelined:
             nxt = gather_outputs(out, world, async_op=True)
             if pending["e2e"] is not None:
                 _d2h(pending["e2e"].wait())
             pending["e2e"] = nxt
         else:
+            if world > 1:
+                out = gather_outputs(out, world)
             _d2h(out)
         return out
+
+    def gather_kind():
+        from unidepth_b200 import parallel
+        if parallel._p2p_cache:
+            return ("one packed all-gather of the per-rank outputs per step: copy-engine pulls over NVLink peer memory "
+                    "(torch symmetric memory) on a side stream, left in flight under the next step's compute (depth-1 "
+                    "pipeline); every gather completes inside the timed region")
+        return "one packed NCCL all_gather_into_tensor of the per-rank outputs per step, synchronous, inside the timed region"
 
     def flush():
         if pending["dev"] is not None:
@@ -313,9 +328,7 @@ def main():
             "config": {"workload": WORKLOAD, "global_batch": B * world, "parallelism": f"dp{world}",
                        "l2": "per-step working set (weights 0.7 GB + activations > 4 GB) exceeds the 126 MB L2",
                        "cuda_graph": True, "engine": "udb_infer_v2 (one C call per infer)",
-                       **({"collective": "one packed NCCL all-gather per step, left in flight under the next step's "
-                                         "compute (depth-1 pipeline); all gathers complete inside the timed region"}
-                          if world > 1 else {})},
+                       **({"collective": gather_kind()} if world > 1 else {})},
             "e2e": {"value": total_images / (ms_e2e / 1000.0), "unit": "images/s",
                     "h2d_bytes_per_step": rgb_host.numel(), "d2h_bytes_per_step": depth_host.numel() * 4 + k_host.numel() * 4},
             "gpu_launches": int(launches_per_step * args.steps),

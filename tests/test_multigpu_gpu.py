@@ -33,6 +33,12 @@ import warnings; warnings.simplefilter("ignore")
 full = infer_sharded(m, rgb)
 single = m.infer(rgb)
 ok = all(torch.equal(full[k].float(), single[k].float()) for k in single)
+# pipelined form: three gathers in flight one after the other, replays of the older (B=2) graph after the
+# capture of the larger (B=4) one
+pend = [infer_sharded(m, rgb, async_op=True) for _ in range(3)]
+for p in pend:
+    got = p.wait()
+    ok &= all(torch.equal(got[k].float(), single[k].float()) for k in single)
 print(f"rank {rank}: gathered == single-GPU: {ok}", flush=True)
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)

@@ -122,7 +122,7 @@ def p2p_gather_for(out: Dict[str, torch.Tensor], group=None):
     (99.0 % weak-scaling efficiency vs 98.4 % for the synchronous NCCL gather and 96.5 % for an in-flight
     NCCL gather), but in tests/test_multigpu_gpu.py's sequence (gather, then capture of a LARGER CUDA
     graph, then replay of the older graph) the older graph's replays return wrong values with this path
-    enabled and not with NCCL; not understood yet (tools/tmp notes in DESIGN.md section 7), so it is off by default."""
+    enabled and not with NCCL; not understood yet, so it is off by default."""
     import os
     if os.environ.get("UDB_GATHER", "nccl") != "p2p" or _p2p_failed[0] is not None or not out["depth"].is_cuda:
         return None

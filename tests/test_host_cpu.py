@@ -159,3 +159,17 @@ def test_engine_geometry_matches_python_and_reference_examples():
     bad = _cabi.Config()
     bad.embed_dim, bad.enc_heads, bad.hidden, bad.dec_heads, bad.n_stages = 1000, 16, 512, 8, 3
     assert lib.udb_create(C.byref(bad), C.byref(h)) != 0
+
+
+def test_hubconf_entry_point():
+    """hubconf.UniDepth(version, backbone, pretrained) as in the reference (hubconf.py:25-41), offline."""
+    sys.path.insert(0, ROOT)
+    import hubconf
+    from unidepth_b200 import UniDepthV2
+    for bb, d in (("vits14", 384), ("vitb14", 768), ("vitl14", 1024)):
+        m = hubconf.UniDepth("v2", bb, pretrained=False)
+        assert isinstance(m, UniDepthV2) and m.spec.embed_dim == d
+    with pytest.raises(NotImplementedError):
+        hubconf.UniDepth("v1", "cnvnxtl", pretrained=False)
+    with pytest.raises(AssertionError):
+        hubconf.UniDepth("v2", "resnet50", pretrained=False)

@@ -48,6 +48,21 @@ def bench_gemm():
             print(f"   + GELU: {ms:.3f} ms  {2*M*N*K/ms/1e9:.1f} TFLOP/s", flush=True)
 
 
+def bench_ln():
+    import torch.nn.functional as F
+    for (rows, dim) in [(12888, 1024), (12880, 512)]:
+        x = torch.randn(rows, dim, device=dev)
+        w, b = torch.randn(dim, device=dev), torch.randn(dim, device=dev)
+        out = torch.empty(rows, dim, device=dev, dtype=torch.float16)
+        ms = timeit(lambda: ops.layernorm(x, w, b, 1e-6, out=out))
+        gb = rows * dim * 6 / 1e9
+        print(f"layernorm {rows}x{dim} f32->f16: {ms * 1000:.1f} us  {gb / ms * 1000:.0f} GB/s", flush=True)
+        ms = timeit(lambda: F.layer_norm(x, (dim,), w, b, 1e-6))
+        print(f"   torch layer_norm f32->f32: {ms * 1000:.1f} us  {rows * dim * 8 / 1e9 / ms * 1000:.0f} GB/s", flush=True)
+        ms = timeit(lambda: out.copy_(x))
+        print(f"   torch cast copy f32->f16: {ms * 1000:.1f} us  {gb / ms * 1000:.0f} GB/s", flush=True)
+
+
 def bench_attn():
     for (B, H, S) in [(8, 16, 1611), (8, 8, 1610), (4, 16, 3129)]:
         D = H * 64
@@ -99,6 +114,8 @@ if __name__ == "__main__":
         bench_gemm()
     if what in ("attn", "all"):
         bench_attn()
+    if what in ("ln", "all"):
+        bench_ln()
     if what in ("conv", "all"):
         bench_conv()
         bench_halo()

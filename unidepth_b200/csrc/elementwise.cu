@@ -18,61 +18,80 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // ------------------------------------------------------------------------------------ LayerNorm
-// one warp per row; dim % 128 == 0, dim <= 1024; lane owns float4 #(lane + 32*i)
-template <bool IN_F32, bool OUT_F32>
+// One warp per R rows (R = 1 by default; the R = 2 variant -- both rows' loads in flight before the first
+// reduction -- measured slower, see udb_layernorm); dim % 128 == 0, dim <= 1024; lane owns float4
+// #(lane + 32*i).
+template <bool IN_F32, bool OUT_F32, int R>
 __global__ void __launch_bounds__(256) layernorm_kernel(const udb_layernorm_t p) {
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int row0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * R;
   const int lane = threadIdx.x & 31;
   pdl_launch_dependents();
   pdl_wait();
-  if (row >= p.rows) return;
-  long long irow = row;
-  if (p.rows_per_group > 0)
-    irow = (long long)(row / p.rows_per_group) * p.group_stride + (row % p.rows_per_group) + p.row_offset;
+  if (row0 >= p.rows) return;
   const int nvec = p.dim >> 7;  // float4 per lane
-  float4 x[8];
-  float s = 0.f;
+  float4 x[R][8];
+  float s[R];
+  bool live[R];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    if (i < nvec) {
-      const int e = (lane + 32 * i) * 4;
-      if (IN_F32) {
-        x[i] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.in) + irow * p.ld_in + e);
-      } else {
-        const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(p.in) + irow * p.ld_in + e);
-        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
-        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
-        x[i] = make_float4(a.x, a.y, b.x, b.y);
+  for (int r = 0; r < R; ++r) {
+    const int row = row0 + r;
+    live[r] = row < p.rows;
+    long long irow = live[r] ? row : row0;
+    if (p.rows_per_group > 0)
+      irow = (long long)(irow / p.rows_per_group) * p.group_stride + (irow % p.rows_per_group) + p.row_offset;
+    s[r] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i < nvec) {
+        const int e = (lane + 32 * i) * 4;
+        if (IN_F32) {
+          x[r][i] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.in) + irow * p.ld_in + e);
+        } else {
+          const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(p.in) + irow * p.ld_in + e);
+          const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+          const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+          x[r][i] = make_float4(a.x, a.y, b.x, b.y);
+        }
       }
-      s += (x[i].x + x[i].y) + (x[i].z + x[i].w);
     }
   }
-  const float mean = warp_sum(s) / (float)p.dim;
-  float v = 0.f;
+  float mean[R], rstd[R];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    if (i < nvec) {
-      const float a = x[i].x - mean, b = x[i].y - mean, c = x[i].z - mean, d = x[i].w - mean;
-      v += (a * a + b * b) + (c * c + d * d);
+  for (int r = 0; r < R; ++r) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < nvec) s[r] += (x[r][i].x + x[r][i].y) + (x[r][i].z + x[r][i].w);
+    mean[r] = warp_sum(s[r]) / (float)p.dim;
+    float v = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i < nvec) {
+        const float a = x[r][i].x - mean[r], b = x[r][i].y - mean[r], c = x[r][i].z - mean[r], d = x[r][i].w - mean[r];
+        v += (a * a + b * b) + (c * c + d * d);
+      }
     }
+    rstd[r] = rsqrtf(warp_sum(v) / (float)p.dim + p.eps);
   }
-  const float rstd = rsqrtf(warp_sum(v) / (float)p.dim + p.eps);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     if (i < nvec) {
       const int e = (lane + 32 * i) * 4;
       const float4 w = __ldg(reinterpret_cast<const float4*>(p.weight + e));
       const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + e));
-      const float y0 = (x[i].x - mean) * rstd * w.x + b.x;
-      const float y1 = (x[i].y - mean) * rstd * w.y + b.y;
-      const float y2 = (x[i].z - mean) * rstd * w.z + b.z;
-      const float y3 = (x[i].w - mean) * rstd * w.w + b.w;
-      if (OUT_F32) {
-        *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (long long)row * p.ld_out + e) =
-            make_float4(y0, y1, y2, y3);
-      } else {
-        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out) + (long long)row * p.ld_out + e) =
-            make_uint2(pack_half2(y0, y1), pack_half2(y2, y3));
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        if (!live[r]) continue;
+        const float y0 = (x[r][i].x - mean[r]) * rstd[r] * w.x + b.x;
+        const float y1 = (x[r][i].y - mean[r]) * rstd[r] * w.y + b.y;
+        const float y2 = (x[r][i].z - mean[r]) * rstd[r] * w.z + b.z;
+        const float y3 = (x[r][i].w - mean[r]) * rstd[r] * w.w + b.w;
+        if (OUT_F32) {
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (long long)(row0 + r) * p.ld_out + e) =
+              make_float4(y0, y1, y2, y3);
+        } else {
+          *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out) + (long long)(row0 + r) * p.ld_out + e) =
+              make_uint2(pack_half2(y0, y1), pack_half2(y2, y3));
+        }
       }
     }
   }
@@ -542,13 +561,25 @@ extern "C" int udb_layernorm(const udb_layernorm_t* p, void* stream) {
     return 1;
   }
   if (p->dim % 128 != 0 || p->dim > 1024) { set_error("udb_layernorm: dim %d unsupported (multiple of 128, <= 1024)", p->dim); return 1; }
-  const int grid = (p->rows + 7) / 8;
+  // UDB_LN_ROWS=2: two rows per warp.  Measured on 12888x1024 f32->f16: 26.6 us vs 22.5 us with one row per warp
+  // (a plain f32->f16 cast copy of the same bytes takes 18.5 us with the same event overhead), so one row is the default.
+  static const int rows_per_warp_env = [] { const char* e = getenv("UDB_LN_ROWS"); return e ? atoi(e) : 1; }();
+  const int R = (p->rows >= 2048 && rows_per_warp_env == 2) ? 2 : 1;
+  const int grid = (p->rows + 8 * R - 1) / (8 * R);
   if (grid == 0) return 0;
   cudaError_t e;
-  if (p->in_f32 && p->out_f32) e = launch_ex(layernorm_kernel<true, true>, dim3(grid), dim3(256), 0, ST(stream), 1, *p);
-  else if (p->in_f32) e = launch_ex(layernorm_kernel<true, false>, dim3(grid), dim3(256), 0, ST(stream), 1, *p);
-  else if (p->out_f32) e = launch_ex(layernorm_kernel<false, true>, dim3(grid), dim3(256), 0, ST(stream), 1, *p);
-  else e = launch_ex(layernorm_kernel<false, false>, dim3(grid), dim3(256), 0, ST(stream), 1, *p);
+  const dim3 g(grid), blk(256);
+  if (R == 2) {
+    if (p->in_f32 && p->out_f32) e = launch_ex(layernorm_kernel<true, true, 2>, g, blk, 0, ST(stream), 1, *p);
+    else if (p->in_f32) e = launch_ex(layernorm_kernel<true, false, 2>, g, blk, 0, ST(stream), 1, *p);
+    else if (p->out_f32) e = launch_ex(layernorm_kernel<false, true, 2>, g, blk, 0, ST(stream), 1, *p);
+    else e = launch_ex(layernorm_kernel<false, false, 2>, g, blk, 0, ST(stream), 1, *p);
+  } else {
+    if (p->in_f32 && p->out_f32) e = launch_ex(layernorm_kernel<true, true, 1>, g, blk, 0, ST(stream), 1, *p);
+    else if (p->in_f32) e = launch_ex(layernorm_kernel<true, false, 1>, g, blk, 0, ST(stream), 1, *p);
+    else if (p->out_f32) e = launch_ex(layernorm_kernel<false, true, 1>, g, blk, 0, ST(stream), 1, *p);
+    else e = launch_ex(layernorm_kernel<false, false, 1>, g, blk, 0, ST(stream), 1, *p);
+  }
   if (e != cudaSuccess) { set_error("layernorm_kernel launch: %s", cudaGetErrorString(e)); return 1; }
   return check_launch("layernorm_kernel");
 }

@@ -345,3 +345,20 @@ def test_vitb_shallow_vs_oracle():
     out2 = m.infer(rgb)
     for k in out:
         assert torch.equal(out[k], out2[k]), k
+
+
+@pytest.mark.parametrize("shape,level", [((1, 333, 517), 0), ((1, 480, 1600), 9), ((1, 1000, 400), 5), ((3, 150, 210), 9)])
+def test_odd_shapes_extreme_ratios_and_levels(shallow, shape, level):
+    """Shapes that are not multiples of anything, aspect ratios outside [0.5, 2.5] (top/bottom and left/right
+    padding, SURVEY 8a1's examples), both ends of resolution_level, odd batch: C engine vs the oracle."""
+    import unidepth_oracle as O
+    cfg, sd = shallow
+    rgb = _rgb(shape, 11 + level)
+    torch.set_num_threads(min(32, os.cpu_count()))
+    ref = O.infer_v2(sd, copy.deepcopy(cfg), rgb, resolution_level=level)
+    m = _model(cfg, sd)
+    m.resolution_level = level
+    out = m.infer(rgb)
+    for k in ref:
+        assert out[k].shape == ref[k].shape, (k, out[k].shape, ref[k].shape)
+    _check(out, ref)

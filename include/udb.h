@@ -329,7 +329,11 @@ typedef struct udb_geometry_t {
   int32_t gh, gw;         /* patch grid */
   double factor;
 } udb_geometry_t;
-/* resolution_level: 0..9, or -1 = attribute unset (default pixel bounds). */
+/* resolution_level: 0..9, -1 = attribute unset (default pixel bounds), or UDB_LEVEL_NETWORK_ONLY: the input
+ * already is the network input (normalised float tensor, H and W multiples of 14): identity geometry, the
+ * outputs are the network's own (the reference's `encode_decode` as used by `forward_test`,
+ * unidepthv2.py:134-160, and by the ONNX wrappers, export.py:27-45). */
+#define UDB_LEVEL_NETWORK_ONLY (-2)
 int udb_geometry(const udb_engine* e, int32_t H, int32_t W, int32_t resolution_level, udb_geometry_t* out);
 
 /* Bytes of scratch udb_infer_v2 needs for this shape; also prepares the per-shape tables (may

@@ -62,6 +62,25 @@ def main():
         d = arrays["depth"]
         print(name, "depth range", float(d.min()), float(d.max()), "conf", float(arrays["confidence"].min()),
               float(arrays["confidence"].max()), "K", arrays["intrinsics"][0].tolist())
+    # reference outputs of the validation glue (misc.py:596-690, evaluation_depth.py:93-110) on seeded inputs
+    from unidepth.utils.misc import match_gt, match_intrinsics
+    from unidepth.utils.evaluation_depth import DICT_METRICS
+    g = torch.Generator().manual_seed(99)
+    pred = torch.rand(3, 2, 28, 42, generator=g) + 0.5
+    gt = torch.rand(3, 1, 37, 61, generator=g) + 0.5
+    img = torch.zeros(3, 3, 28, 42)
+    pads1 = [(0, 0, 0, 0), (2, 3, 0, 0), (0, 0, 4, 1)]
+    pads2 = [(1, 0, 0, 2), (0, 0, 0, 0), (3, 3, 1, 1)]
+    K = torch.tensor([[30.0, 0, 20.5], [0, 31.0, 14.0], [0, 0, 1]]).repeat(3, 1, 1) + torch.rand(3, 3, 3, generator=g) * torch.tensor([[1.0, 0, 1], [0, 1, 1], [0, 0, 0]])
+    arrays = dict(pred=pred.numpy(), gt=gt.numpy(), K=K.numpy(), pads1=np.array(pads1), pads2=np.array(pads2),
+                  m_none=match_gt(pred, gt, None, None).numpy(), m_p1=match_gt(pred, gt, pads1, None).numpy(),
+                  m_p12=match_gt(pred, gt, pads1, pads2).numpy(),
+                  k_p1=match_intrinsics(K, img, gt, pads1, None).numpy(), k_p12=match_intrinsics(K, img, gt, pads1, pads2).numpy())
+    a, b = gt[0, 0].flatten(), (gt[0, 0] * (1 + 0.2 * (torch.rand(37, 61, generator=g) - 0.5))).flatten()
+    arrays["met_gt"], arrays["met_pred"] = a.numpy(), b.numpy()
+    for name in ("d1", "d2", "d3", "rmse", "rmselog", "arel", "sqrel", "log10", "silog"):
+        arrays["met_" + name] = np.array(float(DICT_METRICS[name](a, b).mean()))
+    np.savez_compressed(os.path.join(out_dir, "validation_glue.npz"), **arrays)
     # also copy the configs the tests need (JSON input format, not code)
     for cfg_name in ("config_v2_vits14.json", "config_v2_vitl14.json", "config_v2_vitb14.json"):
         cfg = json.load(open(os.path.join(REF, "configs", cfg_name)))

@@ -362,3 +362,54 @@ def test_odd_shapes_extreme_ratios_and_levels(shallow, shape, level):
     for k in ref:
         assert out[k].shape == ref[k].shape, (k, out[k].shape, ref[k].shape)
     _check(out, ref)
+
+
+def test_network_only_entry_and_forward_test(shallow):
+    """network_forward (the reference's ONNX wrappers, export.py:27-79) and forward_test
+    (unidepthv2.py:134-160): the normalised tensor IS the network input -- here deliberately below
+    pixels_min, where infer() would up-scale -- against the oracle's encoder + decoder at that size."""
+    import unidepth_oracle as O
+    from unidepth_b200.validation import match_gt, match_intrinsics
+    cfg, sd = shallow
+    s = O.ModelSpec(cfg)
+    m = _model(cfg, sd)
+    B, H, W = 2, 14 * 12, 14 * 17
+    x = torch.randn(B, 3, H, W, generator=torch.Generator().manual_seed(3))
+    torch.set_num_threads(min(32, os.cpu_count()))
+    feats, clss = O.vit_encoder(sd, s, x)
+    dec = O.decoder(sd, s, feats, clss, (H, W))
+    rays_ref = dec["rays"].transpose(1, 2).reshape(B, 3, H, W)
+    pts_ref = rays_ref * dec["radius"]
+
+    def check(pts, conf, K, pts_r, dec_r):
+        rel = ((pts[:, 2:].cpu() - pts_r[:, 2:]).abs() / pts_r[:, 2:])
+        kk, kr = K.cpu(), dec_r["intrinsics"]
+        kerr = max(((kk[:, i, j] - kr[:, i, j]).abs() / kr[:, i, j].abs()).max().item() for i, j in ((0, 0), (1, 1), (0, 2), (1, 2)))
+        cerr = ((conf.cpu() - dec_r["confidence"]).abs() / dec_r["confidence"]).mean().item()
+        print(f"network-only: depth ARel {rel.mean().item():.3e} max {rel.max().item():.3e}; K rel {kerr:.3e}; conf {cerr:.3e}")
+        assert rel.mean().item() < 1e-3 and rel.max().item() < 4e-3 and kerr < 3e-4 and cerr < 1e-3
+
+    pts, conf, K = m.network_forward(x)
+    assert pts.shape == (B, 3, H, W) and conf.shape == (B, 1, H, W) and K.shape == (B, 3, 3)
+    check(pts, conf, K, pts_ref, dec)
+    pts_b, conf_b, K_b = m.network_forward(x)                      # graph replay
+    assert torch.equal(pts, pts_b) and torch.equal(K, K_b)
+    # ONNXcam variant: rays supplied by the caller
+    Kc = torch.tensor([[[210.0, 0.0, 120.0], [0.0, 205.0, 80.0], [0.0, 0.0, 1.0]]]).repeat(B, 1, 1)
+    rays_in = O.pinhole_rays(Kc, H, W)                             # [B, HW, 3]
+    dec2 = O.decoder(sd, s, feats, clss, (H, W), rays_gt=rays_in)
+    rmap = rays_in.transpose(1, 2).reshape(B, 3, H, W)
+    pts2, conf2, K2 = m.network_forward(x, rays=rmap)
+    check(pts2, conf2, K2, rmap * dec2["radius"], dec2)
+    # forward_test: predictions matched to a ground-truth frame of another size, with paddings
+    pads = [(0, 0, 0, 0), (14, 0, 0, 28)]
+    gt = torch.ones(B, 1, 2 * H + 3, 2 * W - 5)
+    out = m({"image": x, "depth": gt, "paddings": pads}, [])
+    assert set(out) == {"depth", "points", "confidence", "rays", "intrinsics"}
+    ref_depth = match_gt(pts_ref[:, 2:], gt, padding1=pads, padding2=None)
+    assert out["depth"].shape == gt.shape
+    rel = ((out["depth"].cpu() - ref_depth).abs() / ref_depth)
+    assert rel.mean().item() < 1e-3
+    ref_K = match_intrinsics(dec["intrinsics"], x, gt, padding1=pads, padding2=None)
+    assert ((out["intrinsics"].cpu() - ref_K).abs().max() / ref_K.abs().max()).item() < 3e-4
+    assert out["rays"].shape == (B, 3, H, W)

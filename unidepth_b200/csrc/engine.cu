@@ -586,6 +586,18 @@ int udb_set_scalar(udb_engine* e, const char* name, double value) {
 
 int udb_geometry(const udb_engine* e, int32_t H, int32_t W, int32_t level, udb_geometry_t* out) {
   if (!e || !out || H <= 0 || W <= 0) { set_error("udb_geometry: bad argument"); return 1; }
+  if (level == UDB_LEVEL_NETWORK_ONLY) {
+    // the caller's tensor IS the network input (forward_test / ONNX-style entry, unidepthv2.py:134-160,
+    // export.py:27-45): no padding, no resize, outputs at the same resolution
+    if (H % PATCH || W % PATCH) { set_error("network-only input %dx%d must be a multiple of %d", H, W, PATCH); return 1; }
+    memset(out, 0, sizeof(*out));
+    out->padded_h = out->net_h = H;
+    out->padded_w = out->net_w = W;
+    out->gh = H / PATCH;
+    out->gw = W / PATCH;
+    out->factor = 1.0;
+    return 0;
+  }
   paddings(H, W, e->cfg.ratio_min, e->cfg.ratio_max, out);
   return resize(e->cfg, level, out);
 }

@@ -111,9 +111,6 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
                                       strict=False)
             return model
 
-    def forward(self, *args, **kwargs):
-        raise NotImplementedError("training/validation forward is out of scope; use .infer()")
-
     # ------------------------------------------------------------------ weight packing
     def _fingerprint(self):
         return tuple((p.data_ptr(), p._version) for p in self.parameters())
@@ -372,7 +369,7 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
         lib = cabi.lib()
         dev = rgb.device
         B, _, H, W = rgb.shape
-        lvl = -1 if level is None else int(level)
+        lvl = -1 if level is None else int(level)      # -2: network-only (identity geometry)
         g = cabi.Geometry()
         cabi.check(lib.udb_geometry(eng, H, W, lvl, C.byref(g)), "udb_geometry")
         assert (g.net_h, g.net_w) == tuple(geom["net_hw"]) and (g.pad_l, g.pad_r, g.pad_t, g.pad_b) == tuple(geom["paddings"])
@@ -646,30 +643,91 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
         if rgb.ndim == 3:
             rgb = rgb.unsqueeze(0)
         B, _, H, W = rgb.shape
+        rgb = self._to_device_input(rgb)
+        paddings, (ph, pw) = get_paddings((H, W), self.shape_constraints["ratio_bounds"])
+        factor, (nh, nw) = get_resize_factor((ph, pw), bounds)
+        geom = dict(paddings=paddings, padded_hw=(ph, pw), factor=factor, net_hw=(nh, nw), out_hw=(H, W))
+        key = (level, tuple(self.shape_constraints["ratio_bounds"]), bounds)
+        return self._run(rgb, geom, level, normalize, camera, key)
+
+    NETWORK_ONLY = -2      # udb.h: UDB_LEVEL_NETWORK_ONLY
+
+    @torch.no_grad()
+    def network_forward(self, rgbs: torch.Tensor, rays: Optional[torch.Tensor] = None):
+        """The network alone, as the reference's ONNX wrappers expose it (unidepthv2/export.py:27-45 `forward(rgbs)`
+        and :58-79 `forward(rgbs, rays)`): `rgbs` is the NORMALISED float network input [B,3,H,W] with H, W
+        multiples of 14; no padding / resizing / cropping.  Returns (pts_3d [B,3,H,W], confidence [B,1,H,W],
+        intrinsics [B,3,3])."""
+        out = self._network_outputs(rgbs, rays)
+        return out["points"], out["confidence"], out["intrinsics"]
+
+    def _network_outputs(self, rgbs, rays=None):
+        assert rgbs.ndim == 4 and rgbs.shape[1] == 3, "rgbs must be [B,3,H,W]"
+        B, _, H, W = rgbs.shape
+        if H % PATCH or W % PATCH:
+            raise ValueError(f"network input {H}x{W} must be a multiple of {PATCH}")
+        rgbs = self._to_device_input(rgbs.float())
+        geom = dict(paddings=(0, 0, 0, 0), padded_hw=(H, W), factor=1.0, net_hw=(H, W), out_hw=(H, W))
+        rays_in = None
+        if rays is not None:
+            assert tuple(rays.shape) == (B, 3, H, W), "rays must be [B,3,H,W] at the network resolution"
+            rays_in = rays.to(rgbs.device, f32).permute(0, 2, 3, 1).reshape(B, H * W, 3).contiguous()
+        return self._run(rgbs, geom, self.NETWORK_ONLY, False, None, ("network_only",), rays_in=rays_in)
+
+    @torch.no_grad()
+    def forward_test(self, inputs: dict, image_metas=None):
+        """Validation forward of the reference (unidepthv2.py:134-160): `inputs["image"]` is the data
+        pipeline's normalised network input, `inputs["depth"]` the ground truth whose size the predictions
+        are matched to, `inputs["paddings"]` the per-image (l, r, t, b) paddings of the network input,
+        optional `inputs["camera"]` a camera object for GT rays (:361-362)."""
+        from .validation import match_gt, match_intrinsics
+        image = inputs["image"]
+        rays = None
+        cam = inputs.get("camera", None)
+        if cam is not None:
+            B, _, H, W = image.shape
+            rays = cam.get_rays(shapes=(B, H, W))
+        out = self._network_outputs(image, rays)
+        gt, pads = inputs["depth"], inputs.get("paddings", None)
+        res = {k: match_gt(out[k], gt, padding1=pads, padding2=None) for k in ("depth", "points", "confidence")}
+        res["rays"] = out["rays"] / torch.norm(out["rays"], dim=1, keepdim=True).clip(min=1e-5)
+        res["intrinsics"] = match_intrinsics(out["intrinsics"], image, gt, padding1=pads, padding2=None)
+        return res
+
+    def forward(self, inputs=None, image_metas=None, *args, **kwargs):
+        """Evaluation-mode `forward` of the reference dispatches to `forward_test` (unidepthv2.py:162-166);
+        training is out of scope."""
+        if self.training or not isinstance(inputs, dict):
+            raise NotImplementedError("training forward is out of scope; use .infer() / .forward_test() in eval mode")
+        return self.forward_test(inputs, image_metas)
+
+    def _to_device_input(self, rgb):
         dev = self.device
         if dev.type != "cuda":
             raise RuntimeError("unidepth_b200 has no CPU path: move the model to a CUDA device")
         rgb = rgb.to(dev)
         if rgb.dtype not in (torch.uint8, f32):
             rgb = rgb.float()
-        rgb = rgb.contiguous()
+        return rgb.contiguous()
 
-        paddings, (ph, pw) = get_paddings((H, W), self.shape_constraints["ratio_bounds"])
-        factor, (nh, nw) = get_resize_factor((ph, pw), bounds)
+    def _run(self, rgb, geom, level, normalize, camera, key_extra, rays_in=None):
+        """Common tail of infer / network_forward: camera handling, engine or Python schedule, CUDA graph cache."""
+        B, _, H, W = rgb.shape
+        dev = rgb.device
+        nh, nw = geom["net_hw"]
         gh, gw = nh // PATCH, nw // PATCH
         bands = self.spec.hidden // 2
-        geom = dict(paddings=paddings, padded_hw=(ph, pw), factor=factor, net_hw=(nh, nw), out_hw=(H, W))
         skey = ("scales", gh, gw)
         if skey not in self._posembed_cache:
             # positional_embedding.py:231-233 -- computed with the same torch expression (host, once)
             self._posembed_cache[skey] = (2.0 ** torch.linspace(0.0, math.log2(max(gh, gw) // 2), steps=bands)).to(dev)
         geom["scales"] = self._posembed_cache[skey]
 
-        gt_intr4, camera_k, rays_in = None, None, None
+        gt_intr4, camera_k = None, None
         if camera is not None and not isinstance(camera, torch.Tensor):
-            rays_in = self._camera_rays(camera, B, paddings, factor, (nh, nw), dev)
+            rays_in = self._camera_rays(camera, B, geom["paddings"], geom["factor"], (nh, nw), dev)
         elif camera is not None:
-            gt_intr4 = self._gt_intrinsics(camera, B, paddings, factor, dev)     # validates the argument
+            gt_intr4 = self._gt_intrinsics(camera, B, geom["paddings"], geom["factor"], dev)     # validates the argument
             camera_k = camera.to(dev, f32).reshape(-1, 3, 3)
             if camera_k.shape[0] == 1 and B > 1:
                 camera_k = camera_k.expand(B, 3, 3)
@@ -683,11 +741,10 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
             self._pos_embed(gh, gw)
             return self._forward(inp, geom, normalize, gt_intr4=gt_intr4, rays_in=rays_in)
 
-        if not self.use_cuda_graph or camera is not None:
+        if not self.use_cuda_graph or camera is not None or rays_in is not None:
             return run(rgb)
 
-        key = (B, H, W, rgb.dtype, level, bool(normalize), tuple(self.shape_constraints["ratio_bounds"]), bounds,
-               bool(self.use_engine))
+        key = (B, H, W, rgb.dtype, bool(normalize), bool(self.use_engine)) + tuple(key_extra)
         entry = self._graphs.get(key)
         if entry is None:
             static_in = rgb.clone()

@@ -173,3 +173,36 @@ def test_hubconf_entry_point():
         hubconf.UniDepth("v1", "cnvnxtl", pretrained=False)
     with pytest.raises(AssertionError):
         hubconf.UniDepth("v2", "resnet50", pretrained=False)
+
+
+def test_engine_fails_loudly_without_a_gpu_or_weights():
+    """No CPU fallback anywhere in the C engine: preparing a shape needs the device, and an engine whose
+    packed tensors were never registered reports which one is missing instead of computing."""
+    import ctypes as C
+    from unidepth_b200 import _cabi
+    lib = _cabi.lib()
+    cfg = _cabi.Config()
+    cfg.embed_dim, cfg.depth, cfg.enc_heads, cfg.pos_grid = 384, 12, 6, 37
+    for i, t in enumerate((3, 6, 9, 12)):
+        cfg.taps[i] = t
+    cfg.hidden, cfg.dec_heads, cfg.expansion, cfg.out_dim, cfg.n_stages = 256, 8, 4, 32, 3
+    for i in range(3):
+        cfg.dec_depths[i] = 2
+    cfg.ratio_min, cfg.ratio_max, cfg.pixels_min, cfg.pixels_max = 0.5, 2.5, 200000.0, 600000.0
+    h = C.c_void_p()
+    assert lib.udb_create(C.byref(cfg), C.byref(h)) == 0
+    try:
+        assert lib.udb_workspace_bytes(h, 1, 120, 160, -1) == 0          # 'pos' not registered
+        assert b"pos" in lib.udb_last_error()
+        buf = (C.c_float * 64)()
+        shape = (C.c_int64 * 2)(4, 4)
+        addr = C.addressof(buf)
+        assert lib.udb_set_weight(h, b"pos", C.c_void_p(addr + 4), shape, 2, _cabi.DT_F32) != 0      # misaligned pointer
+        assert b"aligned" in lib.udb_last_error()
+        if not torch.cuda.is_available():
+            aligned = (addr + 15) & ~15
+            assert lib.udb_set_weight(h, b"pos", C.c_void_p(aligned), shape, 2, _cabi.DT_F32) == 0
+            assert lib.udb_workspace_bytes(h, 1, 120, 160, -1) == 0      # cudaMalloc of the tables fails: no device
+            assert lib.udb_last_error() != b""
+    finally:
+        lib.udb_destroy(h)

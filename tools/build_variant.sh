@@ -1,6 +1,6 @@
 #!/bin/bash
 # Build a variant libudb with extra -D flags for same-box A/B runs:
-#   tools/build_variant.sh /root/repo/gpurun_variants/libudb_x.so -DUDB_ATTN_SPEC=0
+#   tools/build_variant.sh /root/repo/variants/libudb_trace.so -DUDB_ATTN_TRACE
 # then run with UDB_LIB=<that path>.
 set -e
 out=$1; shift

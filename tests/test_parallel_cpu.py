@@ -50,6 +50,18 @@ def _worker(rank, world, port, q):
         for k in exp:
             ok &= torch.equal(full[k][2 * r:2 * r + 2], exp[k])
             ok &= torch.equal(full2[k][2 * r:2 * r + 2], exp[k])
+    # uneven tail: 5 images over 2 ranks -> 3 + 2
+    from unidepth_b200.parallel import shard_bounds
+    counts = [shard_bounds(5, r, world)[1] - shard_bounds(5, r, world)[0] for r in range(world)]
+    mine = _fake_out(counts[rank], 10 + rank)
+    full3 = gather_outputs(mine, world, counts=counts)
+    off = 0
+    for r in range(world):
+        exp = _fake_out(counts[r], 10 + r)
+        for k in exp:
+            ok &= torch.equal(full3[k][off:off + counts[r]], exp[k])
+        off += counts[r]
+    ok &= full3["depth"].shape[0] == 5
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 

@@ -138,12 +138,25 @@ def p2p_gather_for(out: Dict[str, torch.Tensor], group=None):
     return _p2p_cache[key]
 
 
-def gather_outputs(out: Dict[str, torch.Tensor], world: int, group=None, async_op: bool = False):
-    """Single all-gather of the packed per-rank buffer (equal per-rank batch sizes).
+def gather_outputs(out: Dict[str, torch.Tensor], world: int, group=None, async_op: bool = False, counts=None):
+    """Single all-gather of the packed per-rank buffer.  `counts` = images per rank when they differ
+    (uneven tail of the global batch; every rank can derive it from shard_bounds): the local buffer is
+    zero-padded to the largest count for the collective and the padding rows are dropped afterwards.
     async_op=True returns a PendingOutputs: the collective then overlaps whatever the caller enqueues
     next (the following micro-batch's infer), which is how a serving loop hides it."""
     if world == 1:
         return PendingOutputs(None, pack_outputs(out), None, out) if async_op else out
+    if counts is not None and len(set(counts)) > 1:
+        assert len(counts) == world and out["depth"].shape[0] == counts[dist.get_rank(group)]
+        bmax = max(counts)
+        local = pack_outputs(out)
+        if local.shape[0] < bmax:
+            local = torch.cat([local, local.new_zeros((bmax - local.shape[0], local.shape[1]))], 0)
+        full = torch.empty((world * bmax, local.shape[1]), device=local.device, dtype=local.dtype)
+        dist.all_gather_into_tensor(full, local, group=group)
+        keep = torch.cat([torch.arange(r * bmax, r * bmax + c) for r, c in enumerate(counts)]).to(full.device)
+        res = unpack_outputs(full.index_select(0, keep), out)
+        return PendingOutputs(None, pack_outputs(res), None, res) if async_op else res
     if dist.get_backend(group) == "nccl":
         p2p = p2p_gather_for(out, group)
         if p2p is not None:
@@ -161,10 +174,11 @@ def gather_outputs(out: Dict[str, torch.Tensor], world: int, group=None, async_o
 def infer_sharded(model, rgb: torch.Tensor, async_op: bool = False, **kw):
     """`rgb` is the GLOBAL batch [N,3,H,W] (same on every rank); returns the global outputs on
     every rank (or, with async_op=True, a PendingOutputs whose gather is still in flight).
-    N must be divisible by the world size."""
+    N need not be divisible by the world size: low ranks take the remainder (shard_bounds)."""
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
     n = rgb.shape[0]
-    assert n % world == 0, "global batch must be divisible by the number of ranks"
+    assert n >= world, "need at least one image per rank"
     lo, hi = shard_bounds(n, rank, world)
-    return gather_outputs(model.infer(rgb[lo:hi], **kw), world, async_op=async_op)
+    counts = [shard_bounds(n, r, world)[1] - shard_bounds(n, r, world)[0] for r in range(world)]
+    return gather_outputs(model.infer(rgb[lo:hi], **kw), world, async_op=async_op, counts=counts)

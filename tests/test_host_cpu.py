@@ -206,3 +206,22 @@ def test_engine_fails_loudly_without_a_gpu_or_weights():
             assert lib.udb_last_error() != b""
     finally:
         lib.udb_destroy(h)
+
+
+def test_c_example_links_and_runs_against_the_abi():
+    """examples/engine_minimal.c: plain C, no torch, links libudb.so and prints the reference's geometry
+    examples: 480x640 -> 490x644, 1024x1536 -> 644x952, 480x1600 -> pad 80/80, 1000x400 -> pad 50/50."""
+    from unidepth_b200 import _cabi
+    from unidepth_b200.build import build
+    build()
+    libdir = os.path.dirname(_cabi.LIB_PATH)
+    with tempfile.TemporaryDirectory() as d:
+        exe = os.path.join(d, "engine_minimal")
+        subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                               os.path.join(ROOT, "examples", "engine_minimal.c"), "-L", libdir, "-ludb",
+                               f"-Wl,-rpath,{libdir}", "-o", exe])
+        out = subprocess.check_output([exe], text=True)
+    assert "480x640 -> pad l0 r0 t0 b0, network 490x644 (grid 35x46)" in out
+    assert "1024x1536 -> pad l0 r0 t0 b0, network 644x952 (grid 46x68)" in out
+    assert "480x1600 -> pad l0 r0 t80 b80" in out and "1000x400 -> pad l50 r50 t0 b0" in out
+    assert "as expected:" in out and "udb version 1" in out

@@ -81,6 +81,11 @@ def main():
     for name in ("d1", "d2", "d3", "rmse", "rmselog", "arel", "sqrel", "log10", "silog"):
         arrays["met_" + name] = np.array(float(DICT_METRICS[name](a, b).mean()))
     np.savez_compressed(os.path.join(out_dir, "validation_glue.npz"), **arrays)
+    # V1 ray embedding basis (next row): the reference's rsh_cart_8 on seeded unit vectors (sht.py:833-1393)
+    from unidepth.utils.sht import rsh_cart_8
+    v = torch.randn(256, 3, generator=torch.Generator().manual_seed(5), dtype=torch.float64)
+    v = v / v.norm(dim=-1, keepdim=True)
+    np.savez_compressed(os.path.join(out_dir, "sh81.npz"), xyz=v.numpy(), rsh=rsh_cart_8(v).numpy())
     # also copy the configs the tests need (JSON input format, not code)
     for cfg_name in ("config_v2_vits14.json", "config_v2_vitl14.json", "config_v2_vitb14.json"):
         cfg = json.load(open(os.path.join(REF, "configs", cfg_name)))

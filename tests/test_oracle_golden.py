@@ -57,3 +57,15 @@ def test_shape_arithmetic_examples():
     levels = {0: (434, 574), 2: (490, 644), 5: (560, 742), 9: (658, 868)}
     for lvl, hw in levels.items():
         assert O.get_resize_factor((480, 640), O.resolve_pixel_bounds((2e5, 6e5), lvl))[1] == hw
+
+
+def test_sh81_recurrence_matches_reference_polynomials(golden_dir):
+    """oracle/sh81.py (definition + recurrences) vs the reference's expanded degree-8 polynomials
+    (unidepth/utils/sht.py:833-1393) on seeded unit vectors: the oracle of V1's ray embedding basis."""
+    from sh81 import rsh_cart
+    z = np.load(os.path.join(golden_dir, "sh81.npz"))
+    xyz, ref = torch.from_numpy(z["xyz"]), torch.from_numpy(z["rsh"])
+    got = rsh_cart(xyz)
+    assert got.shape == ref.shape == (256, 81)
+    assert float((got - ref).abs().max()) < 5e-8          # the reference's literals carry ~15 digits
+    assert float((rsh_cart(xyz.float()) - ref.float()).abs().max()) < 1e-5

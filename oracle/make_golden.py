@@ -86,6 +86,33 @@ def main():
     v = torch.randn(256, 3, generator=torch.Generator().manual_seed(5), dtype=torch.float64)
     v = v / v.norm(dim=-1, keepdim=True)
     np.savez_compressed(os.path.join(out_dir, "sh81.npz"), xyz=v.numpy(), rsh=rsh_cart_8(v).numpy())
+    # V1 host-side pieces (unidepthv1.py:30-94, geometric.py:13-73) on seeded inputs
+    from unidepth.models.unidepthv1.unidepthv1 import _paddings, _postprocess, _preprocess, _shapes
+    from unidepth.utils.geometric import generate_rays as ref_rays, spherical_zbuffer_to_euclidean as ref_s2e
+    g = torch.Generator().manual_seed(21)
+    net = (462, 616)
+    cases = [(480, 640), (375, 1242), (1000, 400), (231, 308)]
+    arr = {"cases": np.array(cases)}
+    for i, (h, w) in enumerate(cases):
+        (rh, rw), ratio = _shapes((h, w), net)
+        pads = _paddings((rh, rw), net)
+        arr[f"shape{i}"] = np.array([rh, rw, *pads], dtype=np.int64)
+        arr[f"ratio{i}"] = np.array(ratio)
+    h, w = 60, 99
+    rgb = torch.rand(2, 3, h, w, generator=g)
+    K = torch.tensor([[[75.0, 0, 50.0], [0, 76.0, 30.5], [0, 0, 1]], [[70.0, 0, 49.0], [0, 69.5, 29.25], [0, 0, 1]]])
+    small_net = (42, 56)
+    (rh, rw), ratio = _shapes((h, w), small_net)
+    pads = _paddings((rh, rw), small_net)
+    x, k2 = _preprocess(rgb, K, (rh, rw), pads, ratio, small_net)
+    preds = [torch.rand(2, 3, small_net[0] // s, small_net[1] // s, generator=g) for s in (1, 2, 4)]
+    post, k3 = _postprocess(preds, k2.clone(), small_net, pads, ratio, (h, w))
+    rays, angles = ref_rays(k2, small_net)
+    tpz = torch.cat([angles, 1.0 + torch.rand(2, small_net[0] * small_net[1], 1, generator=g)], dim=-1)
+    arr.update(rgb=rgb.numpy(), K=K.numpy(), pre=x.numpy(), k_pre=k2.numpy(), post=post.numpy(), k_post=k3.numpy(),
+               rays=rays.numpy(), angles=angles.numpy(), tpz=tpz.numpy(), xyz=ref_s2e(tpz).numpy(),
+               **{f"pred{j}": p.numpy() for j, p in enumerate(preds)})
+    np.savez_compressed(os.path.join(out_dir, "v1_parts.npz"), **arr)
     # also copy the configs the tests need (JSON input format, not code)
     for cfg_name in ("config_v2_vits14.json", "config_v2_vitl14.json", "config_v2_vitb14.json"):
         cfg = json.load(open(os.path.join(REF, "configs", cfg_name)))

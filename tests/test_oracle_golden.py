@@ -69,3 +69,31 @@ def test_sh81_recurrence_matches_reference_polynomials(golden_dir):
     assert got.shape == ref.shape == (256, 81)
     assert float((got - ref).abs().max()) < 5e-8          # the reference's literals carry ~15 digits
     assert float((rsh_cart(xyz.float()) - ref.float()).abs().max()) < 1e-5
+
+
+def test_v1_host_pieces_match_reference(golden_dir):
+    """oracle/unidepth_v1_parts.py vs the reference's V1 helpers (unidepthv1.py:30-94, geometric.py:13-73):
+    fixed-shape resize / pad arithmetic (incl. the reference's benchmark shape 480x640 -> 462x616),
+    pre/post-processing with the K updates, ray generation, (theta, phi, z) -> xyz."""
+    import unidepth_v1_parts as V
+    z = np.load(os.path.join(golden_dir, "v1_parts.npz"))
+    net = (462, 616)
+    for i, (h, w) in enumerate(z["cases"]):
+        (rh, rw), ratio = V.v1_shapes((int(h), int(w)), net)
+        assert [rh, rw, *V.v1_paddings((rh, rw), net)] == list(z[f"shape{i}"]) and ratio == float(z[f"ratio{i}"])
+    assert list(z["shape0"]) == [462, 616, 0, 0, 0, 0]
+    rgb, K = torch.from_numpy(z["rgb"]), torch.from_numpy(z["K"])
+    small_net = (42, 56)
+    (rh, rw), ratio = V.v1_shapes(tuple(rgb.shape[-2:]), small_net)
+    pads = V.v1_paddings((rh, rw), small_net)
+    x, k2 = V.v1_preprocess(rgb, K, (rh, rw), pads, ratio)
+    assert torch.equal(x, torch.from_numpy(z["pre"])) and torch.allclose(k2, torch.from_numpy(z["k_pre"]), rtol=0, atol=0)
+    preds = [torch.from_numpy(z[f"pred{j}"]) for j in range(3)]
+    post, k3 = V.v1_postprocess(preds, k2, small_net, pads, ratio, tuple(rgb.shape[-2:]))
+    assert torch.allclose(post, torch.from_numpy(z["post"]), atol=1e-6, rtol=0)
+    assert torch.allclose(k3, torch.from_numpy(z["k_post"]), atol=1e-4, rtol=1e-6)
+    rays, angles = V.generate_rays(k2, small_net)
+    assert torch.allclose(rays, torch.from_numpy(z["rays"]), atol=2e-6, rtol=0)
+    assert torch.allclose(angles, torch.from_numpy(z["angles"]), atol=2e-6, rtol=0)
+    xyz = V.spherical_zbuffer_to_euclidean(torch.from_numpy(z["tpz"]))
+    assert torch.allclose(xyz, torch.from_numpy(z["xyz"]), atol=0, rtol=0)

@@ -172,3 +172,49 @@ def make_state_dict(config: dict, seed: int = 0) -> Dict[str, torch.Tensor]:
             raise KeyError(key)
         sd[key] = t.float().contiguous()
     return sd
+
+
+def convnext_param_shapes(depths, dims, patch=4, kernel_size=7, mlp_ratio=4):
+    """key -> shape of the reference ConvNeXt encoder's state_dict (backbones/convnext.py:301-448)."""
+    from collections import OrderedDict
+    out = OrderedDict()
+    out["mask_token"] = (1, dims[0], 1, 1)
+    out["stem.0.weight"], out["stem.0.bias"] = (dims[0], 3, patch, patch), (dims[0],)
+    out["stem.1.weight"], out["stem.1.bias"] = (dims[0],), (dims[0],)
+    prev = dims[0]
+    for i, (depth, c) in enumerate(zip(depths, dims)):
+        s = f"stages.{i}."
+        if i > 0:
+            out[s + "downsample.0.weight"], out[s + "downsample.0.bias"] = (prev,), (prev,)
+            out[s + "downsample.1.weight"], out[s + "downsample.1.bias"] = (c, prev, 2, 2), (c,)
+        for j in range(depth):
+            b = f"{s}blocks.{j}."
+            out[b + "gamma"] = (c,)
+            out[b + "conv_dw.weight"], out[b + "conv_dw.bias"] = (c, 1, kernel_size, kernel_size), (c,)
+            out[b + "norm.weight"], out[b + "norm.bias"] = (c,), (c,)
+            out[b + "mlp.fc1.weight"], out[b + "mlp.fc1.bias"] = (mlp_ratio * c, c), (mlp_ratio * c,)
+            out[b + "mlp.fc2.weight"], out[b + "mlp.fc2.bias"] = (c, mlp_ratio * c), (c,)
+        prev = c
+    return out
+
+
+def make_convnext_state_dict(depths, dims, seed: int):
+    """Seeded, well-conditioned weights for the ConvNeXt encoder oracle (same recipe idea as make_state_dict)."""
+    sd = {}
+    for idx, (k, shp) in enumerate(convnext_param_shapes(depths, dims).items()):
+        g = torch.Generator().manual_seed(seed * 1_000_003 + idx)
+        if k.endswith("gamma"):
+            t = 0.5 + torch.rand(shp, generator=g)
+        elif len(shp) == 1 and k.endswith("weight"):
+            t = 1.0 + 0.1 * torch.randn(shp, generator=g)
+        elif len(shp) == 1:
+            t = 0.05 * torch.randn(shp, generator=g)
+        elif k == "mask_token":
+            t = torch.zeros(shp)
+        else:
+            fan_in = 1
+            for d in shp[1:]:
+                fan_in *= d
+            t = torch.randn(shp, generator=g) / fan_in ** 0.5
+        sd[k] = t
+    return sd

@@ -113,6 +113,23 @@ def main():
                rays=rays.numpy(), angles=angles.numpy(), tpz=tpz.numpy(), xyz=ref_s2e(tpz).numpy(),
                **{f"pred{j}": p.numpy() for j, p in enumerate(preds)})
     np.savez_compressed(os.path.join(out_dir, "v1_parts.npz"), **arr)
+    # ConvNeXt encoder (UniDepthV1's cnvnxtl pixel_encoder, scaled down): the reference's module on seeded weights
+    from unidepth.models.backbones.convnext import ConvNeXt
+    from fixture import convnext_param_shapes, make_convnext_state_dict
+    depths, dims = (2, 2, 3, 2), (32, 64, 96, 128)
+    enc = ConvNeXt(depths=depths, dims=dims, output_idx=[2, 4, 7, 9]).eval()
+    assert {k: tuple(v.shape) for k, v in enc.state_dict().items()} == dict(convnext_param_shapes(depths, dims))
+    big = ConvNeXt(depths=(3, 3, 27, 3), dims=(192, 384, 768, 1536), output_idx=[3, 6, 33, 36])     # config_v1_cnvnxtl.json
+    assert {k: tuple(v.shape) for k, v in big.state_dict().items()} == dict(convnext_param_shapes((3, 3, 27, 3), (192, 384, 768, 1536)))
+    del big
+    csd = make_convnext_state_dict(depths, dims, 4)
+    enc.load_state_dict(csd, strict=True)
+    xin = torch.randn(2, 3, 64, 96, generator=torch.Generator().manual_seed(8))
+    with torch.no_grad():
+        feats, toks = enc(xin)
+    ends = [1, 3, 6, 8]      # last block of each stage
+    np.savez_compressed(os.path.join(out_dir, "convnext_small.npz"), x=xin.numpy(),
+                        **{f"tok{j}": t.numpy() for j, t in enumerate(toks)}, **{f"feat{j}": feats[j].numpy() for j in ends})
     # also copy the configs the tests need (JSON input format, not code)
     for cfg_name in ("config_v2_vits14.json", "config_v2_vitl14.json", "config_v2_vitb14.json"):
         cfg = json.load(open(os.path.join(REF, "configs", cfg_name)))

@@ -97,3 +97,24 @@ def test_v1_host_pieces_match_reference(golden_dir):
     assert torch.allclose(angles, torch.from_numpy(z["angles"]), atol=2e-6, rtol=0)
     xyz = V.spherical_zbuffer_to_euclidean(torch.from_numpy(z["tpz"]))
     assert torch.allclose(xyz, torch.from_numpy(z["xyz"]), atol=0, rtol=0)
+
+
+def test_convnext_encoder_restatement_matches_reference_module(golden_dir):
+    """oracle/convnext_oracle.py vs the reference's ConvNeXt module (backbones/convnext.py, run by
+    oracle/make_golden.py with the timm stand-ins) on a scaled-down encoder: every block's mean token and the
+    last feature map of each stage."""
+    from convnext_oracle import convnext_encoder
+    from fixture import convnext_param_shapes, make_convnext_state_dict
+    z = np.load(os.path.join(golden_dir, "convnext_small.npz"))
+    depths, dims = (2, 2, 3, 2), (32, 64, 96, 128)
+    sd = make_convnext_state_dict(depths, dims, 4)
+    feats, toks = convnext_encoder(sd, torch.from_numpy(z["x"]), depths)
+    assert len(feats) == sum(depths)
+    for j, t in enumerate(toks):
+        assert torch.allclose(t, torch.from_numpy(z[f"tok{j}"]), atol=2e-5, rtol=1e-5), j
+    for j in (1, 3, 6, 8):
+        ref = torch.from_numpy(z[f"feat{j}"])
+        assert feats[j].shape == ref.shape and float((feats[j] - ref).abs().max()) < 5e-5, j
+    # the benchmark configuration's parameter census (config_v1_cnvnxtl.json: ConvNeXt-L, 196.2 M parameters)
+    n = sum(int(np.prod(s)) for s in convnext_param_shapes((3, 3, 27, 3), (192, 384, 768, 1536)).values())
+    assert 196.0e6 < n < 196.5e6

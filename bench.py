@@ -1,13 +1,18 @@
 #!/usr/bin/env python
 """Benchmark of the UniDepthV2.infer() hot path (see BASELINE.json / SURVEY.md section 8d).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|torch-gpu] [--workload default|hires]
 
-A "step" = one `infer` pass over one batch of synthetic uint8 RGB (ViT-L/14, 8 x 3x480x640 per GPU).
+A "step" = one `infer` pass over one batch of synthetic uint8 RGB.  Workloads (BASELINE.json `configs`):
+  default  configs[1]/[2]: ViT-L/14, 8 x 3x480x640 per GPU  (the configuration the metric is quoted on)
+  hires    configs[4]:     ViT-L/14, 4 x 3x1024x1536 per GPU (infer resizes to 644x952 -> 3129 tokens)
 Rank 0 prints ONE JSON line.  `value` = images/s with inputs resident in HBM (whole job, max over
 ranks); `e2e` = images/s through the public API with pinned-host input -> H2D -> infer -> D2H of
-depth + intrinsics inside the timed region.  `--impl reference` times the reference algorithm's CPU
-implementation (the torch-fp32 oracle port; /root/reference does not exist on the GPU box).
+depth + intrinsics inside the timed region (`e2e_full`: D2H of the whole seven-tensor output dict).
+`--impl reference` times the reference algorithm's CPU implementation (the torch-fp32 oracle port;
+/root/reference does not exist on the GPU box).  `--impl torch-gpu` is an INFORMATIVE extra arm, never the
+product: the same oracle port run by stock PyTorch on the GPU under fp16 autocast (what the reference itself does
+on a GPU, unidepthv2.py:239-241) -- the "kernel to beat on the same box" of BASELINE.md section 4.
 """
 from __future__ import annotations
 
@@ -25,8 +30,15 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-FLOPS_PER_IMAGE = 1648.56e9     # SURVEY.md section 8d / BASELINE.md section 2 (ViT-L/14 @ 490x644)
-WORKLOAD = dict(model="UniDepthV2 ViT-L/14", batch_per_gpu=8, input="3x480x640 uint8", net_input="490x644")
+# algorithmic FLOPs per image: SURVEY.md section 8d / BASELINE.md section 2
+WORKLOADS = {
+    "default": dict(flops=1648.56e9, batch=8, hw=(480, 640),
+                    desc=dict(model="UniDepthV2 ViT-L/14", batch_per_gpu=8, input="3x480x640 uint8", net_input="490x644",
+                              baseline_config="configs[1] (N=1) / configs[2] (N=8)")),
+    "hires": dict(flops=3708.02e9, batch=4, hw=(1024, 1536),
+                  desc=dict(model="UniDepthV2 ViT-L/14", batch_per_gpu=4, input="3x1024x1536 uint8", net_input="644x952 (3129 tokens)",
+                            baseline_config="configs[4] (long-sequence attention)")),
+}
 
 
 def load_config():
@@ -91,36 +103,113 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def pick_cpu_threads(fn):
+    """Best of {32, 64, 128} torch threads (capped at the core count) for one call of `fn`; returns (threads, seconds)."""
+    best = None
+    ncpu = os.cpu_count() or 1
+    for t in sorted({min(c, ncpu) for c in (32, 64, 128)}):
+        torch.set_num_threads(t)
+        t0 = time.perf_counter()
+        fn()
+        dt = time.perf_counter() - t0
+        if best is None or dt < best[1]:
+            best = (t, dt)
+    torch.set_num_threads(best[0])
+    return best
+
+
+def metric_name(wl):
+    return "images/sec UniDepthV2.infer ViT-L/14 " + ("480x640" if wl == "default" else "1024x1536")
+
+
 def run_reference(args, rank, world):
-    """CPU arm: the oracle port of the reference's infer on the host cores (bounded sample:
-    one image of the workload per step)."""
+    """CPU arm: the oracle port of the reference's infer on the host cores.  Each step is a batch of the workload's
+    own batch size when the whole run fits ~4 minutes, else the largest batch that does (stated in `sample`)."""
     if rank != 0:
         return
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import unidepth_oracle as O
     from fixture import make_state_dict
     cfg = load_config()
-    cores = min(32, os.cpu_count())   # torch CPU ops stop scaling (and regress) beyond a few dozen threads
-    torch.set_num_threads(cores)
+    W = WORKLOADS[args.workload]
     sd = make_state_dict(cfg, 0)
     g = torch.Generator().manual_seed(0)
-    rgb = torch.randint(0, 256, (1, 3, 480, 640), dtype=torch.uint8, generator=g)
-    for _ in range(max(1, min(args.warmup, 2))):
-        O.infer_v2(sd, copy.deepcopy(cfg), rgb)
+    H, Wd = W["hw"]
+    rgb = torch.randint(0, 256, (W["batch"], 3, H, Wd), dtype=torch.uint8, generator=g)
+    O.infer_v2(sd, copy.deepcopy(cfg), rgb[:1])                      # page in
+    cores, t1 = pick_cpu_threads(lambda: O.infer_v2(sd, copy.deepcopy(cfg), rgb[:1]))
     steps = max(1, args.steps)
+    n_warm = max(0, min(args.warmup, 1))
+    budget_s = 240.0
+    b = int(max(1, min(W["batch"], budget_s / (t1 * (steps + n_warm)))))
+    x = rgb[:b]
+    for _ in range(n_warm):
+        O.infer_v2(sd, copy.deepcopy(cfg), x)
     t0 = time.perf_counter()
     for _ in range(steps):
-        O.infer_v2(sd, copy.deepcopy(cfg), rgb)
+        O.infer_v2(sd, copy.deepcopy(cfg), x)
     dt = time.perf_counter() - t0
-    val = steps / dt
+    val = steps * b / dt
+    sample = (f"{steps} steps x batch {b} of the workload's {W['batch']}-image batch, torch fp32, {cores} threads "
+              f"(best of 32/64/128) of {os.cpu_count()} cores")
     line = {
-        "impl": "reference", "metric": "images/sec UniDepthV2.infer ViT-L/14 480x640", "value": val, "unit": "images/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": 1000 * dt / steps,
+        "impl": "reference", "metric": metric_name(args.workload), "value": val, "unit": "images/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": n_warm, "ms_per_step": 1000 * dt / steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": "1 image per step (batch 1) of the 8-image batch"},
-        "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port",
-                         "sample": f"{steps} x batch-1 infer, torch fp32, {cores} threads of {os.cpu_count()} cores"},
+        "config": {"workload": W["desc"], "sample": sample, "same_batch_as_gpu_arm": b == W["batch"]},
+        "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_torch_gpu(args, rank, world):
+    """INFORMATIVE arm (not the product, not the reference arm): the oracle port executed by stock PyTorch on the GPU
+    under fp16 autocast -- cuBLAS / cuDNN / SDPA kernels, i.e. what the reference does on a GPU (unidepthv2.py:239-241).
+    Also reports that path's drift against the fp32 CPU forward (the declared fp16 noise floor)."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import unidepth_oracle as O
+    from fixture import make_state_dict
+    cfg = load_config()
+    W = WORKLOADS[args.workload]
+    dev = torch.device("cuda", 0)
+    sd = make_state_dict(cfg, 0)
+    sd_dev = {k: v.to(dev) for k, v in sd.items()}
+    g = torch.Generator().manual_seed(0)
+    H, Wd = W["hw"]
+    rgb = torch.randint(0, 256, (W["batch"], 3, H, Wd), dtype=torch.uint8, generator=g)
+    rgb_dev = rgb.to(dev)
+
+    def step():
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+            return O.infer_v2(sd_dev, copy.deepcopy(cfg), rgb_dev)
+
+    for _ in range(max(3, args.warmup)):
+        out = step()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(args.steps):
+        out = step()
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e)
+    torch.set_num_threads(min(64, os.cpu_count()))
+    ref = O.infer_v2(sd, copy.deepcopy(cfg), rgb[:1])
+    d, dr = out["depth"][:1].float().cpu(), ref["depth"]
+    rel = (d - dr).abs() / dr
+    k, kr = out["intrinsics"][:1].float().cpu(), ref["intrinsics"]
+    kerr = {n: ((k[:, i, j] - kr[:, i, j]).abs() / kr[:, i, j].abs()).max().item()
+            for n, (i, j) in dict(fx=(0, 0), fy=(1, 1), cx=(0, 2), cy=(1, 2)).items()}
+    line = {
+        "impl": "torch-gpu", "metric": metric_name(args.workload), "value": args.steps * W["batch"] / (ms / 1000.0),
+        "unit": "images/s", "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "dtype": "fp16 autocast (stock PyTorch kernels)", "data": "synthetic",
+        "config": {"workload": W["desc"], "note": "informative: oracle port through stock PyTorch eager on the GPU, "
+                   "inputs resident in HBM; not the product path and not the reference arm"},
+        "fp16_autocast_drift_vs_fp32_cpu": {"depth_arel": rel.mean().item(), "depth_max_rel": rel.max().item(), "intrinsics_rel": kerr},
     }
     print(json.dumps(line), flush=True)
 
@@ -130,8 +219,9 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=8, help="images per GPU per step")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch-gpu"])
+    ap.add_argument("--workload", default="default", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (default: the workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
@@ -140,7 +230,13 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+    if args.impl == "torch-gpu":
+        run_torch_gpu(args, rank, world)
+        return
     warmup = max(3, args.warmup)
+    W = WORKLOADS[args.workload]
+    FLOPS_PER_IMAGE = W["flops"]
+    H_in, W_in = W["hw"]
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -158,19 +254,18 @@ def main():
     model.load_state_dict(synthetic_state_dict(cfg, 0, device=dev), strict=True)   # same seed on every rank
     model = model.to(dev).eval()
     model.resolution_level = None
-    B = args.batch
+    B = args.batch or W["batch"]
     g = torch.Generator().manual_seed(rank)
-    rgb_host = torch.randint(0, 256, (B, 3, 480, 640), dtype=torch.uint8, generator=g).pin_memory()
+    rgb_host = torch.randint(0, 256, (B, 3, H_in, W_in), dtype=torch.uint8, generator=g).pin_memory()
     rgb_dev = rgb_host.to(dev)
     import warnings
     warnings.simplefilter("ignore")
 
-    # N > 1: one all-gather of the packed outputs per step.  Default: synchronous NCCL gather (an NCCL kernel left
-    # in flight under the next step steals SMs from the persistent GEMM CTAs and costs more than it hides:
-    # 18.6 vs 18.0 ms/step at N=2).  UDB_GATHER=p2p: copy-engine pulls over NVLink peer memory, left in flight
-    # under the next step (depth-1 pipeline); every gather is waited for inside the timed region (flush()).
+    # N > 1: one all-gather of the packed outputs per step (unidepth_b200/parallel.py); `pipelined` gathers are left in
+    # flight under the next step's compute (depth-1 pipeline) and every gather is waited for inside the timed region.
     pending = {"dev": None, "e2e": None}
-    pipelined = os.environ.get("UDB_GATHER", "nccl") == "p2p"
+    from unidepth_b200 import parallel
+    pipelined = world > 1 and parallel.gather_mode() != "nccl"
 
     def step_device():
         out = model.infer(rgb_dev)
@@ -183,42 +278,46 @@ def main():
             out = gather_outputs(out, world)
         return out
 
-    depth_host = torch.empty((B, 1, 480, 640), dtype=torch.float32).pin_memory()
+    depth_host = torch.empty((B, 1, H_in, W_in), dtype=torch.float32).pin_memory()
     k_host = torch.empty((B, 3, 3), dtype=torch.float32).pin_memory()
+    full_host = {}
 
-    def _d2h(out):
+    def _d2h(out, full=False):
         lo = rank * B if world > 1 else 0
         depth_host.copy_(out["depth"][lo:lo + B], non_blocking=True)
         k_host.copy_(out["intrinsics"][lo:lo + B], non_blocking=True)
+        if full:
+            for k, v in out.items():
+                if k in ("depth", "intrinsics"):
+                    continue
+                if k not in full_host:
+                    full_host[k] = torch.empty((B,) + tuple(v.shape[1:]), dtype=torch.float32).pin_memory()
+                full_host[k].copy_(v[lo:lo + B], non_blocking=True)
 
-    def step_e2e():
-        x = rgb_host.to(dev, non_blocking=True)
-        out = model.infer(x)
-        if world > 1 and pipelined:
-            nxt = gather_outputs(out, world, async_op=True)
-            if pending["e2e"] is not None:
-                _d2h(pending["e2e"].wait())
-            pending["e2e"] = nxt
-        else:
-            if world > 1:
-                out = gather_outputs(out, world)
-            _d2h(out)
-        return out
+    def make_e2e(full):
+        def step_e2e():
+            x = rgb_host.to(dev, non_blocking=True)
+            out = model.infer(x)
+            if world > 1 and pipelined:
+                nxt = gather_outputs(out, world, async_op=True)
+                if pending["e2e"] is not None:
+                    _d2h(pending["e2e"].wait(), full)
+                pending["e2e"] = nxt
+            else:
+                if world > 1:
+                    out = gather_outputs(out, world)
+                _d2h(out, full)
+            return out
+        return step_e2e
 
-    def gather_kind():
-        from unidepth_b200 import parallel
-        if parallel._p2p_cache:
-            return ("one packed all-gather of the per-rank outputs per step: copy-engine pulls over NVLink peer memory "
-                    "(torch symmetric memory) on a side stream, left in flight under the next step's compute (depth-1 "
-                    "pipeline); every gather completes inside the timed region")
-        return "one packed NCCL all_gather_into_tensor of the per-rank outputs per step, synchronous, inside the timed region"
+    flush_full = [False]
 
     def flush():
         if pending["dev"] is not None:
             pending["dev"].wait()
             pending["dev"] = None
         if pending["e2e"] is not None:
-            _d2h(pending["e2e"].wait())
+            _d2h(pending["e2e"].wait(), flush_full[0])
             pending["e2e"] = None
 
     def barrier():
@@ -243,26 +342,39 @@ def main():
     l0 = _cabi.launch_count()
     model.use_cuda_graph = False
     step_device()                                   # eager once: counts our launches per forward
+    flush()
     torch.cuda.synchronize()
     launches_per_step = _cabi.launch_count() - l0
     model.use_cuda_graph = True
     for _ in range(warmup):
         step_device()
+    flush()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     ms = timed(step_device, args.steps)
     clocks = sampler.stop() if rank == 0 else None
+    step_e2e = make_e2e(False)
     for _ in range(2):
         step_e2e()
+    flush()
     ms_e2e = timed(step_e2e, args.steps)
+    step_e2e_full = make_e2e(True)
+    flush_full[0] = True
+    for _ in range(2):
+        step_e2e_full()
+    flush()
+    ms_e2e_full = timed(step_e2e_full, args.steps)
+    flush_full[0] = False
+    d2h_full_bytes = (depth_host.numel() + k_host.numel() + sum(t.numel() for t in full_host.values())) * 4
 
-    # per-kernel roofline for the dominant kernel (tcgen05 GEMM): instrumented eager pass
+    # per-kernel rooflines: instrumented eager pass (same kernels scheduled from Python so that each launch can be
+    # bracketed by CUDA events on the launching stream)
     roof = None
     if rank == 0:
         from unidepth_b200 import ops
         model.use_cuda_graph = False
-        model.use_engine = False      # same kernels scheduled from Python so that each launch can be bracketed by events
+        model.use_engine = False
         ops.PROFILE = []
         # keep the GPU busy while the host enqueues the whole eager pass (launches + event records),
         # so the events bracket back-to-back kernel executions, not host launch gaps
@@ -273,20 +385,29 @@ def main():
         model.use_cuda_graph = True
         model.use_engine = True
         agg = {}
-        for name, flops, s, e in prof:
-            a = agg.setdefault(name, [0.0, 0.0, 0])
+        for name, flops, s, e, nbytes in prof:
+            a = agg.setdefault(name, [0.0, 0.0, 0, 0.0])
             a[0] += flops
             a[1] += s.elapsed_time(e)
             a[2] += 1
+            a[3] += nbytes
         sustained, burst, hbm, how = measured_peaks()
         tot_ms = sum(a[1] for a in agg.values())
-        kern = {k: {"launches": a[2], "ms": round(a[1], 3), "tflops": round(a[0] / a[1] / 1e9, 1) if a[1] > 0 else None,
-                    "share": round(a[1] / tot_ms, 3)} for k, a in agg.items()}
-        gm = agg.get("gemm_f16_kernel", [0.0, 1.0, 1])   # ops.py labels both GEMM kernels with this key
+        kern = {}
+        for k, a in agg.items():
+            ent = {"launches": a[2], "ms": round(a[1], 3), "share": round(a[1] / tot_ms, 3)}
+            if a[0] > 0 and a[1] > 0:
+                ent["tflops"] = round(a[0] / a[1] / 1e9, 1)
+                ent["frac_of_sustained_tensor_peak"] = round(a[0] / a[1] / 1e9 / sustained, 3)
+            if a[3] > 0 and a[1] > 0:
+                ent["gbs"] = round(a[3] / a[1] / 1e6, 1)           # algorithmic bytes / event time
+                ent["frac_of_hbm_peak"] = round(a[3] / a[1] / 1e6 / hbm, 3)
+            kern[k] = ent
+        gm = agg.get("gemm_f16_kernel", [0.0, 1.0, 1, 0.0])   # ops.py labels both GEMM kernels with this key
         ach = gm[0] / gm[1] / 1e9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "gemm_traffic.json")
-        if os.path.exists(tpath):
+        if os.path.exists(tpath) and args.workload == "default":
             traffic = json.load(open(tpath)).get("bytes_per_launch_avg")   # ncu capture of the 4 encoder GEMM flavours
         roof = {"bound": "tensor", "kernel": "gemm_f16_kernel / gemm2_f16_kernel (linear + conv3x3 + convT launches)",
                 "achieved": round(ach, 1), "peak": sustained, "unit": "TFLOP/s", "frac": round(ach / sustained, 4),
@@ -295,42 +416,57 @@ def main():
                 "flops_per_launch_avg": round(gm[0] / max(gm[2], 1) / 1e9, 2),
                 "step_tflops": round(B * FLOPS_PER_IMAGE / (ms / args.steps) / 1e9, 1),
                 "step_frac": round(B * FLOPS_PER_IMAGE / (ms / args.steps) / 1e9 / sustained, 4),
-                "kernels": kern}
+                "hbm_peak_gbs": hbm, "kernels": kern}
+        at = agg.get("attn_fwd_kernel")
+        if at:
+            roof["attention"] = {"bound": "tensor", "kernel": "attn_fwd_kernel (encoder MHSA + decoder cross-attention)",
+                                 "achieved": round(at[0] / at[1] / 1e9, 1), "peak": sustained, "unit": "TFLOP/s",
+                                 "frac": round(at[0] / at[1] / 1e9 / sustained, 4), "launches": at[2],
+                                 "avg_launch_us": round(1000 * at[1] / at[2], 2)}
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import unidepth_oracle as O
-        cores = min(32, os.cpu_count())
-        torch.set_num_threads(cores)
         sd_cpu = {k: v.detach().cpu() for k, v in model.state_dict().items()}
         one = rgb_host[:1].clone()
         O.infer_v2(sd_cpu, copy.deepcopy(cfg), one)
-        n = 3
+        cores, _ = pick_cpu_threads(lambda: O.infer_v2(sd_cpu, copy.deepcopy(cfg), one))
+        n = 3 if args.workload == "default" else 1
         t0 = time.perf_counter()
         for _ in range(n):
             ref = O.infer_v2(sd_cpu, copy.deepcopy(cfg), one)
         dt = time.perf_counter() - t0
         got = model.infer(rgb_dev[:1])
         d, dr = got["depth"].cpu(), ref["depth"]
-        arel = ((d - dr).abs() / dr).mean().item()
+        rel = (d - dr).abs() / dr
+        k, kr = got["intrinsics"].cpu(), ref["intrinsics"]
+        kerr = {nm: ((k[:, i, j] - kr[:, i, j]).abs() / kr[:, i, j].abs()).max().item()
+                for nm, (i, j) in dict(fx=(0, 0), fy=(1, 1), cx=(0, 2), cy=(1, 2)).items()}
         cpu_base = {"value": n / dt, "unit": "images/s", "cores": cores, "kind": "port",
-                    "sample": f"{n} x batch-1 infer of the same weights/input (torch fp32 oracle, {cores} threads of {os.cpu_count()} cores)",
-                    "depth_arel_vs_cpu": arel}
+                    "sample": f"{n} x batch-1 infer of the same weights/input (torch fp32 oracle, {cores} threads "
+                              f"(best of 32/64/128) of {os.cpu_count()} cores)",
+                    "depth_arel_vs_cpu": rel.mean().item(), "depth_max_rel_vs_cpu": rel.max().item(),
+                    "intrinsics_rel_vs_cpu": kerr}
 
     if rank == 0:
         total_images = B * world * args.steps
         line = {
-            "metric": "images/sec UniDepthV2.infer ViT-L/14 480x640", "value": total_images / (ms / 1000.0),
+            "metric": metric_name(args.workload), "value": total_images / (ms / 1000.0),
             "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f16 operands, f32 accumulate/residual", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "global_batch": B * world, "parallelism": f"dp{world}",
+            "config": {"workload": W["desc"], "global_batch": B * world, "parallelism": f"dp{world}",
                        "l2": "per-step working set (weights 0.7 GB + activations > 4 GB) exceeds the 126 MB L2",
                        "cuda_graph": True, "engine": "udb_infer_v2 (one C call per infer)",
-                       **({"collective": gather_kind()} if world > 1 else {})},
+                       **({"collective": parallel.gather_description()} if world > 1 else {})},
             "e2e": {"value": total_images / (ms_e2e / 1000.0), "unit": "images/s",
-                    "h2d_bytes_per_step": rgb_host.numel(), "d2h_bytes_per_step": depth_host.numel() * 4 + k_host.numel() * 4},
+                    "h2d_bytes_per_step": rgb_host.numel(), "d2h_bytes_per_step": depth_host.numel() * 4 + k_host.numel() * 4,
+                    "d2h": "depth + intrinsics of this rank's images (the reference returns device tensors; these two are "
+                           "what a caller reads back); e2e_full copies the whole output dict"},
+            "e2e_full": {"value": total_images / (ms_e2e_full / 1000.0), "unit": "images/s",
+                         "h2d_bytes_per_step": rgb_host.numel(), "d2h_bytes_per_step": d2h_full_bytes,
+                         "d2h": "all seven output tensors of this rank's images"},
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_base,
         }

@@ -26,6 +26,16 @@ CASES = [
     ("vits_pad_96x288_rl3", "config_v2_vits14.json", 1, (2, 96, 288), 3),
     ("vitb_112x160", "config_v2_vitb14.json", 2, (1, 112, 160), None),
 ]
+# The benchmark configuration itself (BASELINE.json configs[1]: ViT-L/14, 3x480x640), full depth, one image.
+# Takes a few minutes on CPU, so it is generated on request:  python oracle/make_golden.py vitl
+# Stored: depth and intrinsics in full; the other maps every 4th pixel; depth_features every 8th channel.
+# `python oracle/make_golden.py vitl` also writes BASELINE configs[4]'s shape (3x1024x1536 -> 644x952, 3129 tokens) at full
+# depth: depth every 2nd pixel, the other maps every 8th.
+BIG_CASES = [
+    # name, config, seed, (B,H,W), resolution_level, (depth stride, spatial stride, depth_features channel stride)
+    ("vitl_480x640", "config_v2_vitl14.json", 0, (1, 480, 640), None, (1, 4, 8)),
+    ("vitl_1024x1536", "config_v2_vitl14.json", 3, (1, 1024, 1536), None, (2, 8, 16)),
+]
 
 
 def seeded_rgb(shape, seed):
@@ -39,7 +49,12 @@ def main():
     from unidepth.models import UniDepthV2
     out_dir = os.path.join(HERE, "..", "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
-    for name, cfg_name, seed, shape, level in CASES:
+    big = len(sys.argv) > 1 and sys.argv[1] == "vitl"
+    only = sys.argv[2] if len(sys.argv) > 2 else None
+    for name, cfg_name, seed, shape, level, *rest in (BIG_CASES if big else CASES):
+        if only and name != only:
+            continue
+        sd_, ss_, sc_ = rest[0] if rest else (1, 1, 4)
         cfg = json.load(open(os.path.join(REF, "configs", cfg_name)))
         model = UniDepthV2(copy.deepcopy(cfg)).eval()
         ref_sd = model.state_dict()
@@ -56,12 +71,18 @@ def main():
         out = model.infer(rgb)
         arrays = {k: v.detach().cpu().numpy() for k, v in out.items()}
         # depth_features is large; keep every 4th channel (the restatement is checked on those)
-        arrays["depth_features"] = arrays["depth_features"][:, ::4]
-        meta = dict(config=cfg_name, seed=seed, shape=list(shape), resolution_level=level)
+        arrays["depth_features"] = arrays["depth_features"][:, ::sc_]
+        arrays["depth"] = arrays["depth"][:, :, ::sd_, ::sd_]
+        for k in ("confidence", "radius", "points", "rays"):
+            arrays[k] = arrays[k][:, :, ::ss_, ::ss_]
+        meta = dict(config=cfg_name, seed=seed, shape=list(shape), resolution_level=level,
+                    strides=dict(depth=sd_, spatial=ss_, depth_features=sc_))
         np.savez_compressed(os.path.join(out_dir, name + ".npz"), __meta__=json.dumps(meta), **arrays)
         d = arrays["depth"]
         print(name, "depth range", float(d.min()), float(d.max()), "conf", float(arrays["confidence"].min()),
               float(arrays["confidence"].max()), "K", arrays["intrinsics"][0].tolist())
+    if big:
+        return
     # reference outputs of the validation glue (misc.py:596-690, evaluation_depth.py:93-110) on seeded inputs
     from unidepth.utils.misc import match_gt, match_intrinsics
     from unidepth.utils.evaluation_depth import DICT_METRICS

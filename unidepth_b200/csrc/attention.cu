@@ -459,11 +459,10 @@ extern "C" int udb_attention_f16(const udb_attn_t* a, void* stream) {
 #define UDB_ATTN_SMEM_PAD 0   // experiments: extra dynamic smem to lower the CTAs/SM
 #endif
   constexpr int smem_bytes = 16384 + 2 * AT_KV_STAGES * (AT_BK * 128) + AT_BQ * AT_BK * 2 + 256 + UDB_ATTN_SMEM_PAD;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<uint64_t> attr_mask{0};
+  if (first_on_device(attr_mask)) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) { set_error("attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1; }
-    attr_set = true;
   }
   dim3 grid((a->seq_q + AT_BQ - 1) / AT_BQ, a->heads, a->B);
   cudaError_t e = launch_ex(attn_fwd_kernel<HD>, grid, dim3(AT_THREADS), smem_bytes, reinterpret_cast<cudaStream_t>(stream), 1,

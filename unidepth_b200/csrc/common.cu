@@ -17,12 +17,14 @@ void set_error(const char* fmt, ...) {
 }
 
 int num_sms() {
-  static int n = 0;
+  static std::atomic<int> per_dev[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int n = per_dev[dev & 63].load(std::memory_order_relaxed);
   if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
+    per_dev[dev & 63].store(n, std::memory_order_relaxed);
   }
   return n;
 }

@@ -24,7 +24,16 @@ inline int check_launch(const char* what) {
   return 0;
 }
 
-int num_sms();
+int num_sms();   // of the CURRENT device (cached per device)
+
+// true the first time it is called on the current device for this mask (per-device one-time setup such as
+// cudaFuncSetAttribute: function attributes are per device / context, not per process)
+inline bool first_on_device(std::atomic<uint64_t>& mask) {
+  int d = 0;
+  cudaGetDevice(&d);
+  const uint64_t bit = 1ull << (d & 63);
+  return !(mask.fetch_or(bit) & bit);
+}
 
 // UDB_PDL=0 disables programmatic dependent launch (default on)
 bool pdl_enabled();

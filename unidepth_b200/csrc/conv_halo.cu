@@ -198,11 +198,13 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 
 template <int COUT>
 static int launch_halo(const CUtensorMap& tx, const CUtensorMap& tw, const HaloArgs& a, size_t smem, cudaStream_t st) {
-  static size_t set_for = 0;
-  if (smem > set_for) {
+  static std::atomic<size_t> set_for[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (smem > set_for[dev & 63].load()) {
     cudaError_t e = cudaFuncSetAttribute(conv3x3_halo_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("conv3x3_halo: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e)); return 1; }
-    set_for = smem;
+    set_for[dev & 63].store(smem);
   }
   const int grid = a.num_tiles < num_sms() ? a.num_tiles : num_sms();
   cudaError_t e = launch_ex(conv3x3_halo_kernel<COUT>, dim3(grid), dim3(HC_THREADS), smem, st, 1, tx, tw, a);

@@ -18,9 +18,22 @@
 #include <unordered_map>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: stage ranges for nsys / ncu --nvtx (no-ops when no tool is attached)
+
 #include "common.h"
 
 namespace udb {
+
+// NVTX range per stage of the schedule (host-side: it brackets the enqueue of that stage's kernels)
+struct Stage {
+  bool open = false;
+  void next(const char* name) {
+    if (open) nvtxRangePop();
+    nvtxRangePushA(name);
+    open = true;
+  }
+  ~Stage() { if (open) nvtxRangePop(); }
+};
 
 struct Weight {
   const void* p = nullptr;
@@ -144,6 +157,17 @@ struct Ctx {
     return it->second;
   }
   void done(int r) { if (r && !rc) rc = r; }
+  // registered 2-D operand must have exactly this shape (a mis-packed weight would otherwise be read with the
+  // wrong leading dimension and silently produce garbage)
+  void expect2(const std::string& name, int64_t rows, int64_t cols) {
+    const Weight* w = W(name);
+    if (rc) return;
+    if (w->ndim != 2 || w->shape[0] != rows || w->shape[1] != cols) {
+      set_error("engine: packed tensor '%s' has shape [%lld, %lld] (ndim %d), expected [%lld, %lld]", name.c_str(),
+                (long long)w->shape[0], (long long)w->shape[1], w->ndim, (long long)rows, (long long)cols);
+      rc = 1;
+    }
+  }
 
   // out[row(m), :] = resid + gamma * act(a @ w^T + bias)     (ops.gemm)
   struct G {
@@ -273,6 +297,8 @@ static int run(udb_engine* e, const udb_infer_args_t& a, const udb_geometry_t& g
   const size_t BN = static_cast<size_t>(B) * N, BT = static_cast<size_t>(B) * T;
 
   // ---- a2/a3/a4: pre-process + patch embedding + cls / position rows
+  Stage stage;
+  stage.next("udb:preprocess+patch_embed");
   __half* patches = ar.h(BN * 640);
   if (!c.dry) {
     udb_preprocess_t p;
@@ -292,6 +318,7 @@ static int run(udb_engine* e, const udb_infer_args_t& a, const udb_geometry_t& g
   }
 
   // ---- a5-a8: transformer blocks, taps through the final norm
+  stage.next("udb:encoder_blocks");
   __half* feats[4];
   float* clss[4];
   for (int l = 0; l < 4; ++l) { feats[l] = ar.h(BN * D); clss[l] = ar.f(static_cast<size_t>(B) * D); }
@@ -324,6 +351,7 @@ static int run(udb_engine* e, const udb_infer_args_t& a, const udb_geometry_t& g
     ar.release(m);
   }
 
+  stage.next("udb:adapters+camera_head");
   // ---- a9: adapters (features f32 = the prompt blocks' residual; cls tokens -> camera tokens)
   float* Fl[4];
   for (int l = 0; l < 4; ++l) {
@@ -362,6 +390,7 @@ static int run(udb_engine* e, const udb_infer_args_t& a, const udb_geometry_t& g
   if (!c.dry && !c.rc)
     c.done(udb_camera_intrinsics(x4, B, nh, nw, static_cast<float>(g.factor), g.pad_l, g.pad_t, intr4, k_net, a.intrinsics, st));
 
+  stage.next("udb:ray_embedding+prompt_blocks");
   // ---- a11/a12: rays (predicted K, or the caller's pinhole K) -> Fourier embedding on the patch grid
   const float* ray_intr = intr4;
   if (a.camera_k && !a.camera_rays) {
@@ -410,6 +439,7 @@ static int run(udb_engine* e, const udb_infer_args_t& a, const udb_geometry_t& g
     ar.release(m);
   }
 
+  stage.next("udb:upsampling_stages");
   // ---- a14/a15: latents + up-sampling stages (NHWC, fp32 residual + fp16 activated copy)
   { Ctx::G q{cond[0], c.H("lat_w"), static_cast<int>(BN), hid, hid}; q.bias = c.F("lat_b"); q.out = a.depth_features;
     q.out_f32 = 1; c.gemm(q); }
@@ -434,6 +464,8 @@ static int run(udb_engine* e, const udb_infer_args_t& a, const udb_geometry_t& g
                      act, 1, 0);
     for (int j = 0; j < cf.dec_depths[i]; ++j) {
       const std::string r = idx2("ups.%d.rcu.%d.", i, j);
+      c.expect2(r + "w1", cout, 9 * cout);     // 3x3 only (layers/upsample.py:137-180 with kernel_size=3)
+      c.expect2(r + "w2", cout, 9 * cout);
       c.conv3x3(act, B, oh, ow, cout, c.H(r + "w1"), cout, c.F(r + "b1"), UDB_ACT_LEAKY, nullptr, nullptr, 0, tmp, 0,
                 nullptr, 1);
       c.conv3x3(tmp, B, oh, ow, cout, c.H(r + "w2"), cout, c.F(r + "b2"), UDB_ACT_NONE, c.F(r + "gamma"), lat, 1, lat, 1,
@@ -452,6 +484,7 @@ static int run(udb_engine* e, const udb_infer_args_t& a, const udb_geometry_t& g
   const int hh = cur_h, hw = cur_w;
   const size_t hpx = static_cast<size_t>(B) * hh * hw;
 
+  stage.next("udb:depth+confidence_heads");
   // ---- a16/a17: depth + confidence heads (shared normalisation, merged LN->Linear GEMM written
   //      straight into the reflect-padded buffer the 3x3 "lr" convs read)
   __half* xhat = ar.h(hpx * c_hr);
@@ -482,6 +515,7 @@ static int run(udb_engine* e, const udb_infer_args_t& a, const udb_geometry_t& g
     ar.release(m);
   }
 
+  stage.next("udb:postprocess");
   // ---- a18: output assembly at the original resolution
   if (!c.dry && !c.rc) {
     udb_postprocess_t p;

@@ -416,15 +416,14 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 template <int BN>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<uint64_t> attr_mask{0};
+  if (first_on_device(attr_mask)) {
     cudaError_t e = cudaFuncSetAttribute(gemm_f16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
     if (e != cudaSuccess) {
       set_error("gemm: cudaFuncSetAttribute(%d B smem): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
       return 1;
     }
-    attr_set = true;
   }
   const int tiles = a.tiles_m * a.tiles_n;
   const int grid = tiles < num_sms() ? tiles : num_sms();
@@ -615,15 +614,14 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 template <int BN>
 static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, cudaStream_t st) {
   using Cfg = Gemm2Cfg<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<uint64_t> attr_mask{0};
+  if (first_on_device(attr_mask)) {
     cudaError_t e = cudaFuncSetAttribute(gemm2_f16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
     if (e != cudaSuccess) {
       set_error("gemm2: cudaFuncSetAttribute(%d B smem): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
       return 1;
     }
-    attr_set = true;
   }
   const int tiles = ((a.tiles_m + 1) / 2) * a.tiles_n;
   const int max_pairs = num_sms() / 2;

@@ -19,15 +19,20 @@ f16, f32 = torch.float16, torch.float32
 PROFILE = None
 
 
-def _launch(kernel: str, flops: float, fn):
+def _launch(kernel: str, flops: float, fn, nbytes: float = 0.0):
+    """Run one C-ABI launch; with PROFILE set, bracket it with CUDA events and record the algorithmic flops / bytes."""
     if PROFILE is None:
         return fn()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
     rc = fn()
     e.record()
-    PROFILE.append((kernel, flops, s, e))
+    PROFILE.append((kernel, flops, s, e, nbytes))
     return rc
+
+
+def _nb(*tensors):
+    return float(sum(t.numel() * t.element_size() for t in tensors if t is not None))
 
 
 def _stream():
@@ -202,7 +207,8 @@ def layernorm(x, weight, bias, eps, *, out=None, out_dtype=f16, rows=None, rows_
     p.rows_per_group, p.group_stride, p.row_offset = rows_per_group, group_stride, row_offset
     p.eps = eps
     p.dim_valid = dim_valid
-    cabi.check(_launch("layernorm_kernel", 0.0, lambda: cabi.lib().udb_layernorm(C.byref(p), _stream())), "udb_layernorm")
+    nbytes = float(n_rows * dim * (x2.element_size() + out.element_size()))
+    cabi.check(_launch("layernorm_kernel", 0.0, lambda: cabi.lib().udb_layernorm(C.byref(p), _stream()), nbytes), "udb_layernorm")
     return out
 
 
@@ -215,7 +221,8 @@ def preprocess_patchify(rgb, paddings, net_hw, patches, normalize=True):
     p.pad_l, p.pad_r, p.pad_t, p.pad_b = paddings
     p.net_h, p.net_w = net_hw
     p.patches, p.ldp = _ptr(patches), patches.stride(0)
-    cabi.check(_launch("preprocess_patchify_kernel", 0.0, lambda: cabi.lib().udb_preprocess_patchify(C.byref(p), _stream())), "udb_preprocess_patchify")
+    cabi.check(_launch("preprocess_patchify_kernel", 0.0, lambda: cabi.lib().udb_preprocess_patchify(C.byref(p), _stream()),
+                       _nb(rgb, patches)), "udb_preprocess_patchify")
     return patches
 
 
@@ -269,14 +276,15 @@ def ray_embed(intr4, scales, B, net_hw, grid_hw, out_dtype=f32, rays_in=None):
     p.intr4, p.rays_in, p.scales = _ptr(intr4), _ptr(rays_in), _ptr(scales)
     p.B, p.net_h, p.net_w, p.gh, p.gw, p.bands = B, net_hw[0], net_hw[1], grid_hw[0], grid_hw[1], bands
     p.out, p.out_f32 = _ptr(out), _is32(out)
-    cabi.check(_launch("ray_embed_kernel", 0.0, lambda: cabi.lib().udb_ray_embed(C.byref(p), _stream())), "udb_ray_embed")
+    cabi.check(_launch("ray_embed_kernel", 0.0, lambda: cabi.lib().udb_ray_embed(C.byref(p), _stream()), _nb(out, rays_in)), "udb_ray_embed")
     return out
 
 
 def upsample2x(x):
     B, H, W, Cc = x.shape
     out = torch.empty((B, 2 * H, 2 * W, Cc), device=x.device, dtype=f16)
-    cabi.check(_launch("upsample2x_kernel", 0.0, lambda: cabi.lib().udb_upsample2x_nhwc_f16(_ptr(x), _ptr(out), B, H, W, Cc, _stream())),
+    cabi.check(_launch("upsample2x_kernel", 0.0, lambda: cabi.lib().udb_upsample2x_nhwc_f16(_ptr(x), _ptr(out), B, H, W, Cc, _stream()),
+                       _nb(x, out)),
                "udb_upsample2x_nhwc_f16")
     return out
 
@@ -285,7 +293,8 @@ def resize_ac_pad(x, oh, ow, pad):
     B, H, W, Cc = x.shape
     out = torch.empty((B, oh + 2 * pad, ow + 2 * pad, Cc), device=x.device, dtype=f16)
     cabi.check(_launch("resize_ac_pad_kernel", 0.0,
-                       lambda: cabi.lib().udb_resize_ac_pad_nhwc_f16(_ptr(x), _ptr(out), B, H, W, Cc, oh, ow, pad, _stream())),
+                       lambda: cabi.lib().udb_resize_ac_pad_nhwc_f16(_ptr(x), _ptr(out), B, H, W, Cc, oh, ow, pad, _stream()),
+                       _nb(x, out)),
                "udb_resize_ac_pad_nhwc_f16")
     return out
 
@@ -321,5 +330,6 @@ def postprocess(radius, confidence, intr4, B, net_hw, padded_hw, pad_l, pad_t, o
     p.padded_h, p.padded_w, p.pad_l, p.pad_t, p.H, p.W = padded_hw[0], padded_hw[1], pad_l, pad_t, H, W
     p.out_confidence, p.out_radius, p.out_depth = _ptr(outs["confidence"]), _ptr(outs["radius"]), _ptr(outs["depth"])
     p.out_points, p.out_rays = _ptr(outs["points"]), _ptr(outs["rays"])
-    cabi.check(_launch("postprocess_kernel", 0.0, lambda: cabi.lib().udb_postprocess(C.byref(p), _stream())), "udb_postprocess")
+    cabi.check(_launch("postprocess_kernel", 0.0, lambda: cabi.lib().udb_postprocess(C.byref(p), _stream()),
+                       _nb(radius, confidence, rays_in, *outs.values())), "udb_postprocess")
     return outs

@@ -112,6 +112,20 @@ class P2PGather:
         return PendingOutputs(None, full, None, shapes, event=ev)
 
 
+def gather_mode() -> str:
+    """'nccl' (synchronous all_gather_into_tensor) or 'p2p' (copy-engine pulls over NVLink peer memory)."""
+    import os
+    return os.environ.get("UDB_GATHER", "nccl")
+
+
+def gather_description() -> str:
+    if _p2p_cache:
+        return ("one packed all-gather of the per-rank outputs per step: copy-engine pulls over NVLink peer memory on a side "
+                "stream, left in flight under the next step's compute (depth-1 pipeline); every gather completes inside the "
+                "timed region")
+    return "one packed NCCL all_gather_into_tensor of the per-rank outputs per step, synchronous, inside the timed region"
+
+
 _p2p_cache: Dict[tuple, "P2PGather"] = {}
 _p2p_failed = [None]
 
@@ -123,8 +137,7 @@ def p2p_gather_for(out: Dict[str, torch.Tensor], group=None):
     NCCL gather), but in tests/test_multigpu_gpu.py's sequence (gather, then capture of a LARGER CUDA
     graph, then replay of the older graph) the older graph's replays return wrong values with this path
     enabled and not with NCCL; not understood yet, so it is off by default."""
-    import os
-    if os.environ.get("UDB_GATHER", "nccl") != "p2p" or _p2p_failed[0] is not None or not out["depth"].is_cuda:
+    if gather_mode() != "p2p" or _p2p_failed[0] is not None or not out["depth"].is_cuda:
         return None
     b = out["depth"].shape[0]
     feat = sum(out[k][0].numel() for k in _KEYS)
@@ -181,4 +194,30 @@ def infer_sharded(model, rgb: torch.Tensor, async_op: bool = False, **kw):
     assert n >= world, "need at least one image per rank"
     lo, hi = shard_bounds(n, rank, world)
     counts = [shard_bounds(n, r, world)[1] - shard_bounds(n, r, world)[0] for r in range(world)]
+    kw = dict(kw)
+    cam = kw.get("camera", None)
+    if cam is not None:
+        kw["camera"] = shard_camera(cam, n, lo, hi)
     return gather_outputs(model.infer(rgb[lo:hi], **kw), world, async_op=async_op, counts=counts)
+
+
+def shard_camera(camera, n: int, lo: int, hi: int):
+    """Slice a per-image `camera=` argument the way `rgb` is sliced: a [N,3,3] K tensor or a batched camera
+    object (anything indexable whose length is the global batch) gives rank r its images' cameras; a single
+    K / camera is shared by every image and passes through."""
+    if isinstance(camera, torch.Tensor):
+        k = camera.reshape(-1, 3, 3)
+        if k.shape[0] == 1:
+            return camera
+        if k.shape[0] != n:
+            raise ValueError(f"camera holds {k.shape[0]} intrinsics for a global batch of {n} images")
+        return k[lo:hi]
+    try:
+        length = len(camera)
+    except TypeError:
+        return camera
+    if length == 1:
+        return camera
+    if length != n:
+        raise ValueError(f"camera holds {length} cameras for a global batch of {n} images")
+    return camera[lo:hi]

@@ -22,6 +22,7 @@ import json
 import math
 import os
 import warnings
+from collections import OrderedDict
 from typing import Dict, Optional
 
 import torch
@@ -77,11 +78,19 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
         self.use_engine = True        # False: schedule the same kernels from Python (ops.*; debugging taps / per-kernel timing)
         self._engine = None
         self._engine_key = None
-        self._workspaces: Dict[tuple, torch.Tensor] = {}
+        # Bounded caches (LRU): the reference handles arbitrary shapes in constant memory, so a stream of
+        # differently-sized images must not grow device memory without limit.  A captured graph keeps its own
+        # reference to the workspace it was captured with, so evicting a workspace never frees memory a live
+        # graph still replays into.
+        self.max_cached_graphs = 8
+        self.max_cached_workspaces = 8
+        self.max_engine_shapes = 64       # per-(gh,gw) tables live inside the engine; beyond this everything is rebuilt
+        self._workspaces: "OrderedDict[tuple, torch.Tensor]" = OrderedDict()
         self._packed: Optional[dict] = None
         self._packed_key = None
-        self._graphs: Dict[tuple, dict] = {}
+        self._graphs: "OrderedDict[tuple, dict]" = OrderedDict()
         self._posembed_cache: Dict[tuple, torch.Tensor] = {}
+        self._engine_shapes: set = set()
 
     # ------------------------------------------------------------------ reference-compatible API
     @property
@@ -122,6 +131,10 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
             raise RuntimeError("unidepth_b200.UniDepthV2.infer needs the model on a CUDA device "
                                "(model.to('cuda')); there is no CPU fallback")
         s = self.spec
+        if s.kernel_size != 3:
+            raise NotImplementedError(f"pixel_decoder.kernel_size={s.kernel_size}: the residual conv units run as 3x3 "
+                                      "convolutions (every shipped UniDepthV2 config sets 3)")
+        torch.cuda.set_device(dev)      # callers hold `with torch.cuda.device(self.device)`
         sd = {k: v.detach() for k, v in self.state_dict().items()}
         h16 = lambda t: t.to(f16).contiguous()
         c32 = lambda t: t.to(f32).contiguous()
@@ -272,16 +285,22 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
         P["ln_zeros"] = torch.zeros(c_hr, device=dev, dtype=f32)
         self._packed = P
         self._packed_key = self._fingerprint()
-        self._graphs.clear()
-        self._posembed_cache.clear()
         self._drop_engine()
 
     # ------------------------------------------------------------------ C engine (udb_create / udb_infer_v2)
     def _drop_engine(self):
+        """Destroy the engine AND everything that holds raw pointers into it: captured graphs replay kernels whose
+        arguments point at the engine's per-shape tables and at the workspaces, so they go first."""
+        self._graphs.clear()
+        self._posembed_cache.clear()
         if self._engine is not None:
+            dev = getattr(self, "_engine_device", None)
+            if dev is not None:
+                torch.cuda.synchronize(dev)       # nothing may still be running out of the tables we free
             cabi.lib().udb_destroy(self._engine)
         self._engine, self._engine_key = None, None
         self._workspaces.clear()
+        self._engine_shapes = set()
 
     def __del__(self):
         try:
@@ -360,6 +379,7 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
         for name, v in scalars.items():
             cabi.check(cabi.lib().udb_set_scalar(handle, name.encode(), float(v)), f"udb_set_scalar({name})")
         self._engine, self._engine_key = handle, key
+        self._engine_device = self.device
         self._engine_tensors = tensors          # the engine borrows these pointers
         return handle
 
@@ -381,6 +401,12 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
                 raise RuntimeError(f"udb_workspace_bytes failed: {lib.udb_last_error().decode()}")
             ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
             self._workspaces[wkey] = ws
+            self._engine_shapes.add((g.gh, g.gw))
+            while len(self._workspaces) > self.max_cached_workspaces:
+                self._workspaces.popitem(last=False)
+        else:
+            self._workspaces.move_to_end(wkey)
+        self._last_ws = ws
         hid = self.spec.hidden
         E = lambda *shape: torch.empty(shape, device=dev, dtype=f32)
         out = {"confidence": E(B, 1, H, W), "intrinsics": E(B, 3, 3), "radius": E(B, 1, H, W), "depth": E(B, 1, H, W),
@@ -595,6 +621,8 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
         assert camera.shape[-1] == 3 and camera.shape[-2] == 3, \
             "camera tensor should be of shape (..., 3, 3): assume pinhole"
         K = camera.to(dev, f32).reshape(-1, 3, 3)
+        if K.shape[0] not in (1, B):
+            raise ValueError(f"camera holds {K.shape[0]} intrinsics for a batch of {B} images (need 1 or {B})")
         if K.shape[0] == 1 and B > 1:
             K = K.expand(B, 3, 3)
         if float(K[:, 0, 1].abs().max()) != 0.0:
@@ -627,6 +655,8 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
         if rays.ndim == 3:
             rays = rays.unsqueeze(0)
         assert rays.shape[-3:] == (3, nh, nw), f"camera.get_rays returned {tuple(rays.shape)}"
+        if rays.shape[0] not in (1, B):
+            raise ValueError(f"camera.get_rays returned {rays.shape[0]} ray maps for a batch of {B} images")
         if rays.shape[0] == 1 and B > 1:
             rays = rays.expand(B, 3, nh, nw)
         return rays.to(dev, f32).permute(0, 2, 3, 1).reshape(B, nh * nw, 3).contiguous()
@@ -711,7 +741,13 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
         return rgb.contiguous()
 
     def _run(self, rgb, geom, level, normalize, camera, key_extra, rays_in=None):
-        """Common tail of infer / network_forward: camera handling, engine or Python schedule, CUDA graph cache."""
+        """Common tail of infer / network_forward: camera handling, engine or Python schedule, CUDA graph cache.
+        Everything runs with the model's device current (streams, cudaMalloc of the engine tables, the per-device
+        kernel attributes on the C side), so a model on cuda:1 works while cuda:0 is the process default."""
+        with torch.cuda.device(self.device):
+            return self._run_on_device(rgb, geom, level, normalize, camera, key_extra, rays_in)
+
+    def _run_on_device(self, rgb, geom, level, normalize, camera, key_extra, rays_in=None):
         B, _, H, W = rgb.shape
         dev = rgb.device
         nh, nw = geom["net_hw"]
@@ -734,6 +770,8 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
             camera_k = camera_k.contiguous()
 
         self._weights()
+        if len(self._engine_shapes) > self.max_engine_shapes:
+            self._drop_engine()       # too many distinct grids seen: rebuild (frees the engine's per-shape tables)
 
         def run(inp):
             if self.use_engine:
@@ -757,8 +795,12 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 static_out = run(static_in)
-            entry = dict(graph=graph, inp=static_in, out=static_out)
+            entry = dict(graph=graph, inp=static_in, out=static_out, ws=getattr(self, "_last_ws", None))
             self._graphs[key] = entry
+            while len(self._graphs) > self.max_cached_graphs:
+                self._graphs.popitem(last=False)
+        else:
+            self._graphs.move_to_end(key)
         entry["inp"].copy_(rgb, non_blocking=True)
         entry["graph"].replay()
         return {k: v.clone() for k, v in entry["out"].items()}

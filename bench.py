@@ -183,7 +183,8 @@ def run_torch_gpu(args, rank, world):
     rgb_dev = rgb.to(dev)
 
     def step():
-        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        # torch.device(dev): the oracle's constant tensors (mean/std, pixel grids) are created on the GPU too
+        with torch.no_grad(), torch.device(dev), torch.autocast("cuda", dtype=torch.float16):
             return O.infer_v2(sd_dev, copy.deepcopy(cfg), rgb_dev)
 
     for _ in range(max(3, args.warmup)):

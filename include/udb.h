@@ -86,6 +86,14 @@ typedef struct udb_gemm_t {
    * -8, 8) + head_add) written as f32 to out[b*H*W + y*W + x]. */
   const float* head_w;
   float head_b, head_add;
+  /* Split-f16 ("precise") operands, UDB_A_MATRIX only.  a_split_k = K1 > 0: every A row holds [hi(K1) | lo(K1)] with
+   * x = hi + lo to ~22 bits (lo = f16(x - f32(hi))), lda >= 2*K1; W is packed [N, 3*K1] = [W_hi | W_hi | W_lo];
+   * K must be 3*K1.  The k-blocks of the third segment re-read A's hi half, so the same MMAs accumulate
+   * hi.W_hi + lo.W_hi + hi.W_lo in f32 -- the f16 product error (2^-11 per operand) drops to ~2^-21.
+   * out_split > 0 (f16 `out`): also store lo = f16(v - f32(hi)) at column n + out_split, i.e. the output is itself a
+   * split operand for the next GEMM. */
+  int32_t a_split_k;
+  int32_t out_split;
 } udb_gemm_t;
 
 int udb_gemm_f16(const udb_gemm_t* g, void* stream);
@@ -127,6 +135,11 @@ typedef struct udb_attn_t {
   int32_t ldq, ldk, ldv, ldo;
   int32_t q_col0, k_col0, v_col0, o_col0;
   float scale; /* 1/sqrt(head_dim) */
+  /* Split-f16 ("precise") mode: when split != 0 the lo halves of q / k / v / out live lo_off_* elements to the right of
+   * the hi halves (value = hi + lo) and the attention runs in an fp32 CUDA-core kernel (exact exp, f32 products):
+   * a debugging / parity mode, ~50x slower than the tcgen05 kernel. */
+  int32_t split;
+  int32_t lo_off_q, lo_off_k, lo_off_v, lo_off_o;
 } udb_attn_t;
 
 int udb_attention_f16(const udb_attn_t* a, void* stream);
@@ -151,6 +164,7 @@ typedef struct udb_layernorm_t {
   float eps;
   int32_t dim_valid; /* 0 = dim.  f16->f16 rows of 64/128/256 only: statistics over the first dim_valid
                         columns (zero-padded channel rows, e.g. ViT-B's 96-channel map stored as 128) */
+  int32_t out_split; /* > 0 (f32 -> f16 rows only): also store lo = f16(y - f32(hi)) at column + out_split */
 } udb_layernorm_t;
 
 int udb_layernorm(const udb_layernorm_t* p, void* stream);
@@ -170,6 +184,7 @@ typedef struct udb_preprocess_t {
   int32_t net_h, net_w;
   void* patches;
   int32_t ldp;
+  int32_t split; /* 1: rows hold [hi | lo] halves of ldp/2 columns each (split-f16 precise mode) */
 } udb_preprocess_t;
 
 int udb_preprocess_patchify(const udb_preprocess_t* p, void* stream);

@@ -188,3 +188,57 @@ def test_conv3x3_halo(C, N, H, W):
         head = ops.conv3x3_halo(xpad, wp, bias=bias, act=ops.ACT_LEAKY, head_w=hw, head_b=0.1, head_add=2.0)
         hr = torch.exp((F.leaky_relu(ref, 0.01) * hw.view(1, -1, 1, 1)).sum(1).add(0.1).clip(-8, 8) + 2.0)
         _close(head, hr, 3e-5, f"halo conv head {C}->{N} {H}x{W}")
+
+
+def test_split_f16_gemm_layernorm_attention():
+    """Split-f16 precise mode (udb_gemm_t.a_split_k / out_split, udb_layernorm_t.out_split, udb_attn_t.split): operands
+    as hi + lo f16 pairs through the SAME tcgen05 GEMM, attention in fp32.  Against float64 the error must drop from
+    f16's ~3e-4 to ~1e-6."""
+    import torch
+    from unidepth_b200 import ops
+    dev = "cuda:0"
+    g = torch.Generator(device="cpu").manual_seed(7)
+    M, K, N = 777, 1024, 384
+
+    def split(t):
+        hi = t.half()
+        return hi, (t - hi.float()).half()
+
+    a = torch.randn(M, K, generator=g).to(dev)
+    w = (torch.randn(N, K, generator=g) * 0.05).to(dev)
+    bias = torch.randn(N, generator=g).to(dev)
+    ah, al = split(a)
+    wh, wl = split(w)
+    a2 = torch.cat([ah, al], 1).contiguous()
+    w3 = torch.cat([wh, wh, wl], 1).contiguous()
+    ref = (a.double() @ w.double().T + bias.double())
+    out32 = ops.gemm(a2, w3, bias=bias, a_split_k=K, out_dtype=torch.float32)
+    err = ((out32.double() - ref).abs().max() / ref.abs().max()).item()
+    plain = ops.gemm(ah, wh, bias=bias, out_dtype=torch.float32)
+    err16 = ((plain.double() - ref).abs().max() / ref.abs().max()).item()
+    print(f"split GEMM max err / max|ref|: {err:.2e} (plain f16 operands: {err16:.2e})")
+    assert err < 3e-6 and err16 > 20 * err
+    # split output: hi + lo reproduces the f32 result to ~2^-21
+    o2 = ops.gemm(a2, w3, bias=bias, a_split_k=K, out_split=True)
+    rec = o2[:, :N].float() + o2[:, N:].float()
+    assert ((rec - out32).abs().max() / out32.abs().max()).item() < 2e-6
+    # LayerNorm with a split output
+    x = torch.randn(300, 1024, generator=g).to(dev) * 3 + 1
+    lw, lb = torch.randn(1024, generator=g).to(dev), torch.randn(1024, generator=g).to(dev)
+    y2 = ops.layernorm(x, lw, lb, 1e-6, out_split=True)
+    yref = torch.nn.functional.layer_norm(x.double(), (1024,), lw.double(), lb.double(), 1e-6)
+    rec = y2[:, :1024].float() + y2[:, 1024:].float()
+    assert ((rec.double() - yref).abs().max() / yref.abs().max()).item() < 3e-6
+    # fp32 attention on split operands (ragged lengths: 150 queries, 203 keys, 2 images x 3 heads)
+    B, Hh, Sq, Sk = 2, 3, 150, 203
+    q, k, v = (torch.randn(B * S, Hh * 64, generator=g).to(dev) for S in (Sq, Sk, Sk))
+    pack = lambda t: torch.cat(split(t), 1).contiguous()
+    o = torch.empty(B * Sq, 2 * Hh * 64, device=dev, dtype=torch.float16)
+    ops.attention(pack(q), pack(k), pack(v), o, B=B, heads=Hh, seq_q=Sq, seq_k=Sk, head_dim=64,
+                  lo_off_in=Hh * 64, lo_off_out=Hh * 64)
+    rec = (o[:, :Hh * 64].float() + o[:, Hh * 64:].float()).view(B, Sq, Hh, 64)
+    qd, kd, vd = (t.double().view(B, -1, Hh, 64).transpose(1, 2) for t in (q, k, v))
+    aref = torch.softmax(qd @ kd.transpose(-1, -2) / 8.0, -1) @ vd
+    err = ((rec.double().transpose(1, 2) - aref).abs().max() / aref.abs().max()).item()
+    print(f"split attention max err: {err:.2e}")
+    assert err < 3e-6

@@ -40,7 +40,7 @@ def test_ctypes_structs_match_c_layout():
                "udb_preprocess_t": _cabi.Preprocess, "udb_small_linear_t": _cabi.SmallLinear,
                "udb_ray_embed_t": _cabi.RayEmbed, "udb_postprocess_t": _cabi.Postprocess,
                "udb_config_t": _cabi.Config, "udb_geometry_t": _cabi.Geometry, "udb_infer_args_t": _cabi.InferArgs}
-    last = {"udb_gemm_t": "head_add", "udb_conv_halo_t": "head_out", "udb_attn_t": "scale", "udb_layernorm_t": "dim_valid", "udb_preprocess_t": "ldp",
+    last = {"udb_gemm_t": "out_split", "udb_conv_halo_t": "head_out", "udb_attn_t": "lo_off_o", "udb_layernorm_t": "out_split", "udb_preprocess_t": "split",
             "udb_small_linear_t": "ldr", "udb_ray_embed_t": "out_f32", "udb_postprocess_t": "out_rays",
             "udb_config_t": "pixels_max", "udb_geometry_t": "factor", "udb_infer_args_t": "depth_features"}
     src = '#include <stdio.h>\n#include <stddef.h>\n#include "udb.h"\nint main(){\n'

@@ -212,6 +212,35 @@ def test_vitl_golden_inside_batch8():
     _check(subsample_like_golden(one, meta), ref, "golden_vitl_480x640_in_batch8")
 
 
+def test_split_precision_meets_north_star(shallow):
+    """precision="split": hi/lo split-f16 operands through the same tcgen05 GEMM kernels (three products per GEMM) and
+    fp32 attention in the encoder.  The intrinsics (fp32 camera head on the encoder's cls tokens) then carry no f16
+    operand rounding and meet north_star's 1e-4 with a wide margin; the default mode's residual is therefore rounding,
+    not logic.  Checked on the shallow model against the oracle and on the full ViT-L 480x640 against the output of
+    the unmodified reference."""
+    import numpy as np
+    import unidepth_oracle as O
+    from fixture import make_state_dict
+    from test_oracle_golden import subsample_like_golden
+    cfg, sd = shallow
+    rgb = _rgb((2, 240, 320), 0)
+    torch.set_num_threads(min(32, os.cpu_count()))
+    ref = O.infer_v2(sd, copy.deepcopy(cfg), rgb)
+    m = _model(cfg, sd)
+    m.precision = "split"
+    _check(m.infer(rgb), ref, "split_shallow_b2", tol=NORTH_STAR)
+    m.precision = "f16"                       # switching back repacks and matches the default path again
+    _check(m.infer(rgb), ref, "shallow_b2")
+    z = np.load(os.path.join(ROOT, "tests", "golden", "vitl_480x640.npz"))
+    meta = json.loads(str(z["__meta__"]))
+    cfgL = json.load(open(os.path.join(ROOT, "tests", "golden", meta["config"])))
+    mL = _model(cfgL, make_state_dict(cfgL, meta["seed"]))
+    mL.precision = "split"
+    out = mL.infer(_rgb(meta["shape"], meta["seed"]))
+    refL = {k: torch.from_numpy(z[k]) for k in z.files if k != "__meta__"}
+    _check(subsample_like_golden(dict(out), meta), refL, "split_golden_vitl_480x640", tol=NORTH_STAR)
+
+
 def test_high_res_1024x1536_long_sequence():
     """BASELINE config 5 shape: 3x1024x1536 is resized by infer to 644x952 -> 3129 tokens (long-sequence
     attention, 25 key tiles).  ViT-L widths with a 4-block encoder so the CPU oracle stays fast."""

@@ -29,6 +29,7 @@ class Gemm(C.Structure):
         ("resid_mod", i32), ("resid_row_offset", i32), ("ldr", i64),
         ("ct_k", i32), ("ct_cout", i32), ("ct_h", i32), ("ct_w", i32), ("ct_pad", i32),
         ("head_w", vp), ("head_b", f32), ("head_add", f32),
+        ("a_split_k", i32), ("out_split", i32),
     ]
 
 
@@ -46,6 +47,7 @@ class Attn(C.Structure):
         ("B", i32), ("heads", i32), ("seq_q", i32), ("seq_k", i32), ("head_dim", i32),
         ("ldq", i32), ("ldk", i32), ("ldv", i32), ("ldo", i32),
         ("q_col0", i32), ("k_col0", i32), ("v_col0", i32), ("o_col0", i32), ("scale", f32),
+        ("split", i32), ("lo_off_q", i32), ("lo_off_k", i32), ("lo_off_v", i32), ("lo_off_o", i32),
     ]
 
 
@@ -54,6 +56,7 @@ class LayerNorm(C.Structure):
         ("inp", vp), ("in_f32", i32), ("out", vp), ("out_f32", i32), ("weight", vp), ("bias", vp),
         ("rows", i32), ("dim", i32), ("ld_in", i64), ("ld_out", i64),
         ("rows_per_group", i32), ("group_stride", i32), ("row_offset", i32), ("eps", f32), ("dim_valid", i32),
+        ("out_split", i32),
     ]
 
 
@@ -61,7 +64,7 @@ class Preprocess(C.Structure):
     _fields_ = [
         ("rgb", vp), ("rgb_is_u8", i32), ("normalize", i32), ("B", i32), ("H", i32), ("W", i32),
         ("pad_l", i32), ("pad_r", i32), ("pad_t", i32), ("pad_b", i32), ("net_h", i32), ("net_w", i32),
-        ("patches", vp), ("ldp", i32),
+        ("patches", vp), ("ldp", i32), ("split", i32),
     ]
 
 

@@ -417,6 +417,146 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Split-f16 ("precise") attention: operands arrive as hi + lo f16 pairs, everything is computed in
+// fp32 on the CUDA cores (exact expf, f32 products and sums) and the result leaves as a hi/lo pair.
+// A parity / debugging mode (udb_attn_t.split): it exists to show that the default path's residual
+// against the fp32 reference is operand rounding, not logic.  64 queries x 64 keys per step, 256 threads,
+// thread (ty, tx) owns rows ty+16i and columns / head dims tx+16j.
+// ---------------------------------------------------------------------------------------------
+constexpr int SP_T = 64;          // tile edge
+constexpr int SP_P = 65;          // smem pitch (floats): conflict-free row-strided reads
+constexpr int SP_SMEM = (4 * SP_T * SP_P + 3 * SP_T) * 4;
+
+__global__ void __launch_bounds__(256) attn_split_f32_kernel(const udb_attn_t a) {
+  extern __shared__ float sp_smem[];
+  float* Qs = sp_smem;
+  float* Ks = Qs + SP_T * SP_P;
+  float* Vs = Ks + SP_T * SP_P;
+  float* Ps = Vs + SP_T * SP_P;
+  float* m_s = Ps + SP_T * SP_P;
+  float* l_s = m_s + SP_T;
+  float* al_s = l_s + SP_T;
+  const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
+  const int q0 = blockIdx.x * SP_T, h = blockIdx.y, b = blockIdx.z;
+  const __half* qp = reinterpret_cast<const __half*>(a.q);
+  const __half* kp = reinterpret_cast<const __half*>(a.k);
+  const __half* vp = reinterpret_cast<const __half*>(a.v);
+  auto ld = [](const __half* base, long long off, int lo_off) {
+    return __half2float(base[off]) + (lo_off ? __half2float(base[off + lo_off]) : 0.f);
+  };
+  for (int i = t; i < SP_T * SP_T; i += 256) {
+    const int r = i >> 6, d = i & 63;
+    const int sq = q0 + r;
+    Qs[r * SP_P + d] = sq < a.seq_q ? ld(qp, ((long long)b * a.seq_q + sq) * a.ldq + a.q_col0 + h * 64 + d, a.lo_off_q) * a.scale : 0.f;
+  }
+  if (t < SP_T) { m_s[t] = -INFINITY; l_s[t] = 0.f; }
+  float O[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) O[i][j] = 0.f;
+  const int n_kt = (a.seq_k + SP_T - 1) / SP_T;
+  for (int kt = 0; kt < n_kt; ++kt) {
+    __syncthreads();     // previous tile's Ks / Vs / Ps fully consumed (and Qs / m / l initialised)
+    for (int i = t; i < SP_T * SP_T; i += 256) {
+      const int r = i >> 6, d = i & 63;
+      const int sk = kt * SP_T + r;
+      const bool ok = sk < a.seq_k;
+      const long long row = (long long)b * a.seq_k + sk;
+      Ks[r * SP_P + d] = ok ? ld(kp, row * a.ldk + a.k_col0 + h * 64 + d, a.lo_off_k) : 0.f;
+      Vs[r * SP_P + d] = ok ? ld(vp, row * a.ldv + a.v_col0 + h * 64 + d, a.lo_off_v) : 0.f;
+    }
+    __syncthreads();
+    float S[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) S[i][j] = 0.f;
+    for (int d = 0; d < 64; ++d) {
+      float qv[4], kv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) qv[i] = Qs[(ty + 16 * i) * SP_P + d];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) kv[j] = Ks[(tx + 16 * j) * SP_P + d];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) S[i][j] = fmaf(qv[i], kv[j], S[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = tx + 16 * j;
+        Ps[(ty + 16 * i) * SP_P + c] = (kt * SP_T + c < a.seq_k) ? S[i][j] : -INFINITY;
+      }
+    __syncthreads();
+    {   // online softmax: 4 threads per row, 16 columns each
+      const int r = t >> 2, part = t & 3;
+      float* pr = Ps + r * SP_P + part * 16;
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) mx = fmaxf(mx, pr[c]);
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      const float m_old = m_s[r];
+      const float m_new = fmaxf(m_old, mx);
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        const float pv = expf(pr[c] - m_new);
+        pr[c] = pv;
+        sum += pv;
+      }
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      __syncwarp();
+      if (part == 0) {
+        const float al = expf(m_old - m_new);
+        al_s[r] = al;
+        m_s[r] = m_new;
+        l_s[r] = l_s[r] * al + sum;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float al = al_s[ty + 16 * i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) O[i][j] *= al;
+    }
+    for (int c = 0; c < SP_T; ++c) {
+      float pv[4], vv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) pv[i] = Ps[(ty + 16 * i) * SP_P + c];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) vv[j] = Vs[c * SP_P + tx + 16 * j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) O[i][j] = fmaf(pv[i], vv[j], O[i][j]);
+    }
+  }
+  __half* op = reinterpret_cast<__half*>(a.out);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = ty + 16 * i;
+    const int sq = q0 + r;
+    if (sq >= a.seq_q) continue;
+    const float inv = 1.0f / l_s[r];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float v = O[i][j] * inv;
+      const long long off = ((long long)b * a.seq_q + sq) * a.ldo + a.o_col0 + h * 64 + tx + 16 * j;
+      const __half hi = __float2half_rn(v);
+      op[off] = hi;
+      if (a.lo_off_o) op[off + a.lo_off_o] = __float2half_rn(v - __half2float(hi));
+    }
+  }
+}
+
 }  // namespace udb
 
 #ifdef UDB_ATTN_TRACE
@@ -429,6 +569,16 @@ extern "C" int udb_attention_f16(const udb_attn_t* a, void* stream) {
   using namespace udb;
   if (a->head_dim != 64) { set_error("udb_attention_f16: head_dim %d unsupported (64 only)", a->head_dim); return 1; }
   if ((a->ldq | a->ldk | a->ldv | a->ldo) % 8) { set_error("udb_attention_f16: leading dims must be multiples of 8"); return 1; }
+  if (a->split) {
+    static std::atomic<uint64_t> sp_mask{0};
+    if (first_on_device(sp_mask)) {
+      cudaError_t e = cudaFuncSetAttribute(attn_split_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SMEM);
+      if (e != cudaSuccess) { set_error("attention(split): cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1; }
+    }
+    dim3 grid((a->seq_q + SP_T - 1) / SP_T, a->heads, a->B);
+    attn_split_f32_kernel<<<grid, 256, SP_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(*a);
+    return check_launch("attn_split_f32_kernel");
+  }
   constexpr int HD = 64;
   CUtensorMap tq, tk, tv;
   const uint32_t box_q[3] = {HD, AT_BQ, 1};

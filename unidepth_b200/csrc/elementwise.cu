@@ -89,8 +89,14 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const udb_layernorm_t p)
           *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (long long)(row0 + r) * p.ld_out + e) =
               make_float4(y0, y1, y2, y3);
         } else {
-          *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out) + (long long)(row0 + r) * p.ld_out + e) =
-              make_uint2(pack_half2(y0, y1), pack_half2(y2, y3));
+          __half* op = reinterpret_cast<__half*>(p.out) + (long long)(row0 + r) * p.ld_out + e;
+          const uint2 hi = make_uint2(pack_half2(y0, y1), pack_half2(y2, y3));
+          *reinterpret_cast<uint2*>(op) = hi;
+          if (p.out_split > 0) {      // split-f16 precise mode: lo = f16(y - f32(hi)) at column + out_split
+            const float2 h01 = __half22float2(*reinterpret_cast<const __half2*>(&hi.x));
+            const float2 h23 = __half22float2(*reinterpret_cast<const __half2*>(&hi.y));
+            *reinterpret_cast<uint2*>(op + p.out_split) = make_uint2(pack_half2(y0 - h01.x, y1 - h01.y), pack_half2(y2 - h23.x, y3 - h23.y));
+          }
         }
       }
     }
@@ -159,36 +165,50 @@ __device__ __forceinline__ void bilinear_src(float scale, int dst, int in_size, 
   l0 = 1.f - l1;
 }
 
+// One thread per 8 consecutive patch-matrix columns (one 16-byte store).  `split`: the row holds [hi | lo] halves of
+// ldp/2 columns each, lo = f16(val - f32(hi)) (split-f16 precise mode, see udb_gemm_t.a_split_k).
 __global__ void __launch_bounds__(256) preprocess_patchify_kernel(const udb_preprocess_t p, int gh, int gw, float sh, float sw) {
-  const long long total = (long long)p.B * gh * gw * p.ldp;
+  const int vec_per_row = p.ldp >> 3;
+  const long long total = (long long)p.B * gh * gw * vec_per_row;
   const float mean[3] = {0.485f, 0.456f, 0.406f};
   const float stdv[3] = {0.229f, 0.224f, 0.225f};
   const int padded_h = p.H + p.pad_t + p.pad_b, padded_w = p.W + p.pad_l + p.pad_r;
+  const int half_w = p.split ? (p.ldp >> 1) : p.ldp;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
-    const int col = (int)(idx % p.ldp);
-    const long long rowi = idx / p.ldp;
-    float val = 0.f;
-    if (col < 588) {
-      const int c = col / 196, py = (col % 196) / 14, px = col % 14;
-      const int gx = (int)(rowi % gw), gy = (int)((rowi / gw) % gh), b = (int)(rowi / ((long long)gw * gh));
-      const int Y = gy * 14 + py, X = gx * 14 + px;
-      int y0, y1, x0, x1;
-      float ly0, ly1, lx0, lx1;
-      bilinear_src(sh, Y, padded_h, y0, y1, ly0, ly1);
-      bilinear_src(sw, X, padded_w, x0, x1, lx0, lx1);
-      auto fetch = [&](int yy, int xx) -> float {
-        const int oy = yy - p.pad_t, ox = xx - p.pad_l;
-        if (oy < 0 || oy >= p.H || ox < 0 || ox >= p.W) return 0.f;
-        const long long o = (((long long)b * 3 + c) * p.H + oy) * p.W + ox;
-        float v = p.rgb_is_u8 ? (float)reinterpret_cast<const uint8_t*>(p.rgb)[o]
-                              : reinterpret_cast<const float*>(p.rgb)[o];
-        if (p.normalize) v = (v / 255.0f - mean[c]) / stdv[c];
-        return v;
-      };
-      val = ly0 * (lx0 * fetch(y0, x0) + lx1 * fetch(y0, x1)) + ly1 * (lx0 * fetch(y1, x0) + lx1 * fetch(y1, x1));
+    const int col_store = (int)(idx % vec_per_row) * 8;
+    const long long rowi = idx / vec_per_row;
+    const bool lo_half = col_store >= half_w;
+    const int col0 = lo_half ? col_store - half_w : col_store;
+    const int gx = (int)(rowi % gw), gy = (int)((rowi / gw) % gh), b = (int)(rowi / ((long long)gw * gh));
+    float val[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int col = col0 + j;
+      float v = 0.f;
+      if (col < 588) {
+        const int c = col / 196, py = (col % 196) / 14, px = col % 14;
+        const int Y = gy * 14 + py, X = gx * 14 + px;
+        int y0, y1, x0, x1;
+        float ly0, ly1, lx0, lx1;
+        bilinear_src(sh, Y, padded_h, y0, y1, ly0, ly1);
+        bilinear_src(sw, X, padded_w, x0, x1, lx0, lx1);
+        auto fetch = [&](int yy, int xx) -> float {
+          const int oy = yy - p.pad_t, ox = xx - p.pad_l;
+          if (oy < 0 || oy >= p.H || ox < 0 || ox >= p.W) return 0.f;
+          const long long o = (((long long)b * 3 + c) * p.H + oy) * p.W + ox;
+          float t = p.rgb_is_u8 ? (float)__ldg(reinterpret_cast<const uint8_t*>(p.rgb) + o)
+                                : __ldg(reinterpret_cast<const float*>(p.rgb) + o);
+          if (p.normalize) t = (t / 255.0f - mean[c]) / stdv[c];
+          return t;
+        };
+        v = ly0 * (lx0 * fetch(y0, x0) + lx1 * fetch(y0, x1)) + ly1 * (lx0 * fetch(y1, x0) + lx1 * fetch(y1, x1));
+      }
+      if (lo_half) v -= __half2float(__float2half_rn(v));
+      val[j] = v;
     }
-    reinterpret_cast<__half*>(p.patches)[idx] = __float2half_rn(val);
+    uint4 o4 = make_uint4(pack_half2(val[0], val[1]), pack_half2(val[2], val[3]), pack_half2(val[4], val[5]), pack_half2(val[6], val[7]));
+    *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.patches) + rowi * p.ldp + col_store) = o4;
   }
 }
 
@@ -585,11 +605,14 @@ extern "C" int udb_layernorm(const udb_layernorm_t* p, void* stream) {
 }
 
 extern "C" int udb_preprocess_patchify(const udb_preprocess_t* p, void* stream) {
-  if (p->net_h % 14 || p->net_w % 14 || p->ldp < 588) { set_error("udb_preprocess_patchify: bad shape"); return 1; }
+  if (p->net_h % 14 || p->net_w % 14 || p->ldp < (p->split ? 1184 : 592) || p->ldp % 16) {
+    set_error("udb_preprocess_patchify: bad shape (net %dx%d, ldp %d)", p->net_h, p->net_w, p->ldp);
+    return 1;
+  }
   const int gh = p->net_h / 14, gw = p->net_w / 14;
   const int padded_h = p->H + p->pad_t + p->pad_b, padded_w = p->W + p->pad_l + p->pad_r;
   const float sh = (float)padded_h / (float)p->net_h, sw = (float)padded_w / (float)p->net_w;
-  const long long total = (long long)p->B * gh * gw * p->ldp;
+  const long long total = (long long)p->B * gh * gw * (p->ldp / 8);
   preprocess_patchify_kernel<<<grid_for(total), 256, 0, ST(stream)>>>(*p, gh, gw, sh, sw);
   return check_launch("preprocess_patchify_kernel");
 }

@@ -175,6 +175,7 @@ struct Ctx {
     const float* bias = nullptr; const float* gamma = nullptr; const void* resid = nullptr; int resid_f32 = 0;
     long long ldr = 0; void* out = nullptr; int out_f32 = 0; long long ldc = 0; void* out2 = nullptr; int out2_leaky = 1;
     int act = UDB_ACT_NONE; int rows_per_group = 0, group_stride = 0, row_offset = 0, resid_mod = 0, resid_row_offset = 0;
+    int a_split_k = 0, out_split = 0;    // split-f16 precise mode (udb_gemm_t)
   };
   void gemm(const G& q) {
     if (dry || rc) return;
@@ -190,6 +191,7 @@ struct Ctx {
     g.act = q.act; g.store_mode = UDB_STORE_ROWS;
     g.rows_per_group = q.rows_per_group; g.group_stride = q.group_stride; g.row_offset = q.row_offset;
     g.resid_mod = q.resid_mod; g.resid_row_offset = q.resid_row_offset;
+    g.a_split_k = q.a_split_k; g.out_split = q.out_split;
     done(udb_gemm_f16(&g, st));
   }
   // ConvTranspose2d with kernel == stride == k as a GEMM with a pixel-shuffle store (ops.conv_transpose_ks)
@@ -233,24 +235,27 @@ struct Ctx {
     done(udb_conv3x3_halo_f16(&c, st));
   }
   void attention(const void* q, const void* k, const void* v, void* out, int B, int heads, int sq, int sk, int ldq,
-                 int ldk, int ldv, int ldo, int q0, int k0, int v0, float scale) {
+                 int ldk, int ldv, int ldo, int q0, int k0, int v0, float scale, int lo_in = 0, int lo_out = 0) {
     if (dry || rc) return;
     udb_attn_t a;
     memset(&a, 0, sizeof(a));
     a.q = q; a.k = k; a.v = v; a.out = out; a.B = B; a.heads = heads; a.seq_q = sq; a.seq_k = sk; a.head_dim = 64;
     a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.ldo = ldo; a.q_col0 = q0; a.k_col0 = k0; a.v_col0 = v0; a.o_col0 = 0;
     a.scale = scale;
+    if (lo_in) { a.split = 1; a.lo_off_q = a.lo_off_k = a.lo_off_v = lo_in; a.lo_off_o = lo_out; }
     done(udb_attention_f16(&a, st));
   }
   void layernorm(const void* in, int in_f32, void* out, int out_f32, const float* w, const float* b, int rows, int dim,
-                 float eps, int rows_per_group = 0, int group_stride = 0, int row_offset = 0, int dim_valid = 0) {
+                 float eps, int rows_per_group = 0, int group_stride = 0, int row_offset = 0, int dim_valid = 0,
+                 int out_split = 0) {
     if (dry || rc) return;
     udb_layernorm_t p;
     memset(&p, 0, sizeof(p));
     p.in = in; p.in_f32 = in_f32; p.out = out; p.out_f32 = out_f32; p.weight = w; p.bias = b;
-    p.rows = rows; p.dim = dim; p.ld_in = dim; p.ld_out = dim;
+    p.rows = rows; p.dim = dim; p.ld_in = dim; p.ld_out = out_split ? 2 * dim : dim;
     p.rows_per_group = rows_per_group; p.group_stride = group_stride; p.row_offset = row_offset; p.eps = eps;
     p.dim_valid = dim_valid;
+    p.out_split = out_split;
     done(udb_layernorm(&p, st));
   }
   void small_linear(const float* x, int M, int K, const float* w, int N, const float* bias, int act, const float* gamma,
@@ -299,20 +304,27 @@ static int run(udb_engine* e, const udb_infer_args_t& a, const udb_geometry_t& g
   // ---- a2/a3/a4: pre-process + patch embedding + cls / position rows
   Stage stage;
   stage.next("udb:preprocess+patch_embed");
-  __half* patches = ar.h(BN * 640);
+  // Split-f16 precise mode (udb_set_scalar("precision", 1)): every f16 GEMM operand of the ENCODER is a hi/lo pair and
+  // the weights are packed [N, 3K] = [hi | hi | lo] (udb_gemm_t.a_split_k); attention runs in the fp32 kernel.  The
+  // cls tokens / camera head are fp32 anyway, so the intrinsics then carry no f16 operand rounding at all.
+  const bool sp = e->scalars.count("precision") && e->scalars["precision"] == 1.0;
+  const int sx = sp ? 2 : 1;
+  __half* patches = ar.h(BN * 640 * sx);
   if (!c.dry) {
     udb_preprocess_t p;
     memset(&p, 0, sizeof(p));
     p.rgb = a.rgb; p.rgb_is_u8 = a.rgb_is_u8; p.normalize = a.normalize; p.B = B; p.H = a.H; p.W = a.W;
     p.pad_l = g.pad_l; p.pad_r = g.pad_r; p.pad_t = g.pad_t; p.pad_b = g.pad_b; p.net_h = nh; p.net_w = nw;
-    p.patches = patches; p.ldp = 640;
+    p.patches = patches; p.ldp = 640 * sx; p.split = sp ? 1 : 0;
     c.done(udb_preprocess_patchify(&p, st));
   }
   float* x = ar.f(BT * D);           // fp32 residual stream
   {
-    Ctx::G q{patches, c.H("patch_w"), static_cast<int>(BN), D, 640};
+    Ctx::G q{patches, c.H("patch_w"), static_cast<int>(BN), D, sp ? 3 * 640 : 640};
+    q.lda = 640 * sx; q.a_split_k = sp ? 640 : 0;
     q.bias = c.F("patch_b"); q.resid = tb.pos; q.resid_f32 = 1; q.ldr = D; q.out = x; q.out_f32 = 1;
     q.rows_per_group = N; q.group_stride = T; q.row_offset = 1; q.resid_mod = N; q.resid_row_offset = 1;
+    if (sp) c.expect2("patch_w", D, 3 * 640);
     c.gemm(q);
     if (!c.dry && !c.rc) c.done(udb_set_cls_rows(x, c.F("cls"), tb.pos, B, T, D, st));
   }
@@ -324,22 +336,30 @@ static int run(udb_engine* e, const udb_infer_args_t& a, const udb_geometry_t& g
   for (int l = 0; l < 4; ++l) { feats[l] = ar.h(BN * D); clss[l] = ar.f(static_cast<size_t>(B) * D); }
   {
     const size_t m = ar.mark();
-    __half* h = ar.h(BT * D);
-    __half* qkv = ar.h(BT * 3 * D);
-    __half* att = ar.h(BT * D);
-    __half* mid = ar.h(BT * 4 * D);
+    __half* h = ar.h(BT * D * sx);
+    __half* qkv = ar.h(BT * 3 * D * sx);
+    __half* att = ar.h(BT * D * sx);
+    __half* mid = ar.h(BT * 4 * D * sx);
+    const int kx = sp ? 3 : 1;          // logical K multiplier of a split operand
     int tap = 0;
     for (int i = 0; i < cf.depth; ++i) {
       const std::string b = idx("blocks.%d.", i);
-      c.layernorm(x, 1, h, 0, c.F(b + "n1w"), c.F(b + "n1b"), static_cast<int>(BT), D, 1e-6f);
-      { Ctx::G q{h, c.H(b + "qkv_w"), static_cast<int>(BT), 3 * D, D}; q.bias = c.F(b + "qkv_b"); q.out = qkv; c.gemm(q); }
-      c.attention(qkv, qkv, qkv, att, B, cf.enc_heads, T, T, 3 * D, 3 * D, 3 * D, D, 0, D, 2 * D, 0.125f);
-      { Ctx::G q{att, c.H(b + "proj_w"), static_cast<int>(BT), D, D}; q.bias = c.F(b + "proj_b"); q.gamma = c.F(b + "ls1");
+      if (sp) { c.expect2(b + "qkv_w", 3 * D, 3 * D); c.expect2(b + "proj_w", D, 3 * D); c.expect2(b + "fc1_w", 4 * D, 3 * D);
+                c.expect2(b + "fc2_w", D, 12 * D); }
+      c.layernorm(x, 1, h, 0, c.F(b + "n1w"), c.F(b + "n1b"), static_cast<int>(BT), D, 1e-6f, 0, 0, 0, 0, sp ? D : 0);
+      { Ctx::G q{h, c.H(b + "qkv_w"), static_cast<int>(BT), 3 * D, D * kx}; q.lda = D * sx; q.a_split_k = sp ? D : 0;
+        q.bias = c.F(b + "qkv_b"); q.out = qkv; q.ldc = 3 * D * sx; q.out_split = sp ? 3 * D : 0; c.gemm(q); }
+      c.attention(qkv, qkv, qkv, att, B, cf.enc_heads, T, T, 3 * D * sx, 3 * D * sx, 3 * D * sx, D * sx, 0, D, 2 * D, 0.125f,
+                  sp ? 3 * D : 0, sp ? D : 0);
+      { Ctx::G q{att, c.H(b + "proj_w"), static_cast<int>(BT), D, D * kx}; q.lda = D * sx; q.a_split_k = sp ? D : 0;
+        q.bias = c.F(b + "proj_b"); q.gamma = c.F(b + "ls1");
         q.resid = x; q.resid_f32 = 1; q.out = x; q.out_f32 = 1; c.gemm(q); }
-      c.layernorm(x, 1, h, 0, c.F(b + "n2w"), c.F(b + "n2b"), static_cast<int>(BT), D, 1e-6f);
-      { Ctx::G q{h, c.H(b + "fc1_w"), static_cast<int>(BT), 4 * D, D}; q.bias = c.F(b + "fc1_b"); q.act = UDB_ACT_GELU;
-        q.out = mid; c.gemm(q); }
-      { Ctx::G q{mid, c.H(b + "fc2_w"), static_cast<int>(BT), D, 4 * D}; q.bias = c.F(b + "fc2_b"); q.gamma = c.F(b + "ls2");
+      c.layernorm(x, 1, h, 0, c.F(b + "n2w"), c.F(b + "n2b"), static_cast<int>(BT), D, 1e-6f, 0, 0, 0, 0, sp ? D : 0);
+      { Ctx::G q{h, c.H(b + "fc1_w"), static_cast<int>(BT), 4 * D, D * kx}; q.lda = D * sx; q.a_split_k = sp ? D : 0;
+        q.bias = c.F(b + "fc1_b"); q.act = UDB_ACT_GELU;
+        q.out = mid; q.ldc = 4 * D * sx; q.out_split = sp ? 4 * D : 0; c.gemm(q); }
+      { Ctx::G q{mid, c.H(b + "fc2_w"), static_cast<int>(BT), D, 4 * D * kx}; q.lda = 4 * D * sx; q.a_split_k = sp ? 4 * D : 0;
+        q.bias = c.F(b + "fc2_b"); q.gamma = c.F(b + "ls2");
         q.resid = x; q.resid_f32 = 1; q.out = x; q.out_f32 = 1; c.gemm(q); }
       if (tap < 4 && i + 1 == cf.taps[tap]) {
         c.layernorm(x, 1, feats[tap], 0, c.F("norm_w"), c.F("norm_b"), static_cast<int>(BN), D, 1e-5f, N, T, 1);

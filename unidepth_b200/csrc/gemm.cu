@@ -44,6 +44,8 @@ struct GemmArgs {
   int conv_coff;
   const float* head_w;
   float head_b, head_add;
+  int a_wrap;      // split-f16 operands: k-blocks at or beyond this element offset re-read A from (k - a_wrap); 0 = off
+  int out_split;   // f16 `out`: lo half stored out_split elements to the right; 0 = off
 };
 
 template <int BN>
@@ -229,10 +231,24 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, const EpiWarp& 
               });
             } else {
               __half* op = reinterpret_cast<__half*>(p.out) + c32 + l4;
-              for_rows([&](int rr, bool ok) {
-                const float4 t = *reinterpret_cast<const float4*>(T + rr * kTP + l4);
-                if (ok) *reinterpret_cast<uint2*>(op + roff_out[rr]) = make_uint2(pack_half2(t.x, t.y), pack_half2(t.z, t.w));
-              });
+              if (p.out_split == 0) {
+                for_rows([&](int rr, bool ok) {
+                  const float4 t = *reinterpret_cast<const float4*>(T + rr * kTP + l4);
+                  if (ok) *reinterpret_cast<uint2*>(op + roff_out[rr]) = make_uint2(pack_half2(t.x, t.y), pack_half2(t.z, t.w));
+                });
+              } else {   // split-f16 output: hi and lo = f16(v - f32(hi))
+                for_rows([&](int rr, bool ok) {
+                  const float4 t = *reinterpret_cast<const float4*>(T + rr * kTP + l4);
+                  const uint2 hi = make_uint2(pack_half2(t.x, t.y), pack_half2(t.z, t.w));
+                  const float2 h01 = __half22float2(*reinterpret_cast<const __half2*>(&hi.x));
+                  const float2 h23 = __half22float2(*reinterpret_cast<const __half2*>(&hi.y));
+                  if (ok) {
+                    *reinterpret_cast<uint2*>(op + roff_out[rr]) = hi;
+                    *reinterpret_cast<uint2*>(op + roff_out[rr] + p.out_split) =
+                        make_uint2(pack_half2(t.x - h01.x, t.y - h01.y), pack_half2(t.z - h23.x, t.w - h23.y));
+                  }
+                });
+              }
             }
             __syncwarp();
           }
@@ -331,7 +347,9 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               tma_load_4d(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], c0, cx + tap % 3,
                           cy + tap / 3, cb);
             } else {
-              tma_load_2d(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * BK, mt * BM);
+              int ka = kb * BK;
+              if (p.a_wrap && ka >= p.a_wrap) ka -= p.a_wrap;
+              tma_load_2d(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], ka, mt * BM);
             }
             tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * BK, nt * BN);
           }
@@ -531,7 +549,9 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               const int c0 = p.conv_coff + (kb % p.conv_cpb) * BK;
               tma_load_4d_2sm(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], c0, cx + tap % 3, cy + tap / 3, cb);
             } else {
-              tma_load_2d_2sm(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * BK, mt * BM);
+              int ka = kb * BK;
+              if (p.a_wrap && ka >= p.a_wrap) ka -= p.a_wrap;
+              tma_load_2d_2sm(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], ka, mt * BM);
             }
             tma_load_2d_2sm(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * BK, nt * BN + (int)rank * (BN / 2));
           }
@@ -653,6 +673,19 @@ extern "C" int udb_gemm_f16(const udb_gemm_t* g, void* stream) {
   a.ct_k = g->ct_k; a.ct_cout = g->ct_cout; a.ct_h = g->ct_h; a.ct_w = g->ct_w; a.ct_pad = g->ct_pad;
   a.conv_coff = g->conv_coff;
   a.head_w = g->head_w; a.head_b = g->head_b; a.head_add = g->head_add;
+  a.a_wrap = 0;
+  a.out_split = g->out_split;
+  if (g->a_split_k > 0) {
+    if (g->a_mode != UDB_A_MATRIX || g->a_split_k % BK || g->K != 3 * g->a_split_k || g->lda < 2 * g->a_split_k) {
+      set_error("udb_gemm_f16: split operands need a_mode MATRIX, K1 %% 64 == 0, K == 3*K1, lda >= 2*K1 (K1=%d K=%d lda=%d)",
+                g->a_split_k, g->K, g->lda);
+      return 1;
+    }
+    a.a_wrap = 2 * g->a_split_k;
+  }
+  if (g->out_split && (g->out_f32 || !g->out || g->store_mode != UDB_STORE_ROWS)) {
+    set_error("udb_gemm_f16: out_split needs an f16 `out` with the ROWS store"); return 1;
+  }
 
   // tile width: widest that divides the work sensibly
   int bn;
@@ -704,7 +737,7 @@ extern "C" int udb_gemm_f16(const udb_gemm_t* g, void* stream) {
     if (g->store_mode == UDB_STORE_CONVTILE || g->store_mode == UDB_STORE_HEAD) {
       set_error("udb_gemm_f16: tile store modes need a_mode == CONV3X3"); return 1;
     }
-    const uint64_t dims[2] = {(uint64_t)g->K, (uint64_t)g->M};
+    const uint64_t dims[2] = {(uint64_t)(g->a_split_k > 0 ? 2 * g->a_split_k : g->K), (uint64_t)g->M};
     const uint64_t str[1] = {(uint64_t)g->lda * 2};
     const uint32_t box[2] = {(uint32_t)BK, (uint32_t)BM};
     if (make_tmap_f16(&tmA, g->a, 2, dims, str, box, true)) return 1;

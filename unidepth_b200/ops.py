@@ -56,14 +56,21 @@ def _is32(t):
 def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, act=ACT_NONE, gamma=None, resid=None,
          out: Optional[torch.Tensor] = None, out_dtype=f16, out2: Optional[torch.Tensor] = None, out2_leaky=True,
          rows_per_group=0, group_stride=0, row_offset=0, resid_mod=0, resid_row_offset=0,
-         out_rows: Optional[int] = None):
-    """out[row(m), :] = resid + gamma * act(a @ w.T + bias).  a f16 [M,K], w f16 [N,K]."""
+         out_rows: Optional[int] = None, a_split_k: int = 0, out_split: bool = False):
+    """out[row(m), :] = resid + gamma * act(a @ w.T + bias).  a f16 [M,K], w f16 [N,K].
+    Split-f16 mode (udb_gemm_t.a_split_k = K1): a is [M, 2*K1] = [hi | lo], w is [N, 3*K1] = [hi | hi | lo];
+    out_split: the f16 output is written as [M, 2N] = [hi | lo]."""
     assert a.dtype == f16 and w.dtype == f16 and a.stride(-1) == 1 and w.stride(-1) == 1
     M, K = a.shape
     N = w.shape[0]
-    assert w.shape[1] == K
+    if a_split_k:
+        assert K == 2 * a_split_k and w.shape[1] == 3 * a_split_k
+        K = 3 * a_split_k
+    else:
+        assert w.shape[1] == K
     if out is None:
-        out = torch.empty((out_rows if out_rows is not None else M, N), device=a.device, dtype=out_dtype)
+        out = torch.empty((out_rows if out_rows is not None else M, 2 * N if out_split else N), device=a.device,
+                          dtype=f16 if out_split else out_dtype)
     g = cabi.Gemm()
     g.a, g.w = _ptr(a), _ptr(w)
     g.M, g.N, g.K = M, N, K
@@ -77,6 +84,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, act=ACT_NONE, gamma=Non
     g.act, g.store_mode = act, STORE_ROWS
     g.rows_per_group, g.group_stride, g.row_offset = rows_per_group, group_stride, row_offset
     g.resid_mod, g.resid_row_offset = resid_mod, resid_row_offset
+    g.a_split_k, g.out_split = a_split_k, (N if out_split else 0)
     cabi.check(_launch("gemm_f16_kernel", 2.0 * M * N * K, lambda: cabi.lib().udb_gemm_f16(C.byref(g), _stream())),
                "udb_gemm_f16")
     return out
@@ -179,25 +187,29 @@ def conv_transpose_ks(x: torch.Tensor, w: torch.Tensor, k: int, cout: int, grid_
     return out
 
 
-def attention(q, k, v, out, *, B, heads, seq_q, seq_k, head_dim, q_col0=0, k_col0=0, v_col0=0, o_col0=0, scale=None):
+def attention(q, k, v, out, *, B, heads, seq_q, seq_k, head_dim, q_col0=0, k_col0=0, v_col0=0, o_col0=0, scale=None,
+              lo_off_in=0, lo_off_out=0):
+    """lo_off_in > 0: split-f16 operands (lo halves lo_off_in columns to the right), fp32 CUDA-core kernel."""
     a = cabi.Attn()
     a.q, a.k, a.v, a.out = _ptr(q), _ptr(k), _ptr(v), _ptr(out)
     a.B, a.heads, a.seq_q, a.seq_k, a.head_dim = B, heads, seq_q, seq_k, head_dim
     a.ldq, a.ldk, a.ldv, a.ldo = q.stride(0), k.stride(0), v.stride(0), out.stride(0)
     a.q_col0, a.k_col0, a.v_col0, a.o_col0 = q_col0, k_col0, v_col0, o_col0
     a.scale = head_dim ** -0.5 if scale is None else scale   # explicit scale: zero-padded narrower heads
+    if lo_off_in:
+        a.split, a.lo_off_q, a.lo_off_k, a.lo_off_v, a.lo_off_o = 1, lo_off_in, lo_off_in, lo_off_in, lo_off_out
     cabi.check(_launch("attn_fwd_kernel", 4.0 * B * heads * seq_q * seq_k * head_dim,
                        lambda: cabi.lib().udb_attention_f16(C.byref(a), _stream())), "udb_attention_f16")
     return out
 
 
 def layernorm(x, weight, bias, eps, *, out=None, out_dtype=f16, rows=None, rows_per_group=0,
-              group_stride=0, row_offset=0, dim_valid=0):
+              group_stride=0, row_offset=0, dim_valid=0, out_split=False):
     dim = x.shape[-1]
     x2 = x.reshape(-1, dim)
     n_rows = rows if rows is not None else x2.shape[0]
     if out is None:
-        out = torch.empty((n_rows, dim), device=x.device, dtype=out_dtype)
+        out = torch.empty((n_rows, 2 * dim if out_split else dim), device=x.device, dtype=f16 if out_split else out_dtype)
     p = cabi.LayerNorm()
     p.inp, p.in_f32 = _ptr(x2), _is32(x2)
     p.out, p.out_f32 = _ptr(out), _is32(out)
@@ -207,6 +219,7 @@ def layernorm(x, weight, bias, eps, *, out=None, out_dtype=f16, rows=None, rows_
     p.rows_per_group, p.group_stride, p.row_offset = rows_per_group, group_stride, row_offset
     p.eps = eps
     p.dim_valid = dim_valid
+    p.out_split = dim if out_split else 0
     nbytes = float(n_rows * dim * (x2.element_size() + out.element_size()))
     cabi.check(_launch("layernorm_kernel", 0.0, lambda: cabi.lib().udb_layernorm(C.byref(p), _stream()), nbytes), "udb_layernorm")
     return out

@@ -76,6 +76,12 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
         self.interpolation_mode = "bilinear"                 # unidepthv2.py:460
         self.use_cuda_graph = True
         self.use_engine = True        # False: schedule the same kernels from Python (ops.*; debugging taps / per-kernel timing)
+        # "f16": f16 GEMM / attention operands with f32 accumulation (the reference's own GPU dtype, unidepthv2.py:240).
+        # "split": parity / debugging mode -- every f16 operand of the ENCODER is a hi + lo pair fed through the same
+        # tcgen05 GEMM (three products hi.W_hi + lo.W_hi + hi.W_lo, include/udb.h udb_gemm_t.a_split_k) and attention
+        # runs in fp32; ~4x slower.  It shows that the default mode's residual against the fp32 reference is operand
+        # rounding: the intrinsics (fp32 camera head on the encoder's cls tokens) then meet north_star's 1e-4.
+        self.precision = "f16"
         self._engine = None
         self._engine_key = None
         # Bounded caches (LRU): the reference handles arbitrary shapes in constant memory, so a stream of
@@ -122,7 +128,7 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
 
     # ------------------------------------------------------------------ weight packing
     def _fingerprint(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+        return (self.precision,) + tuple((p.data_ptr(), p._version) for p in self.parameters())
 
     def _pack(self):
         """One-time (per weight version) repack into kernel operand layouts."""
@@ -138,7 +144,20 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
         sd = {k: v.detach() for k, v in self.state_dict().items()}
         h16 = lambda t: t.to(f16).contiguous()
         c32 = lambda t: t.to(f32).contiguous()
-        P: dict = {}
+        if self.precision not in ("f16", "split"):
+            raise ValueError(f"precision must be 'f16' or 'split', not {self.precision!r}")
+        split = self.precision == "split"
+
+        def enc16(w):
+            """Encoder GEMM weight [N, K]: f16, or in split mode [N, 3K] = [hi | hi | lo] with w ~= hi + lo."""
+            w = w.to(f32)
+            hi = w.to(f16)
+            if not split:
+                return hi.contiguous()
+            lo = (w - hi.to(f32)).to(f16)
+            return torch.cat([hi, hi, lo], dim=1).contiguous()
+
+        P: dict = {"split": split}
         d, hid = s.embed_dim, s.hidden
         # The attention kernel works on 64-wide heads.  Narrower decoder heads (ViT-S: 256/8 = 32) are
         # zero-padded to 64 in the packed q / kv / out weights: padded q,k columns add 0 to q.k, padded
@@ -159,9 +178,9 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
             raise NotImplementedError(f"high-resolution feature width {c_hr_real} not supported")
         P["dec_hd"], P["dec_hp"] = hd, s.dec_heads * 64
         pe = "pixel_encoder."
-        wpe = torch.zeros((d, 640), device=dev, dtype=f16)
-        wpe[:, :588] = sd[pe + "patch_embed.proj.weight"].reshape(d, 588).to(f16)
-        P["patch_w"], P["patch_b"] = wpe, c32(sd[pe + "patch_embed.proj.bias"])
+        wpe = torch.zeros((d, 640), device=dev, dtype=f32)
+        wpe[:, :588] = sd[pe + "patch_embed.proj.weight"].reshape(d, 588).to(f32)
+        P["patch_w"], P["patch_b"] = enc16(wpe), c32(sd[pe + "patch_embed.proj.bias"])
         P["cls"] = c32(sd[pe + "cls_token"].reshape(d))
         P["pos"] = c32(sd[pe + "pos_embed"].reshape(-1, d))
         P["blocks"] = []
@@ -169,12 +188,12 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
             b = f"{pe}blocks.{i}."
             P["blocks"].append(dict(
                 n1w=c32(sd[b + "norm1.weight"]), n1b=c32(sd[b + "norm1.bias"]),
-                qkv_w=h16(sd[b + "attn.qkv.weight"]), qkv_b=c32(sd[b + "attn.qkv.bias"]),
-                proj_w=h16(sd[b + "attn.proj.weight"]), proj_b=c32(sd[b + "attn.proj.bias"]),
+                qkv_w=enc16(sd[b + "attn.qkv.weight"]), qkv_b=c32(sd[b + "attn.qkv.bias"]),
+                proj_w=enc16(sd[b + "attn.proj.weight"]), proj_b=c32(sd[b + "attn.proj.bias"]),
                 ls1=c32(sd[b + "ls1.gamma"]),
                 n2w=c32(sd[b + "norm2.weight"]), n2b=c32(sd[b + "norm2.bias"]),
-                fc1_w=h16(sd[b + "mlp.fc1.weight"]), fc1_b=c32(sd[b + "mlp.fc1.bias"]),
-                fc2_w=h16(sd[b + "mlp.fc2.weight"]), fc2_b=c32(sd[b + "mlp.fc2.bias"]),
+                fc1_w=enc16(sd[b + "mlp.fc1.weight"]), fc1_b=c32(sd[b + "mlp.fc1.bias"]),
+                fc2_w=enc16(sd[b + "mlp.fc2.weight"]), fc2_b=c32(sd[b + "mlp.fc2.bias"]),
                 ls2=c32(sd[b + "ls2.gamma"])))
         P["norm_w"], P["norm_b"] = c32(sd[pe + "norm.weight"]), c32(sd[pe + "norm.bias"])
 
@@ -316,6 +335,7 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
         for k in ("patch_w", "patch_b", "cls", "pos", "norm_w", "norm_b", "lat_w", "lat_b", "head_mlp_w", "head_mlp_b",
                   "ln_ones", "ln_zeros"):
             T[k] = P[k]
+        S["precision"] = 1.0 if P.get("split") else 0.0
         for i, blk in enumerate(P["blocks"]):
             for k, v in blk.items():
                 T[f"blocks.{i}.{k}"] = v
@@ -774,6 +794,8 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
             self._drop_engine()       # too many distinct grids seen: rebuild (frees the engine's per-shape tables)
 
         def run(inp):
+            if not self.use_engine and self.precision != "f16":
+                raise NotImplementedError("precision='split' runs through the C engine only (use_engine=True)")
             if self.use_engine:
                 return self._forward_engine(inp, geom, normalize, level, camera_k=camera_k, rays_in=rays_in)
             self._pos_embed(gh, gw)

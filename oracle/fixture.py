@@ -218,3 +218,46 @@ def make_convnext_state_dict(depths, dims, seed: int):
             t = torch.randn(shp, generator=g) / fan_in ** 0.5
         sd[k] = t
     return sd
+
+
+def make_v1_state_dict(config: dict, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Seeded, well-conditioned fixture for UniDepthV1 (ConvNeXt encoder): names / shapes from
+    unidepth_b200.spec_v1.param_shapes (oracle/make_golden_v1.py asserts they equal the reference model's)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+    from unidepth_b200.spec_v1 import param_shapes as v1_shapes
+    sd: Dict[str, torch.Tensor] = {}
+    for idx, (key, shape) in enumerate(v1_shapes(config).items()):
+        g = torch.Generator().manual_seed(seed * 1_000_003 + idx)
+        n = lambda *s: torch.randn(*s, generator=g)
+        u = lambda *s: torch.rand(*s, generator=g)
+        leaf = key.rsplit(".", 1)[-1]
+        is_norm = ("norm" in key or key.endswith((".0.weight", ".0.bias")) and "input_adapters" in key
+                   or "cls_project.0." in key or "level_embed_layer.3." in key or "stem.1." in key
+                   or "downsample.0." in key)
+        if key.endswith("mask_token"):
+            t = torch.zeros(*shape)
+        elif key.endswith("level_embeds"):
+            t = 0.5 * n(*shape)
+        elif key.endswith("latents_pos"):
+            t = 0.5 * n(*shape)
+        elif ".ls1.gamma" in key or ".ls2.gamma" in key:
+            t = 0.3 * (0.5 + u(*shape))
+        elif leaf == "gamma":
+            t = 0.4 * (0.5 + u(*shape))
+        elif is_norm and len(shape) == 1:
+            t = 1.0 + 0.1 * n(*shape) if leaf == "weight" else 0.05 * n(*shape)
+        elif leaf == "bias":
+            t = 0.05 * n(*shape)
+        elif leaf == "weight":
+            fan_in = 1
+            for s_ in shape[1:]:
+                fan_in *= s_
+            t = n(*shape) / fan_in ** 0.5
+            if key.endswith(("camera_layer.out.proj2.weight", "out2.weight", "out4.weight", "out8.weight")):
+                t = 0.3 * t
+        else:
+            raise KeyError(key)
+        sd[key] = t.float().contiguous()
+    return sd

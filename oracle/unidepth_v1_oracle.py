@@ -315,12 +315,10 @@ def infer_v1(sd: Dict[str, torch.Tensor], cfg: dict, rgbs: torch.Tensor, intrins
     if taps is not None:
         taps["out8"], taps["out4"], taps["out2"], taps["K_net"] = outs[0], outs[1], outs[2], K.clone()
     pred, K_out = v1_postprocess(outs, K.clone(), net_hw, pads, ratio, (H, W))
-    use_k = gt_k_original(intrinsics) if intrinsics is not None else K_out
+    # unidepthv1.py:354-356: with GT intrinsics the reference back-projects with the PRE-PROCESSED K (scaled by `ratio`,
+    # shifted by the paddings) on the original-resolution pixel grid -- reproduced as is
+    use_k = gt_k if gt_k is not None else K_out
     angles = generate_rays(use_k, (H, W))[1]
     angles = angles.transpose(1, 2).reshape(B, 2, H, W)
     pts = spherical_zbuffer_to_euclidean(torch.cat((angles, pred), dim=1).permute(0, 2, 3, 1)).permute(0, 3, 1, 2)
     return {"intrinsics": K_out, "points": pts, "depth": pred[:, -1:]}
-
-
-def gt_k_original(intrinsics: torch.Tensor) -> torch.Tensor:
-    return intrinsics

@@ -135,3 +135,56 @@ def test_convnext_encoder_restatement_matches_reference_module(golden_dir):
     # the benchmark configuration's parameter census (config_v1_cnvnxtl.json: ConvNeXt-L, 196.2 M parameters)
     n = sum(int(np.prod(s)) for s in convnext_param_shapes((3, 3, 27, 3), (192, 384, 768, 1536)).values())
     assert 196.0e6 < n < 196.5e6
+
+
+V1_CASES = ["v1_cnvnxtl_480x640", "v1_cnvnxtl_gtK_375x1242"]
+
+
+def v1_case_inputs(golden_dir, name):
+    """(config, state dict, rgb, K or None, meta, golden arrays) of one tests/golden/v1_*.npz case."""
+    from fixture import make_v1_state_dict
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    meta = json.loads(str(z["__meta__"]))
+    cfg = json.load(open(os.path.join(golden_dir, meta["config"])))
+    g = torch.Generator().manual_seed(4321 + meta["seed"])
+    b, h, w = meta["shape"]
+    rgb = torch.randint(0, 256, (b, 3, h, w), dtype=torch.uint8, generator=g)
+    K = torch.from_numpy(z["K_in"]) if meta["with_k"] else None
+    return cfg, make_v1_state_dict(cfg, meta["seed"]), rgb, K, meta, z
+
+
+@pytest.mark.parametrize("name", V1_CASES)
+def test_v1_oracle_matches_reference_golden(name, golden_dir):
+    """UniDepthV1 (ConvNeXt-L, config_v1_cnvnxtl.json) oracle vs the unmodified reference's `infer` outputs
+    (oracle/make_golden_v1.py; the one substitution -- Nystrom attention -- is described there)."""
+    import unidepth_v1_oracle as O1
+    cfg, sd, rgb, K, meta, z = v1_case_inputs(golden_dir, name)
+    out = O1.infer_v1(sd, cfg, rgb, K, skip_camera=meta["skip_camera"])
+    assert set(out) == {"intrinsics", "points", "depth"}
+    for k in ("intrinsics", "depth", "points"):
+        ref = torch.from_numpy(z[k])
+        got = out[k][:, :, ::meta["strides"]["points"], ::meta["strides"]["points"]] if k == "points" else out[k]
+        assert got.shape == ref.shape, (k, got.shape, ref.shape)
+        floor = 0.1 * ref.abs().mean().item()
+        err = ((got - ref).abs() / ref.abs().clamp(min=floor)).max().item()
+        print(k, "max rel err", err)
+        assert err < 5e-5, (k, err)
+
+
+def test_nystrom_restatement_properties():
+    """The Nystrom restatement has no reference output to be pinned to (xformers absent: "parity unpinned"), so check
+    what the published algorithm guarantees: with as many landmarks as keys it IS softmax attention, rows of the
+    reconstruction are close to exact attention for smooth inputs, and the Newton-Schulz iteration inverts a
+    well-conditioned row-stochastic matrix."""
+    import unidepth_v1_oracle as O1
+    g = torch.Generator().manual_seed(3)
+    q, k, v = (torch.randn(2, 3, 128, 64, generator=g) for _ in range(3))
+    exact = torch.softmax(q @ k.transpose(-1, -2) / 8.0, -1) @ v
+    assert torch.allclose(O1.nystrom_attention(q, k, v, 128), exact, atol=1e-6)
+    m = torch.softmax(torch.randn(4, 128, 128, generator=g) * 0.1 + 8 * torch.eye(128), -1)
+    inv = O1._iterative_pinv(m, 12)
+    assert (inv @ m - torch.eye(128)).abs().max() < 1e-3
+    # ragged segment means: 300 rows into 128 landmarks = 84 segments of 2 rows + 44 of 3
+    x = torch.arange(300.0).reshape(1, 1, 300, 1)
+    lm = O1._avg_landmarks(x, 128)[0, 0, :, 0]
+    assert lm[0] == 0.5 and lm[83] == 166.5 and lm[84] == 169.0 and lm[-1] == 298.0

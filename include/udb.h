@@ -269,6 +269,135 @@ int udb_reflect_pad1_nhwc_f16(const void* in, void* out, int32_t B, int32_t H, i
  * (the interior having been written by a GEMM with ct_pad = 1). */
 int udb_reflect_border_fill_nhwc_f16(void* buf, int32_t B, int32_t H, int32_t W, int32_t C, void* stream);
 
+/* =============================================================================================
+ * UniDepthV1 operators (ConvNeXt encoder + V1 decoder; BASELINE config 4).  Reference call sites:
+ * unidepth/models/backbones/convnext.py:130-298,459-471, unidepth/models/unidepthv1/decoder.py:38-300,
+ * unidepth/models/unidepthv1/unidepthv1.py:30-94,288-373, unidepth/layers/{convnext,upsample,nystrom_attention}.py,
+ * unidepth/utils/geometric.py:13-73,228-252, unidepth/utils/sht.py:833.  GEMM-shaped V1 work (every Linear, the stem /
+ * downsample convolutions as im2col GEMMs, 1x1 and 3x3 convolutions, the 8x64-head attention blocks) reuses
+ * udb_gemm_f16 / udb_attention_f16 above.
+ * ============================================================================================= */
+
+/* V1 pre-processing + stem im2col (unidepthv1.py:49-63,298-317; convnext.py:371-383): uint8 / f32 NCHW -> (/255) ->
+ * ImageNet normalise -> antialiased bilinear to (rh, rw) -> zero pad (pad_l, pad_t) into (net_h, net_w) -> f16 rows
+ * [B*gh*gw, 64] of the 4x4 stride-4 patches (column c*16 + py*4 + px, 48 used; gh = (net_h-4)/4+1). */
+typedef struct udb_v1_preprocess_t {
+  const void* rgb;
+  int32_t rgb_is_u8, scale255, normalize;
+  int32_t B, H, W;
+  int32_t rh, rw, pad_l, pad_t;
+  int32_t net_h, net_w;
+  void* patches;
+} udb_v1_preprocess_t;
+int udb_v1_preprocess(const udb_v1_preprocess_t* p, void* stream);
+
+/* LayerNorm over the last dim for widths that are multiples of 64 up to 1536 (ConvNeXt channel LayerNorm / LayerNorm2d,
+ * convnext.py:214,252-263; decoder LayerNorms).  in row r at in + r*ld_in (+ add[(r % add_mod)*dim ..] when add != NULL:
+ * "tokens + positional embedding", decoder.py:92-94,224).  s2d_w > 0: rows are the pixels of [B, s2d_h, s2d_w] maps and
+ * pixel (y,x) is written to row (b, y/2, x/2), columns ((y&1)*2+(x&1))*dim.. of the k2 s2 downsample's im2col matrix
+ * [B*(s2d_h/2)*(s2d_w/2), ld_out] (a trailing odd row / column is dropped, as the strided convolution drops it). */
+typedef struct udb_layernorm_any_t {
+  const void* in;
+  int32_t in_f32;
+  void* out;
+  int32_t out_f32;
+  const float* weight;
+  const float* bias;
+  int64_t rows;
+  int32_t dim;
+  int64_t ld_in, ld_out;
+  float eps;
+  const float* add;
+  int64_t add_mod;
+  int32_t s2d_h, s2d_w;
+} udb_layernorm_any_t;
+int udb_layernorm_any(const udb_layernorm_any_t* p, void* stream);
+
+/* Depthwise 7x7, zero padding 3 (convnext.py:208-211 conv_dw; layers/convnext.py:16-24 dwconv): x f16 NHWC [B,H,W,C],
+ * w f32 [49, C] (tap-major), bias f32 [C] -> y f16 NHWC.  C % 64 == 0. */
+int udb_dwconv7_nhwc_f16(const void* x, const float* w, const float* bias, void* y, int32_t B, int32_t H, int32_t W,
+                         int32_t C, void* stream);
+
+/* dst = first ? src : max(dst, src) element-wise over n f16 values (decoder.py:371-374 max_stack over a stage's blocks). */
+int udb_max_accum_f16(const void* src, void* dst, int64_t n, int32_t first, void* stream);
+
+/* Mean over the HW pixels of an f32 NHWC map -> [B, C] (ConvNeXt "cls tokens", convnext.py:471). */
+int udb_spatial_mean_f32(const float* x, float* out, int32_t B, int32_t HW, int32_t C, void* stream);
+
+/* F.interpolate(bilinear, align_corners=False, antialias=True) of an f16 NHWC map (flat_interpolate, geometric.py:228-252). */
+int udb_aa_resize_nhwc_f16(const void* in, void* out, int32_t B, int32_t H, int32_t W, int32_t C, int32_t oh, int32_t ow,
+                           void* stream);
+
+/* Ray embedding of one decoder level (decoder.py:203-220): analytic unit rays of K (intr4 = fx,fy,cx,cy per image, network
+ * resolution) antialias-averaged per token, re-normalised, 81 real spherical harmonics (sht.py:833, index l*(l+1)+m),
+ * then the projection MLP's input LayerNorm (ln_w / ln_b [81], eps 1e-5).  out f16 [B*gh*gw, 128], columns >= 81 zero.
+ * sh_k[l*9+m] = K_l^m (times sqrt(2) for m > 0). */
+typedef struct udb_v1_rays_t {
+  const float* intr4;
+  int32_t B, net_h, net_w, gh, gw;
+  const float* ln_w;
+  const float* ln_b;
+  void* out;
+  float sh_k[81];
+} udb_v1_rays_t;
+int udb_v1_rays_sh81(const udb_v1_rays_t* p, void* stream);
+
+/* Camera head tail (decoder.py:96-106,326-331; unidepthv1.py:56-62,88-91,354-356).  x4 [B,4] (may be NULL with
+ * skip_camera) -> intr4_rays [B,4]: K the decoder's rays use (prediction, or the pre-processed GT K); k_out [B,3,3]: the
+ * intrinsics returned to the caller; k4_points [B,4]: K of the final back-projection. */
+int udb_v1_camera_intrinsics(const float* x4, const float* gt_k, int32_t B, int32_t net_h, int32_t net_w, float ratio,
+                             int32_t pad_l, int32_t pad_t, int32_t skip_camera, float* intr4_rays, float* k_out,
+                             float* k4_points, void* stream);
+
+/* Single-head cross attention with a handful of queries (camera head `aggregate`, decoder.py:95): q f32 [B*nq, D]
+ * (+ q_pos [nq, D] when not NULL: the learned latents_pos, layers/attention.py:129-131; then scaled by `scale`),
+ * kv f16 [B*nk, 2D] = (k | v), out f32 [B*nq, D]. */
+int udb_cross_attn_small(const float* q, const float* q_pos, const void* kv, float* out, int32_t B, int32_t nq, int32_t nk,
+                         int32_t D, float scale, void* stream);
+
+/* p[r, j] = softmax_j(scale * s[r, j]) over j < n_valid, f32 [rows, ld_in] -> f16 [rows, ld_out], columns >= n_valid zero
+ * (the P operand of the dense single-head attentions aggregate_16 / prompt_camera, decoder.py:231-236). */
+int udb_softmax_rows(const float* s, void* p, int64_t rows, int32_t n_valid, int32_t ld_in, int32_t ld_out, float scale,
+                     void* stream);
+
+/* out = a + b (f32; out and/or an f16 copy), n % 4 == 0 (decoder.py:246-252 `latents + rays_embedding`). */
+int udb_add_f32(const float* a, const float* b, float* out, void* out_f16, int64_t n, void* stream);
+
+/* f32 [groups*rows_per_group, D] -> f16 rows (g*dst_group_stride + dst_row0 + r) of dst (decoder.py:94 torch.cat). */
+int udb_copy_rows_f32_to_f16(const float* src, void* dst, int32_t groups, int32_t rows_per_group, int32_t D,
+                             int64_t dst_group_stride, int64_t dst_row0, void* stream);
+
+/* exp(clamp(conv3x3(x; w [9, C], bias), -10, 10)) with one output channel, zero padding: x f16 NHWC -> f32 [B,H,W]
+ * (decoder.py:253,268,283,292-294 out8 / out4 / out2). */
+int udb_conv3x3_c1_exp(const void* x, const float* w, float bias, float* out, int32_t B, int32_t H, int32_t W, int32_t C,
+                       void* stream);
+
+/* Nystrom attention pieces (layers/nystrom_attention.py:22-84 -> xformers NystromAttention(num_landmarks=128); restated
+ * algorithm and its "parity unpinned" status: oracle/unidepth_v1_oracle.py).  64-wide heads.
+ * landmarks: segment means of q (qbuf [B*n, ldq]) and k (kvbuf [B*n, ldkv]) -> f16 [B*128, 2*heads*64] = (ql | kl).
+ * k2_pinv:   kernel_2 = softmax(ql kl^T / 8) -> k2 [B*heads,128,128] f32; z = its Newton-Schulz pseudo-inverse
+ *            (`iters` steps, tmp = 3 * B*heads*128*128 floats).
+ * zk3:       out[(b, lm), h*64+d] = sum_j z[b,h][lm][j] * k3[(b, j), h*64+d]   (f16 in / out). */
+int udb_nystrom_landmarks(const void* q, int32_t ldq, const void* kv, int32_t ldkv, void* out, int32_t B, int32_t n,
+                          int32_t heads, void* stream);
+int udb_nystrom_k2_pinv(const void* landmarks, float* k2, float* z, float* tmp, int32_t B, int32_t heads, int32_t iters,
+                        void* stream);
+int udb_nystrom_zk3(const float* z, const void* k3, int32_t ldk3, void* out, int32_t ldo, int32_t B, int32_t heads, void* stream);
+
+/* V1 post-processing (unidepthv1.py:66-94,352-366).  mean_maps: the three exp'ed maps (gh*2, gh*4, gh*8 grids) antialias-
+ * resized to the network shape and averaged.  postprocess: crop the paddings, antialias-resize to (H, W) -> depth; points =
+ * spherical_zbuffer_to_euclidean(theta, phi, z) with the angles of the unit ray of k4 (fx,fy,cx,cy) through each pixel. */
+int udb_v1_mean_maps(const float* o8, const float* o4, const float* o2, float* mean, int32_t B, int32_t gh, int32_t gw,
+                     int32_t net_h, int32_t net_w, void* stream);
+typedef struct udb_v1_postprocess_t {
+  const float* mean;
+  const float* k4;
+  int32_t B, net_h, net_w, pad_l, pad_r, pad_t, pad_b, H, W;
+  float* out_depth;
+  float* out_points;
+} udb_v1_postprocess_t;
+int udb_v1_postprocess(const udb_v1_postprocess_t* p, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Output assembly (unidepthv2.py:80-89, 311-339, 375-377; unidepthv2/decoder.py:456-462):
  * radius/confidence f32 [B,net_h,net_w] (already exp'ed), rays from intr4 (or rays_in) ->
@@ -381,6 +510,48 @@ typedef struct udb_infer_args_t {
 } udb_infer_args_t;
 
 int udb_infer_v2(udb_engine* e, const udb_infer_args_t* a, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * UniDepthV1 engine: the whole `UniDepthV1.infer` path (ConvNeXt encoder) as one call (SURVEY.md section 8b
+ * `udb_infer_v1`; reference unidepth/models/unidepthv1/unidepthv1.py:288-373).  Same contract as the V2 engine: the
+ * caller owns packed weights (names listed in unidepth_b200/unidepthv1.py::_pack), workspace and outputs; nothing is
+ * allocated, copied or synchronised inside udb_infer_v1.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct udb_engine_v1 udb_engine_v1;
+
+typedef struct udb_v1_config_t {
+  int32_t depths[4];      /* ConvNeXt blocks per stage (convnext_large: 3,3,27,3) */
+  int32_t dims[4];        /* stage widths (192,384,768,1536) */
+  int32_t hidden, heads, expansion;
+  int32_t dec_depths[3];  /* attention blocks at 1/16, Nystrom blocks at 1/8 and 1/4 (config pixel_decoder.depths) */
+  int32_t net_h, net_w;   /* fixed network input (config data.image_shape: 462 x 616) */
+} udb_v1_config_t;
+
+int udb_v1_create(const udb_v1_config_t* cfg, udb_engine_v1** out);
+void udb_v1_destroy(udb_engine_v1* e);
+int udb_v1_set_weight(udb_engine_v1* e, const char* name, const void* dev_ptr, const int64_t* shape, int32_t ndim,
+                      int32_t dtype);
+int udb_v1_set_scalar(udb_engine_v1* e, const char* name, double value);
+/* bytes of workspace udb_infer_v1 needs for this shape (0 + udb_last_error on failure); must be called once per
+ * (B, H, W) after the weights are registered and outside stream capture */
+size_t udb_v1_workspace_bytes(udb_engine_v1* e, int32_t B, int32_t H, int32_t W);
+
+typedef struct udb_infer_v1_args_t {
+  const void* rgb;        /* [B,3,H,W] uint8 or float32 */
+  int32_t rgb_is_u8;
+  int32_t scale255;       /* divide by 255 first (uint8, or float data with max > 5: unidepthv1.py:301-302) */
+  int32_t normalize;      /* ImageNet mean / std (data in [0,1] after the optional /255: unidepthv1.py:303-308) */
+  int32_t B, H, W;
+  const float* intrinsics; /* optional GT pinhole K [B,3,3] (original image frame) */
+  int32_t skip_camera;     /* with intrinsics: do not run the camera head, return the GT K (unidepthv1.py:336) */
+  void* workspace;
+  size_t workspace_bytes;
+  float* out_intrinsics;  /* [B,3,3] */
+  float* out_points;      /* [B,3,H,W] */
+  float* out_depth;       /* [B,1,H,W] */
+} udb_infer_v1_args_t;
+
+int udb_infer_v1(udb_engine_v1* e, const udb_infer_v1_args_t* a, void* stream);
 
 #ifdef __cplusplus
 }

@@ -39,10 +39,14 @@ def test_ctypes_structs_match_c_layout():
     structs = {"udb_gemm_t": _cabi.Gemm, "udb_conv_halo_t": _cabi.ConvHalo, "udb_attn_t": _cabi.Attn, "udb_layernorm_t": _cabi.LayerNorm,
                "udb_preprocess_t": _cabi.Preprocess, "udb_small_linear_t": _cabi.SmallLinear,
                "udb_ray_embed_t": _cabi.RayEmbed, "udb_postprocess_t": _cabi.Postprocess,
-               "udb_config_t": _cabi.Config, "udb_geometry_t": _cabi.Geometry, "udb_infer_args_t": _cabi.InferArgs}
+               "udb_config_t": _cabi.Config, "udb_geometry_t": _cabi.Geometry, "udb_infer_args_t": _cabi.InferArgs,
+               "udb_v1_preprocess_t": _cabi.V1Preprocess, "udb_layernorm_any_t": _cabi.LayerNormAny, "udb_v1_rays_t": _cabi.V1Rays,
+               "udb_v1_postprocess_t": _cabi.V1Postprocess, "udb_v1_config_t": _cabi.V1Config, "udb_infer_v1_args_t": _cabi.InferV1Args}
     last = {"udb_gemm_t": "out_split", "udb_conv_halo_t": "head_out", "udb_attn_t": "lo_off_o", "udb_layernorm_t": "out_split", "udb_preprocess_t": "split",
             "udb_small_linear_t": "ldr", "udb_ray_embed_t": "out_f32", "udb_postprocess_t": "out_rays",
-            "udb_config_t": "pixels_max", "udb_geometry_t": "factor", "udb_infer_args_t": "depth_features"}
+            "udb_config_t": "pixels_max", "udb_geometry_t": "factor", "udb_infer_args_t": "depth_features",
+            "udb_v1_preprocess_t": "patches", "udb_layernorm_any_t": "s2d_w", "udb_v1_rays_t": "sh_k", "udb_v1_postprocess_t": "out_points",
+            "udb_v1_config_t": "net_w", "udb_infer_v1_args_t": "out_depth"}
     src = '#include <stdio.h>\n#include <stddef.h>\n#include "udb.h"\nint main(){\n'
     for n in structs:
         src += f'printf("{n} %zu %zu\\n", sizeof({n}), offsetof({n}, {last[n]}));\n'
@@ -169,8 +173,11 @@ def test_hubconf_entry_point():
     for bb, d in (("vits14", 384), ("vitb14", 768), ("vitl14", 1024)):
         m = hubconf.UniDepth("v2", bb, pretrained=False)
         assert isinstance(m, UniDepthV2) and m.spec.embed_dim == d
+    from unidepth_b200 import UniDepthV1
+    m1 = hubconf.UniDepth("v1", "cnvnxtl", pretrained=False)
+    assert isinstance(m1, UniDepthV1) and m1.image_shape == [462, 616]
     with pytest.raises(NotImplementedError):
-        hubconf.UniDepth("v1", "cnvnxtl", pretrained=False)
+        hubconf.UniDepth("v1", "vitl14", pretrained=False)
     with pytest.raises(AssertionError):
         hubconf.UniDepth("v2", "resnet50", pretrained=False)
 
@@ -225,3 +232,21 @@ def test_c_example_links_and_runs_against_the_abi():
     assert "1024x1536 -> pad l0 r0 t0 b0, network 644x952 (grid 46x68)" in out
     assert "480x1600 -> pad l0 r0 t80 b80" in out and "1000x400 -> pad l50 r50 t0 b0" in out
     assert "as expected:" in out and "udb version 1" in out
+
+
+def test_v1_geometry_and_fail_loudly():
+    """V1's fixed-shape arithmetic (unidepthv1.py:30-46) against the values the reference functions produced
+    (tests/golden/v1_parts.npz), and the V1 class has no CPU path."""
+    import numpy as np
+    from unidepth_b200 import UniDepthV1
+    from unidepth_b200.spec_v1 import v1_paddings, v1_shapes
+    z = np.load(os.path.join(ROOT, "tests", "golden", "v1_parts.npz"))
+    for i, (h, w) in enumerate(z["cases"]):
+        (rh, rw), ratio = v1_shapes((int(h), int(w)), (462, 616))
+        assert [rh, rw, *v1_paddings((rh, rw), (462, 616))] == z[f"shape{i}"].tolist()
+        assert abs(ratio - float(z[f"ratio{i}"])) < 1e-12
+    cfg = json.load(open(os.path.join(ROOT, "tests", "golden", "config_v1_cnvnxtl.json")))
+    cfg["model"]["pixel_encoder"]["arch"] = {"depths": [1, 1, 1, 1], "dims": [64, 64, 64, 64]}
+    m = UniDepthV1(cfg)
+    with pytest.raises(RuntimeError):
+        m.infer(torch.zeros(3, 32, 32, dtype=torch.uint8))

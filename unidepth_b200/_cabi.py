@@ -118,6 +118,50 @@ class InferArgs(C.Structure):
     ]
 
 
+class V1Preprocess(C.Structure):
+    _fields_ = [
+        ("rgb", vp), ("rgb_is_u8", i32), ("scale255", i32), ("normalize", i32), ("B", i32), ("H", i32), ("W", i32),
+        ("rh", i32), ("rw", i32), ("pad_l", i32), ("pad_t", i32), ("net_h", i32), ("net_w", i32), ("patches", vp),
+    ]
+
+
+class LayerNormAny(C.Structure):
+    _fields_ = [
+        ("inp", vp), ("in_f32", i32), ("out", vp), ("out_f32", i32), ("weight", vp), ("bias", vp),
+        ("rows", i64), ("dim", i32), ("ld_in", i64), ("ld_out", i64), ("eps", f32), ("add", vp), ("add_mod", i64),
+        ("s2d_h", i32), ("s2d_w", i32),
+    ]
+
+
+class V1Rays(C.Structure):
+    _fields_ = [
+        ("intr4", vp), ("B", i32), ("net_h", i32), ("net_w", i32), ("gh", i32), ("gw", i32),
+        ("ln_w", vp), ("ln_b", vp), ("out", vp), ("sh_k", f32 * 81),
+    ]
+
+
+class V1Postprocess(C.Structure):
+    _fields_ = [
+        ("mean", vp), ("k4", vp), ("B", i32), ("net_h", i32), ("net_w", i32), ("pad_l", i32), ("pad_r", i32),
+        ("pad_t", i32), ("pad_b", i32), ("H", i32), ("W", i32), ("out_depth", vp), ("out_points", vp),
+    ]
+
+
+class V1Config(C.Structure):
+    _fields_ = [
+        ("depths", i32 * 4), ("dims", i32 * 4), ("hidden", i32), ("heads", i32), ("expansion", i32),
+        ("dec_depths", i32 * 3), ("net_h", i32), ("net_w", i32),
+    ]
+
+
+class InferV1Args(C.Structure):
+    _fields_ = [
+        ("rgb", vp), ("rgb_is_u8", i32), ("scale255", i32), ("normalize", i32), ("B", i32), ("H", i32), ("W", i32),
+        ("intrinsics", vp), ("skip_camera", i32), ("workspace", vp), ("workspace_bytes", C.c_size_t),
+        ("out_intrinsics", vp), ("out_points", vp), ("out_depth", vp),
+    ]
+
+
 DT_F16, DT_F32 = 0, 1
 
 EXPORTS = {
@@ -148,6 +192,31 @@ EXPORTS = {
     "udb_geometry": (i32, [vp, i32, i32, i32, C.POINTER(Geometry)]),
     "udb_workspace_bytes": (C.c_size_t, [vp, i32, i32, i32, i32]),
     "udb_infer_v2": (i32, [vp, C.POINTER(InferArgs), vp]),
+    # UniDepthV1 operators + engine
+    "udb_v1_preprocess": (i32, [C.POINTER(V1Preprocess), vp]),
+    "udb_layernorm_any": (i32, [C.POINTER(LayerNormAny), vp]),
+    "udb_dwconv7_nhwc_f16": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp]),
+    "udb_max_accum_f16": (i32, [vp, vp, i64, i32, vp]),
+    "udb_spatial_mean_f32": (i32, [vp, vp, i32, i32, i32, vp]),
+    "udb_aa_resize_nhwc_f16": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),
+    "udb_v1_rays_sh81": (i32, [C.POINTER(V1Rays), vp]),
+    "udb_v1_camera_intrinsics": (i32, [vp, vp, i32, i32, i32, f32, i32, i32, i32, vp, vp, vp, vp]),
+    "udb_cross_attn_small": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, f32, vp]),
+    "udb_softmax_rows": (i32, [vp, vp, i64, i32, i32, i32, f32, vp]),
+    "udb_add_f32": (i32, [vp, vp, vp, vp, i64, vp]),
+    "udb_copy_rows_f32_to_f16": (i32, [vp, vp, i32, i32, i32, i64, i64, vp]),
+    "udb_conv3x3_c1_exp": (i32, [vp, vp, f32, vp, i32, i32, i32, i32, vp]),
+    "udb_nystrom_landmarks": (i32, [vp, i32, vp, i32, vp, i32, i32, i32, vp]),
+    "udb_nystrom_k2_pinv": (i32, [vp, vp, vp, vp, i32, i32, i32, vp]),
+    "udb_nystrom_zk3": (i32, [vp, vp, i32, vp, i32, i32, i32, vp]),
+    "udb_v1_mean_maps": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+    "udb_v1_postprocess": (i32, [C.POINTER(V1Postprocess), vp]),
+    "udb_v1_create": (i32, [C.POINTER(V1Config), C.POINTER(vp)]),
+    "udb_v1_destroy": (None, [vp]),
+    "udb_v1_set_weight": (i32, [vp, C.c_char_p, vp, C.POINTER(i64), i32, i32]),
+    "udb_v1_set_scalar": (i32, [vp, C.c_char_p, C.c_double]),
+    "udb_v1_workspace_bytes": (C.c_size_t, [vp, i32, i32, i32]),
+    "udb_infer_v1": (i32, [vp, C.POINTER(InferV1Args), vp]),
 }
 
 _lib = None

@@ -1,11 +1,12 @@
 #!/usr/bin/env python
 """Benchmark of the UniDepthV2.infer() hot path (see BASELINE.json / SURVEY.md section 8d).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|torch-gpu] [--workload default|hires]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|torch-gpu] [--workload default|hires|v1]
 
 A "step" = one `infer` pass over one batch of synthetic uint8 RGB.  Workloads (BASELINE.json `configs`):
   default  configs[1]/[2]: ViT-L/14, 8 x 3x480x640 per GPU  (the configuration the metric is quoted on)
   hires    configs[4]:     ViT-L/14, 4 x 3x1024x1536 per GPU (infer resizes to 644x952 -> 3129 tokens)
+  v1       configs[3]:     UniDepthV1 ConvNeXt-L, 16 x 3x480x640 per GPU (fixed network shape 462x616; conv path)
 Rank 0 prints ONE JSON line.  `value` = images/s with inputs resident in HBM (whole job, max over
 ranks); `e2e` = images/s through the public API with pinned-host input -> H2D -> infer -> D2H of
 depth + intrinsics inside the timed region (`e2e_full`: D2H of the whole seven-tensor output dict).
@@ -18,6 +19,7 @@ from __future__ import annotations
 
 import argparse
 import copy
+import ctypes as C
 import json
 import os
 import subprocess
@@ -38,11 +40,28 @@ WORKLOADS = {
     "hires": dict(flops=3708.02e9, batch=4, hw=(1024, 1536),
                   desc=dict(model="UniDepthV2 ViT-L/14", batch_per_gpu=4, input="3x1024x1536 uint8", net_input="644x952 (3129 tokens)",
                             baseline_config="configs[4] (long-sequence attention)")),
+    # encoder 375.35 GF + decoder ~145 GF (the Nystrom part approximate); the line also reports
+    # the flops the launched GEMM / attention kernels declared (roofline.declared_tflop_per_step)
+    "v1": dict(flops=520.0e9, batch=16, hw=(480, 640), v1=True,
+               desc=dict(model="UniDepthV1 ConvNeXt-L", batch_per_gpu=16, input="3x480x640 uint8", net_input="462x616 (fixed)",
+                         baseline_config="configs[3] (conv path)")),
 }
 
 
-def load_config():
-    return json.load(open(os.path.join(ROOT, "tests", "golden", "config_v2_vitl14.json")))
+def load_config(workload="default"):
+    name = "config_v1_cnvnxtl.json" if WORKLOADS[workload].get("v1") else "config_v2_vitl14.json"
+    return json.load(open(os.path.join(ROOT, "tests", "golden", name)))
+
+
+def oracle_for(workload):
+    """(make_state_dict(cfg, seed), infer(sd, cfg, rgb)) of the CPU oracle for this workload."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from fixture import make_state_dict, make_v1_state_dict
+    if WORKLOADS[workload].get("v1"):
+        import unidepth_v1_oracle as O1
+        return make_v1_state_dict, lambda sd, cfg, rgb: O1.infer_v1(sd, copy.deepcopy(cfg), rgb)
+    import unidepth_oracle as O
+    return make_state_dict, lambda sd, cfg, rgb: O.infer_v2(sd, copy.deepcopy(cfg), rgb)
 
 
 def measured_peaks():
@@ -119,6 +138,8 @@ def pick_cpu_threads(fn):
 
 
 def metric_name(wl):
+    if WORKLOADS[wl].get("v1"):
+        return "images/sec UniDepthV1.infer ConvNeXt-L 480x640"
     return "images/sec UniDepthV2.infer ViT-L/14 " + ("480x640" if wl == "default" else "1024x1536")
 
 
@@ -127,27 +148,25 @@ def run_reference(args, rank, world):
     own batch size when the whole run fits ~4 minutes, else the largest batch that does (stated in `sample`)."""
     if rank != 0:
         return
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import unidepth_oracle as O
-    from fixture import make_state_dict
-    cfg = load_config()
+    make_sd, oracle_infer = oracle_for(args.workload)
+    cfg = load_config(args.workload)
     W = WORKLOADS[args.workload]
-    sd = make_state_dict(cfg, 0)
+    sd = make_sd(cfg, 0)
     g = torch.Generator().manual_seed(0)
     H, Wd = W["hw"]
     rgb = torch.randint(0, 256, (W["batch"], 3, H, Wd), dtype=torch.uint8, generator=g)
-    O.infer_v2(sd, copy.deepcopy(cfg), rgb[:1])                      # page in
-    cores, t1 = pick_cpu_threads(lambda: O.infer_v2(sd, copy.deepcopy(cfg), rgb[:1]))
+    oracle_infer(sd, cfg, rgb[:1])                      # page in
+    cores, t1 = pick_cpu_threads(lambda: oracle_infer(sd, cfg, rgb[:1]))
     steps = max(1, args.steps)
     n_warm = max(0, min(args.warmup, 1))
     budget_s = 240.0
     b = int(max(1, min(W["batch"], budget_s / (t1 * (steps + n_warm)))))
     x = rgb[:b]
     for _ in range(n_warm):
-        O.infer_v2(sd, copy.deepcopy(cfg), x)
+        oracle_infer(sd, cfg, x)
     t0 = time.perf_counter()
     for _ in range(steps):
-        O.infer_v2(sd, copy.deepcopy(cfg), x)
+        oracle_infer(sd, cfg, x)
     dt = time.perf_counter() - t0
     val = steps * b / dt
     sample = (f"{steps} steps x batch {b} of the workload's {W['batch']}-image batch, torch fp32, {cores} threads "
@@ -169,13 +188,11 @@ def run_torch_gpu(args, rank, world):
     Also reports that path's drift against the fp32 CPU forward (the declared fp16 noise floor)."""
     if rank != 0:
         return
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import unidepth_oracle as O
-    from fixture import make_state_dict
-    cfg = load_config()
+    make_sd, oracle_infer = oracle_for(args.workload)
+    cfg = load_config(args.workload)
     W = WORKLOADS[args.workload]
     dev = torch.device("cuda", 0)
-    sd = make_state_dict(cfg, 0)
+    sd = make_sd(cfg, 0)
     sd_dev = {k: v.to(dev) for k, v in sd.items()}
     g = torch.Generator().manual_seed(0)
     H, Wd = W["hw"]
@@ -185,7 +202,7 @@ def run_torch_gpu(args, rank, world):
     def step():
         # torch.device(dev): the oracle's constant tensors (mean/std, pixel grids) are created on the GPU too
         with torch.no_grad(), torch.device(dev), torch.autocast("cuda", dtype=torch.float16):
-            return O.infer_v2(sd_dev, copy.deepcopy(cfg), rgb_dev)
+            return oracle_infer(sd_dev, cfg, rgb_dev)
 
     for _ in range(max(3, args.warmup)):
         out = step()
@@ -198,7 +215,7 @@ def run_torch_gpu(args, rank, world):
     torch.cuda.synchronize()
     ms = s.elapsed_time(e)
     torch.set_num_threads(min(64, os.cpu_count()))
-    ref = O.infer_v2(sd, copy.deepcopy(cfg), rgb[:1])
+    ref = oracle_infer(sd, cfg, rgb[:1])
     d, dr = out["depth"][:1].float().cpu(), ref["depth"]
     rel = (d - dr).abs() / dr
     k, kr = out["intrinsics"][:1].float().cpu(), ref["intrinsics"]
@@ -245,16 +262,22 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    from unidepth_b200 import UniDepthV2
+    from unidepth_b200 import UniDepthV1, UniDepthV2
     from unidepth_b200 import _cabi
-    from unidepth_b200.synthetic import synthetic_state_dict
+    from unidepth_b200.synthetic import synthetic_state_dict, synthetic_state_dict_v1
     from unidepth_b200.parallel import gather_outputs
 
-    cfg = load_config()
-    model = UniDepthV2(copy.deepcopy(cfg))
-    model.load_state_dict(synthetic_state_dict(cfg, 0, device=dev), strict=True)   # same seed on every rank
-    model = model.to(dev).eval()
-    model.resolution_level = None
+    is_v1 = bool(W.get("v1"))
+    cfg = load_config(args.workload)
+    if is_v1:
+        model = UniDepthV1(copy.deepcopy(cfg))
+        model.load_state_dict(synthetic_state_dict_v1(cfg, 0, device=dev), strict=True)
+        model = model.to(dev).eval()
+    else:
+        model = UniDepthV2(copy.deepcopy(cfg))
+        model.load_state_dict(synthetic_state_dict(cfg, 0, device=dev), strict=True)   # same seed on every rank
+        model = model.to(dev).eval()
+        model.resolution_level = None
     B = args.batch or W["batch"]
     g = torch.Generator().manual_seed(rank)
     rgb_host = torch.randint(0, 256, (B, 3, H_in, W_in), dtype=torch.uint8, generator=g).pin_memory()
@@ -369,74 +392,72 @@ def main():
     flush_full[0] = False
     d2h_full_bytes = (depth_host.numel() + k_host.numel() + sum(t.numel() for t in full_host.values())) * 4
 
-    # per-kernel rooflines: instrumented eager pass (same kernels scheduled from Python so that each launch can be
-    # bracketed by CUDA events on the launching stream)
+    # per-kernel rooflines: one eager pass through the engine with the library's per-launch profile on (a CUDA event after
+    # every kernel on the launching stream, include/udb.h udb_profile_begin / udb_profile_end)
     roof = None
     if rank == 0:
-        from unidepth_b200 import ops
         model.use_cuda_graph = False
-        model.use_engine = False
-        ops.PROFILE = []
         # keep the GPU busy while the host enqueues the whole eager pass (launches + event records),
-        # so the events bracket back-to-back kernel executions, not host launch gaps
-        torch.cuda._sleep(int(0.12 * 1.9e9))
-        model.infer(rgb_dev)
+        # so consecutive events bracket back-to-back kernel executions, not host launch gaps
+        torch.cuda._sleep(int(0.15 * 1.9e9))
+        stream_ptr = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        prof = _cabi.profile(lambda: model.infer(rgb_dev), stream_ptr, cap=8192)
         torch.cuda.synchronize()
-        prof, ops.PROFILE = ops.PROFILE, None
         model.use_cuda_graph = True
-        model.use_engine = True
         agg = {}
-        for name, flops, s, e, nbytes in prof:
-            a = agg.setdefault(name, [0.0, 0.0, 0, 0.0])
+        for name, kms, flops, nbytes in prof[1:]:        # entry 0 absorbs the spin kernel's tail
+            key = "gemm_f16_kernel" if name.startswith("gemm") else name
+            a = agg.setdefault(key, [0.0, 0.0, 0, 0.0])
             a[0] += flops
-            a[1] += s.elapsed_time(e)
+            a[1] += kms
             a[2] += 1
             a[3] += nbytes
         sustained, burst, hbm, how = measured_peaks()
         tot_ms = sum(a[1] for a in agg.values())
         kern = {}
-        for k, a in agg.items():
+        for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             ent = {"launches": a[2], "ms": round(a[1], 3), "share": round(a[1] / tot_ms, 3)}
             if a[0] > 0 and a[1] > 0:
                 ent["tflops"] = round(a[0] / a[1] / 1e9, 1)
                 ent["frac_of_sustained_tensor_peak"] = round(a[0] / a[1] / 1e9 / sustained, 3)
-            if a[3] > 0 and a[1] > 0:
+            if a[3] > 0 and a[1] > 0 and not k.startswith(("gemm", "attn", "conv3x3_halo")):
                 ent["gbs"] = round(a[3] / a[1] / 1e6, 1)           # algorithmic bytes / event time
                 ent["frac_of_hbm_peak"] = round(a[3] / a[1] / 1e6 / hbm, 3)
             kern[k] = ent
-        gm = agg.get("gemm_f16_kernel", [0.0, 1.0, 1, 0.0])   # ops.py labels both GEMM kernels with this key
+        gm = agg.get("gemm_f16_kernel", [0.0, 1.0, 1, 0.0])
         ach = gm[0] / gm[1] / 1e9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "gemm_traffic.json")
         if os.path.exists(tpath) and args.workload == "default":
             traffic = json.load(open(tpath)).get("bytes_per_launch_avg")   # ncu capture of the 4 encoder GEMM flavours
-        roof = {"bound": "tensor", "kernel": "gemm_f16_kernel / gemm2_f16_kernel (linear + conv3x3 + convT launches)",
+        declared = sum(a[0] for a in agg.values())
+        roof = {"bound": "tensor", "kernel": "gemm_f16_kernel / gemm2_f16_kernel (linear + conv + convT launches)",
                 "achieved": round(ach, 1), "peak": sustained, "unit": "TFLOP/s", "frac": round(ach / sustained, 4),
                 "peak_source": f"{how} bf16_tflops_sustained (MEASURED_PEAKS.json)", "traffic": traffic,
                 "launches": gm[2], "avg_launch_us": round(1000 * gm[1] / max(gm[2], 1), 2),
                 "flops_per_launch_avg": round(gm[0] / max(gm[2], 1) / 1e9, 2),
                 "step_tflops": round(B * FLOPS_PER_IMAGE / (ms / args.steps) / 1e9, 1),
                 "step_frac": round(B * FLOPS_PER_IMAGE / (ms / args.steps) / 1e9 / sustained, 4),
+                "declared_tflop_per_step": round(declared / 1e12, 3),
+                "profiled_launches": len(prof), "profiled_ms": round(tot_ms, 3),
                 "hbm_peak_gbs": hbm, "kernels": kern}
         at = agg.get("attn_fwd_kernel")
         if at:
-            roof["attention"] = {"bound": "tensor", "kernel": "attn_fwd_kernel (encoder MHSA + decoder cross-attention)",
-                                 "achieved": round(at[0] / at[1] / 1e9, 1), "peak": sustained, "unit": "TFLOP/s",
-                                 "frac": round(at[0] / at[1] / 1e9 / sustained, 4), "launches": at[2],
-                                 "avg_launch_us": round(1000 * at[1] / at[2], 2)}
+            roof["attention"] = {"bound": "tensor", "kernel": "attn_fwd_kernel", "achieved": round(at[0] / at[1] / 1e9, 1),
+                                 "peak": sustained, "unit": "TFLOP/s", "frac": round(at[0] / at[1] / 1e9 / sustained, 4),
+                                 "launches": at[2], "avg_launch_us": round(1000 * at[1] / at[2], 2)}
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sys.path.insert(0, os.path.join(ROOT, "oracle"))
-        import unidepth_oracle as O
+        _, oracle_infer = oracle_for(args.workload)
         sd_cpu = {k: v.detach().cpu() for k, v in model.state_dict().items()}
         one = rgb_host[:1].clone()
-        O.infer_v2(sd_cpu, copy.deepcopy(cfg), one)
-        cores, _ = pick_cpu_threads(lambda: O.infer_v2(sd_cpu, copy.deepcopy(cfg), one))
-        n = 3 if args.workload == "default" else 1
+        oracle_infer(sd_cpu, cfg, one)
+        cores, _ = pick_cpu_threads(lambda: oracle_infer(sd_cpu, cfg, one))
+        n = 1 if args.workload == "hires" else 3
         t0 = time.perf_counter()
         for _ in range(n):
-            ref = O.infer_v2(sd_cpu, copy.deepcopy(cfg), one)
+            ref = oracle_infer(sd_cpu, cfg, one)
         dt = time.perf_counter() - t0
         got = model.infer(rgb_dev[:1])
         d, dr = got["depth"].cpu(), ref["depth"]
@@ -458,8 +479,8 @@ def main():
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f16 operands, f32 accumulate/residual", "data": "synthetic",
             "config": {"workload": W["desc"], "global_batch": B * world, "parallelism": f"dp{world}",
-                       "l2": "per-step working set (weights 0.7 GB + activations > 4 GB) exceeds the 126 MB L2",
-                       "cuda_graph": True, "engine": "udb_infer_v2 (one C call per infer)",
+                       "l2": "per-step working set (f16 weights 0.4-0.7 GB + activations > 4 GB) exceeds the 126 MB L2",
+                       "cuda_graph": True, "engine": ("udb_infer_v1" if is_v1 else "udb_infer_v2") + " (one C call per infer)",
                        **({"collective": parallel.gather_description()} if world > 1 else {})},
             "e2e": {"value": total_images / (ms_e2e / 1000.0), "unit": "images/s",
                     "h2d_bytes_per_step": rgb_host.numel(), "d2h_bytes_per_step": depth_host.numel() * 4 + k_host.numel() * 4,
@@ -467,7 +488,7 @@ def main():
                            "what a caller reads back); e2e_full copies the whole output dict"},
             "e2e_full": {"value": total_images / (ms_e2e_full / 1000.0), "unit": "images/s",
                          "h2d_bytes_per_step": rgb_host.numel(), "d2h_bytes_per_step": d2h_full_bytes,
-                         "d2h": "all seven output tensors of this rank's images"},
+                         "d2h": "every output tensor of this rank's images"},
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_base,
         }

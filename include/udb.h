@@ -27,6 +27,19 @@ extern "C" {
 #define UDB_VERSION 1
 
 int udb_version(void);
+
+/* Per-launch profile: between begin and end every kernel this library enqueues on `stream` is followed by a CUDA event;
+ * end synchronises and returns, per launch in order, the kernel's name, the time since the previous event (its duration
+ * when the stream stays busy) and the algorithmic flops / bytes its launcher declared.  Returns the number of launches
+ * (which may exceed cap; only the first cap entries are written), -1 on error.  Not for use under stream capture. */
+typedef struct udb_profile_entry_t {
+  char name[48];
+  float ms;
+  double flops;
+  double bytes;
+} udb_profile_entry_t;
+int udb_profile_begin(void* stream);
+int udb_profile_end(udb_profile_entry_t* out, int32_t cap);
 const char* udb_last_error(void);
 /* Number of kernels launched by this library on the calling process since load (bench evidence). */
 int64_t udb_launch_count(void);

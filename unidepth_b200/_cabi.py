@@ -162,12 +162,18 @@ class InferV1Args(C.Structure):
     ]
 
 
+class ProfileEntry(C.Structure):
+    _fields_ = [("name", C.c_char * 48), ("ms", f32), ("flops", C.c_double), ("bytes", C.c_double)]
+
+
 DT_F16, DT_F32 = 0, 1
 
 EXPORTS = {
     "udb_version": (i32, []),
     "udb_last_error": (C.c_char_p, []),
     "udb_launch_count": (i64, []),
+    "udb_profile_begin": (i32, [vp]),
+    "udb_profile_end": (i32, [C.POINTER(ProfileEntry), i32]),
     "udb_gemm_f16": (i32, [C.POINTER(Gemm), vp]),
     "udb_conv3x3_halo_f16": (i32, [C.POINTER(ConvHalo), vp]),
     "udb_attention_f16": (i32, [C.POINTER(Attn), vp]),
@@ -244,6 +250,20 @@ def lib():
 def check(rc: int, what: str):
     if rc != 0:
         raise RuntimeError(f"{what} failed: {lib().udb_last_error().decode()}")
+
+
+def profile(fn, stream_ptr, cap: int = 4096):
+    """Run fn() between udb_profile_begin / udb_profile_end on the given stream; returns [(kernel, ms, flops, bytes)]."""
+    l = lib()
+    check(l.udb_profile_begin(stream_ptr), "udb_profile_begin")
+    try:
+        fn()
+    finally:
+        buf = (ProfileEntry * cap)()
+        n = l.udb_profile_end(buf, cap)
+    if n < 0:
+        raise RuntimeError(f"udb_profile_end failed: {l.udb_last_error().decode()}")
+    return [(buf[i].name.decode(), buf[i].ms, buf[i].flops, buf[i].bytes) for i in range(min(n, cap))]
 
 
 def launch_count() -> int:

@@ -4,6 +4,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <vector>
+
 namespace udb {
 
 static thread_local char g_err[512] = "";
@@ -14,6 +16,38 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+// ---- per-launch profile (off unless udb_profile_begin was called)
+struct ProfEntry {
+  const char* name;
+  cudaEvent_t ev;
+  double flops, bytes;
+};
+static std::vector<ProfEntry> g_prof;
+static bool g_prof_on = false;
+static cudaStream_t g_prof_stream = nullptr;
+static cudaEvent_t g_prof_start = nullptr;
+static thread_local double g_flops = 0.0, g_bytes = 0.0;
+
+void note_work(double flops, double bytes) {
+  g_flops = flops;
+  g_bytes = bytes;
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return 1;
+  }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (g_prof_on) {
+    ProfEntry pe{what, nullptr, g_flops, g_bytes};
+    if (cudaEventCreate(&pe.ev) == cudaSuccess && cudaEventRecord(pe.ev, g_prof_stream) == cudaSuccess) g_prof.push_back(pe);
+  }
+  g_flops = g_bytes = 0.0;
+  return 0;
 }
 
 int num_sms() {
@@ -100,4 +134,44 @@ extern "C" {
 int udb_version(void) { return UDB_VERSION; }
 const char* udb_last_error(void) { return udb::g_err; }
 int64_t udb_launch_count(void) { return udb::g_launches.load(); }
+
+int udb_profile_begin(void* stream) {
+  using namespace udb;
+  if (g_prof_on) { set_error("udb_profile_begin: already profiling"); return 1; }
+  g_prof.clear();
+  g_prof_stream = reinterpret_cast<cudaStream_t>(stream);
+  if (cudaEventCreate(&g_prof_start) != cudaSuccess || cudaEventRecord(g_prof_start, g_prof_stream) != cudaSuccess) {
+    set_error("udb_profile_begin: event creation failed");
+    return 1;
+  }
+  g_prof_on = true;
+  return 0;
+}
+
+int udb_profile_end(udb_profile_entry_t* out, int32_t cap) {
+  using namespace udb;
+  if (!g_prof_on) { set_error("udb_profile_end: not profiling"); return -1; }
+  g_prof_on = false;
+  cudaStreamSynchronize(g_prof_stream);
+  cudaEvent_t prev = g_prof_start;
+  int n = 0;
+  for (auto& pe : g_prof) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, prev, pe.ev);
+    if (out && n < cap) {
+      strncpy(out[n].name, pe.name, sizeof(out[n].name) - 1);
+      out[n].name[sizeof(out[n].name) - 1] = 0;
+      out[n].ms = ms;
+      out[n].flops = pe.flops;
+      out[n].bytes = pe.bytes;
+    }
+    ++n;
+    if (prev != g_prof_start) cudaEventDestroy(prev);
+    prev = pe.ev;
+  }
+  if (prev != g_prof_start) cudaEventDestroy(prev);
+  cudaEventDestroy(g_prof_start);
+  g_prof.clear();
+  return n;
+}
 }

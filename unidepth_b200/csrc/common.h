@@ -14,15 +14,11 @@ namespace udb {
 void set_error(const char* fmt, ...);
 extern std::atomic<int64_t> g_launches;
 
-inline int check_launch(const char* what) {
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) {
-    set_error("%s: %s", what, cudaGetErrorString(e));
-    return 1;
-  }
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  return 0;
-}
+// Called after every kernel launch of this library: error check, launch counting and -- between udb_profile_begin /
+// udb_profile_end -- a CUDA event per launch so that per-kernel durations can be read back (bench.py's rooflines).
+int check_launch(const char* what);
+// Algorithmic work of the launch that follows (consumed by its check_launch): flops and bytes moved, for the profile.
+void note_work(double flops, double bytes);
 
 int num_sms();   // of the CURRENT device (cached per device)
 

@@ -207,6 +207,7 @@ static int launch_halo(const CUtensorMap& tx, const CUtensorMap& tw, const HaloA
     set_for[dev & 63].store(smem);
   }
   const int grid = a.num_tiles < num_sms() ? a.num_tiles : num_sms();
+  note_work(2.0 * a.B * (double)a.H * a.W * COUT * 9 * 64 * a.slabs, 0.0);
   cudaError_t e = launch_ex(conv3x3_halo_kernel<COUT>, dim3(grid), dim3(HC_THREADS), smem, st, 1, tx, tw, a);
   if (e != cudaSuccess) { set_error("conv3x3_halo_kernel launch: %s", cudaGetErrorString(e)); return 1; }
   return check_launch("conv3x3_halo_kernel");

@@ -563,6 +563,7 @@ using namespace udb;
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
 
 extern "C" int udb_layernorm(const udb_layernorm_t* p, void* stream) {
+  note_work(0.0, (double)p->rows * p->dim * ((p->in_f32 ? 4 : 2) + (p->out_f32 ? 4 : 2) + (p->out_split ? 2 : 0)));
   if (p->dim_valid < 0 || p->dim_valid > p->dim || p->dim_valid % 8) {
     set_error("udb_layernorm: dim_valid %d must be a multiple of 8 in [0, dim]", p->dim_valid);
     return 1;
@@ -613,6 +614,7 @@ extern "C" int udb_preprocess_patchify(const udb_preprocess_t* p, void* stream) 
   const int padded_h = p->H + p->pad_t + p->pad_b, padded_w = p->W + p->pad_l + p->pad_r;
   const float sh = (float)padded_h / (float)p->net_h, sw = (float)padded_w / (float)p->net_w;
   const long long total = (long long)p->B * gh * gw * (p->ldp / 8);
+  note_work(0.0, (double)p->B * 3 * p->H * p->W * (p->rgb_is_u8 ? 1 : 4) + (double)p->B * gh * gw * p->ldp * 2);
   preprocess_patchify_kernel<<<grid_for(total), 256, 0, ST(stream)>>>(*p, gh, gw, sh, sw);
   return check_launch("preprocess_patchify_kernel");
 }
@@ -668,6 +670,7 @@ extern "C" int udb_camera_adjust_k(const float* K, int32_t B, float factor, int3
 
 extern "C" int udb_ray_embed(const udb_ray_embed_t* p, void* stream) {
   const int toks = p->B * p->gh * p->gw;
+  note_work(0.0, (double)toks * 2 * p->bands * (p->out_f32 ? 4 : 2));
   ray_embed_kernel<<<(toks + 7) / 8, 256, 0, ST(stream)>>>(*p);
   return check_launch("ray_embed_kernel");
 }
@@ -675,6 +678,7 @@ extern "C" int udb_ray_embed(const udb_ray_embed_t* p, void* stream) {
 extern "C" int udb_upsample2x_nhwc_f16(const void* in, void* out, int32_t B, int32_t H, int32_t W, int32_t C, void* stream) {
   if (C % 8) { set_error("udb_upsample2x_nhwc_f16: C %% 8 != 0"); return 1; }
   dim3 grid((2 * W * (C / 8) + 255) / 256, 2 * H, B);
+  note_work(0.0, 2.0 * B * H * W * C * 5);
   upsample2x_kernel<<<grid, 256, 0, ST(stream)>>>(reinterpret_cast<const __half*>(in), reinterpret_cast<__half*>(out), H, W, C);
   return check_launch("upsample2x_kernel");
 }
@@ -685,6 +689,7 @@ extern "C" int udb_resize_ac_pad_nhwc_f16(const void* in, void* out, int32_t B, 
   const float sh = (oh > 1) ? (float)(H - 1) / (float)(oh - 1) : 0.f;
   const float sw = (ow > 1) ? (float)(W - 1) / (float)(ow - 1) : 0.f;
   dim3 grid(((ow + 2 * pad) * (C / 8) + 255) / 256, oh + 2 * pad, B);
+  note_work(0.0, 2.0 * B * C * ((double)H * W + (double)(oh + 2 * pad) * (ow + 2 * pad)));
   resize_ac_pad_kernel<<<grid, 256, 0, ST(stream)>>>(reinterpret_cast<const __half*>(in), reinterpret_cast<__half*>(out), H, W, C, oh, ow, pad, sh, sw);
   return check_launch("resize_ac_pad_kernel");
 }
@@ -704,6 +709,7 @@ extern "C" int udb_reflect_border_fill_nhwc_f16(void* buf, int32_t B, int32_t H,
 }
 
 extern "C" int udb_postprocess(const udb_postprocess_t* p, void* stream) {
+  note_work(0.0, 4.0 * p->B * (2.0 * p->net_h * p->net_w + 9.0 * p->H * p->W));
   postprocess_kernel<<<grid_for((long long)p->B * p->H * p->W), 256, 0, ST(stream)>>>(*p);
   return check_launch("postprocess_kernel");
 }

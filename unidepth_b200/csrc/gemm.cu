@@ -749,6 +749,9 @@ extern "C" int udb_gemm_f16(const udb_gemm_t* g, void* stream) {
     if (make_tmap_f16(&tmB, g->w, 2, dims, str, box, true)) return 1;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  note_work(2.0 * a.M * (double)g->N * g->K,
+            2.0 * ((double)a.M * (g->a_mode == UDB_A_CONV3X3 ? g->conv_C : (g->a_split_k ? 2 * g->a_split_k : g->K)) + (double)g->N * g->K) +
+                (double)a.M * g->N * ((g->out ? (g->out_f32 ? 4 : 2) : 0) + (g->out2 ? 2 : 0) + (g->resid ? (g->resid_f32 ? 4 : 2) : 0)));
   if (use_pair) {
     return bn == 256 ? launch_gemm2<256>(tmA, tmB, a, st) : launch_gemm2<128>(tmA, tmB, a, st);
   }

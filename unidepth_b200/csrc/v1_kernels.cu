@@ -734,6 +734,7 @@ int udb_layernorm_any(const udb_layernorm_any_t* p, void* stream) {
   if (p->dim % 64 || p->dim > 1536 || p->dim <= 0) { set_error("udb_layernorm_any: dim %d unsupported (multiple of 64, <= 1536)", p->dim); return 1; }
   if (p->rows <= 0) return 0;
   const int grid = (int)((p->rows + 7) / 8);
+  note_work(0.0, (double)p->rows * p->dim * ((p->in_f32 ? 4 : 2) + (p->out_f32 ? 4 : 2)));
   if (p->in_f32 && p->out_f32) layernorm_any_kernel<true, true><<<grid, 256, 0, ST(stream)>>>(*p);
   else if (p->in_f32) layernorm_any_kernel<true, false><<<grid, 256, 0, ST(stream)>>>(*p);
   else if (p->out_f32) layernorm_any_kernel<false, true><<<grid, 256, 0, ST(stream)>>>(*p);
@@ -745,12 +746,14 @@ int udb_dwconv7_nhwc_f16(const void* x, const float* w, const float* bias, void*
   if (C % DW_CB) { set_error("udb_dwconv7_nhwc_f16: C=%d must be a multiple of 64", C); return 1; }
   const int tx = (W + DW_TW - 1) / DW_TW, ty = (H + DW_TH - 1) / DW_TH;
   dim3 grid(tx * ty, C / DW_CB, B);
+  note_work(2.0 * 49 * B * H * W * C, 4.0 * B * H * W * C);
   dwconv7_kernel<<<grid, 256, 0, ST(stream)>>>(reinterpret_cast<const __half*>(x), w, bias, reinterpret_cast<__half*>(y), H, W, C, tx);
   return check_launch("dwconv7_kernel");
 }
 
 int udb_max_accum_f16(const void* src, void* dst, int64_t n, int32_t first, void* stream) {
   if (n % 8) { set_error("udb_max_accum_f16: n must be a multiple of 8"); return 1; }
+  note_work(0.0, (first ? 4.0 : 6.0) * n);
   max_accum_kernel<<<grid_1d(n / 8), 256, 0, ST(stream)>>>(reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst), n / 8, first);
   return check_launch("max_accum_kernel");
 }
@@ -763,6 +766,7 @@ int udb_spatial_mean_f32(const float* x, float* out, int32_t B, int32_t HW, int3
 
 int udb_aa_resize_nhwc_f16(const void* in, void* out, int32_t B, int32_t H, int32_t W, int32_t C, int32_t oh, int32_t ow, void* stream) {
   if (C % 8) { set_error("udb_aa_resize_nhwc_f16: C must be a multiple of 8"); return 1; }
+  note_work(0.0, 2.0 * B * C * ((double)H * W + (double)oh * ow));
   aa_resize_nhwc_kernel<<<grid_1d((long long)B * oh * ow * (C / 8)), 256, 0, ST(stream)>>>(
       reinterpret_cast<const __half*>(in), reinterpret_cast<__half*>(out), B, H, W, C, oh, ow, (float)H / (float)oh, (float)W / (float)ow);
   return check_launch("aa_resize_nhwc_kernel");
@@ -805,6 +809,7 @@ int udb_softmax_rows(const float* s, void* p, int64_t rows, int32_t n_valid, int
 
 int udb_add_f32(const float* a, const float* b, float* out, void* out_f16, int64_t n, void* stream) {
   if (n % 4) { set_error("udb_add_f32: n must be a multiple of 4"); return 1; }
+  note_work(0.0, (8.0 + (out ? 4.0 : 0.0) + (out_f16 ? 2.0 : 0.0)) * n);
   add_f32_kernel<<<grid_1d(n / 4), 256, 0, ST(stream)>>>(reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b),
                                                          reinterpret_cast<float4*>(out), reinterpret_cast<uint2*>(out_f16), n / 4);
   return check_launch("add_f32_kernel");

@@ -12,6 +12,11 @@ import torch.distributed as dist
 _KEYS = ("confidence", "intrinsics", "radius", "depth", "points", "rays", "depth_features")
 
 
+def _keys(out):
+    """Packing order: UniDepthV2's seven outputs, or the subset a model returns (UniDepthV1: intrinsics, depth, points)."""
+    return [k for k in _KEYS if k in out]
+
+
 def shard_bounds(n_images: int, rank: int, world: int):
     """Contiguous slice [lo, hi) of the global batch owned by `rank` (remainder to low ranks)."""
     base, rem = divmod(n_images, world)
@@ -22,13 +27,13 @@ def shard_bounds(n_images: int, rank: int, world: int):
 def pack_outputs(out: Dict[str, torch.Tensor]) -> torch.Tensor:
     """Flatten the per-image outputs of one rank into one contiguous f32 buffer [B, F]."""
     b = out["depth"].shape[0]
-    return torch.cat([out[k].reshape(b, -1).float() for k in _KEYS], dim=1).contiguous()
+    return torch.cat([out[k].reshape(b, -1).float() for k in _keys(out)], dim=1).contiguous()
 
 
 def unpack_outputs(buf: torch.Tensor, like: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
     res, off = {}, 0
     n = buf.shape[0]
-    for k in _KEYS:
+    for k in _keys(like):
         shp = like[k].shape[1:]
         cnt = 1
         for s in shp:
@@ -93,7 +98,7 @@ class P2PGather:
         if self.last[slot] is not None:
             cur.wait_event(self.last[slot])            # every peer has pulled the previous content
         b = out["depth"].shape[0]
-        torch.cat([out[k].reshape(b, -1) for k in _KEYS], dim=1, out=self.send[slot])
+        torch.cat([out[k].reshape(b, -1) for k in _keys(out)], dim=1, out=self.send[slot])
         full = torch.empty((self.world * b, self.shape[1]), device=self.send[slot].device, dtype=torch.float32)
         hdl = self.hdl[slot]
         self.stream.wait_stream(cur)
@@ -108,7 +113,7 @@ class P2PGather:
         # no full.record_stream(): PendingOutputs keeps `full` alive and its wait() orders the consumer
         # stream after the side stream, so the block is never freed with side-stream work pending
         self.last[slot] = ev
-        shapes = {k: torch.empty((0,) + tuple(out[k].shape[1:]), device="meta") for k in _KEYS}
+        shapes = {k: torch.empty((0,) + tuple(out[k].shape[1:]), device="meta") for k in _keys(out)}
         return PendingOutputs(None, full, None, shapes, event=ev)
 
 
@@ -140,7 +145,7 @@ def p2p_gather_for(out: Dict[str, torch.Tensor], group=None):
     if gather_mode() != "p2p" or _p2p_failed[0] is not None or not out["depth"].is_cuda:
         return None
     b = out["depth"].shape[0]
-    feat = sum(out[k][0].numel() for k in _KEYS)
+    feat = sum(out[k][0].numel() for k in _keys(out))
     key = (b, feat, out["depth"].device.index)
     if key not in _p2p_cache:
         try:
@@ -179,7 +184,7 @@ def gather_outputs(out: Dict[str, torch.Tensor], world: int, group=None, async_o
     local = pack_outputs(out)
     full = torch.empty((world * local.shape[0], local.shape[1]), device=local.device, dtype=local.dtype)
     work = dist.all_gather_into_tensor(full, local, group=group, async_op=True)
-    shapes = {k: torch.empty((0,) + tuple(out[k].shape[1:]), device="meta") for k in _KEYS}
+    shapes = {k: torch.empty((0,) + tuple(out[k].shape[1:]), device="meta") for k in _keys(out)}
     pending = PendingOutputs(work, full, local, shapes)
     return pending if async_op else pending.wait()
 

@@ -291,8 +291,18 @@ def main():
     from unidepth_b200 import parallel
     pipelined = world > 1 and parallel.gather_mode() != "nccl"
 
+    last_out = {"v": None}
+
+    def infer_into_slot(x):
+        # N > 1 with the peer-memory gather: outputs go straight into the send slot (no clone, no pack)
+        if world > 1 and pipelined and last_out["v"] is not None:
+            model.output_buffers = parallel.output_views(last_out["v"])
+        out = model.infer(x)
+        last_out["v"] = out
+        return out
+
     def step_device():
-        out = model.infer(rgb_dev)
+        out = infer_into_slot(rgb_dev)
         if world > 1 and pipelined:
             nxt = gather_outputs(out, world, async_op=True)
             if pending["dev"] is not None:
@@ -321,7 +331,7 @@ def main():
     def make_e2e(full):
         def step_e2e():
             x = rgb_host.to(dev, non_blocking=True)
-            out = model.infer(x)
+            out = infer_into_slot(x)
             if world > 1 and pipelined:
                 nxt = gather_outputs(out, world, async_op=True)
                 if pending["e2e"] is not None:
@@ -405,7 +415,7 @@ def main():
         torch.cuda.synchronize()
         model.use_cuda_graph = True
         agg = {}
-        for name, kms, flops, nbytes in prof[1:]:        # entry 0 absorbs the spin kernel's tail
+        for name, kms, flops, nbytes in prof:            # the profile's start event fires when the spin kernel ends
             key = "gemm_f16_kernel" if name.startswith("gemm") else name
             a = agg.setdefault(key, [0.0, 0.0, 0, 0.0])
             a[0] += flops

@@ -566,6 +566,21 @@ typedef struct udb_infer_v1_args_t {
 
 int udb_infer_v1(udb_engine_v1* e, const udb_infer_v1_args_t* a, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Peer-memory plumbing of the multi-GPU output gather (one process per GPU on one node).
+ * alloc: device buffer (zero-filled) + its 64-byte CUDA IPC handle, to be exchanged out of band (torch.distributed);
+ * open: map a peer's buffer; barrier: device-side barrier over flags in peer memory (flag arrays of `world` uint32,
+ * peer_flags_dev = device array of the ranks' flag-array pointers as mapped HERE; epochs only grow; a missing peer sets
+ * *timeout_flag_dev instead of hanging); copy: copy-engine device-to-device copy (no SM involved).
+ * ------------------------------------------------------------------------------------------- */
+int udb_p2p_alloc(size_t bytes, void** dev_ptr, void* handle64);
+int udb_p2p_open(const void* handle64, void** peer_ptr);
+int udb_p2p_close(void* peer_ptr);
+int udb_p2p_free(void* dev_ptr);
+int udb_p2p_barrier(void* const* peer_flags_dev, void* my_flags, int32_t rank, int32_t world, uint32_t epoch,
+                    int32_t* timeout_flag_dev, void* stream);
+int udb_p2p_copy(void* dst, const void* src, size_t bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

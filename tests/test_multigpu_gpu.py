@@ -1,5 +1,6 @@
-"""Image-wise data-parallel infer on 2 GPUs (torchrun, NCCL): the gathered dict must equal the
-single-GPU dict bit for bit (no cross-image op on the path).  Skipped with fewer than 2 GPUs."""
+"""Image-wise data-parallel infer on 2 GPUs (torchrun): the gathered dict must equal the single-GPU dict bit for bit
+(no cross-image op on the path), with the default peer-memory gather (copy-engine pulls over CUDA-IPC buffers, outputs
+written straight into the send slot) and with the NCCL fallback.  Skipped with fewer than 2 GPUs."""
 import os
 import subprocess
 import sys
@@ -15,7 +16,8 @@ import copy, json, os, sys
 sys.path[:0] = [sys.argv[1], os.path.join(sys.argv[1], "oracle")]
 import torch, torch.distributed as dist
 from unidepth_b200 import UniDepthV2
-from unidepth_b200.parallel import infer_sharded
+from unidepth_b200 import parallel
+from unidepth_b200.parallel import infer_sharded, shard_bounds
 from unidepth_b200.synthetic import synthetic_state_dict
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
@@ -39,19 +41,35 @@ pend = [infer_sharded(m, rgb, async_op=True) for _ in range(3)]
 for p in pend:
     got = p.wait()
     ok &= all(torch.equal(got[k].float(), single[k].float()) for k in single)
-print(f"rank {rank}: gathered == single-GPU: {ok}", flush=True)
+# outputs produced straight into the send slot (model.output_buffers = the slot's views): no staging copy
+lo, hi = shard_bounds(4, rank, world)
+loc = m.infer(rgb[lo:hi])
+in_slot = 0
+for _ in range(3):
+    m.output_buffers = parallel.output_views(loc)
+    in_slot += m.output_buffers is not None
+    got = infer_sharded(m, rgb)
+    ok &= all(torch.equal(got[k].float(), single[k].float()) for k in single)
+m.output_buffers = None
+mode = parallel.gather_mode()
+if mode == "p2p":
+    ok &= parallel._p2p_failed[0] is None and len(parallel._p2p_cache) > 0 and in_slot == 3
+    ok &= all(not pg.timed_out() for pg in parallel._p2p_cache.values())
+print(f"rank {rank}: mode {mode} (p2p objects {len(parallel._p2p_cache)}, failure {parallel._p2p_failed[0]}), "
+      f"gathered == single-GPU: {ok}", flush=True)
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
 """
 
 
-def test_two_gpu_gather_equals_single_gpu(tmp_path):
+@pytest.mark.parametrize("mode", ["p2p", "nccl"])
+def test_two_gpu_gather_equals_single_gpu(tmp_path, mode):
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", "29611", str(script), ROOT]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+           "--master-port", "29611" if mode == "p2p" else "29612", str(script), ROOT]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env={**os.environ, "UDB_GATHER": mode})
     print(out.stdout[-2000:], out.stderr[-2000:])
     assert out.returncode == 0

@@ -21,8 +21,8 @@ for r in rows[1:]:
     t[1] += 1
     seq.append((name, us))
 total = sum(t[0] for t in tot.values())
-print("ncu --metrics gpu__time_duration.sum --clock-control none, one eager infer step, ViT-L/14, 8 x 3x480x640 "
-      "(tools/profile_step.py)")
+print("ncu --metrics gpu__time_duration.sum --clock-control none, one eager infer step (tools/profile_step.py"
+      + (" " + " ".join(sys.argv[2:]) if len(sys.argv) > 2 else "") + ")")
 print(f"total {total:.1f} us over {len(seq)} launches (cold-cache, serialised: compare shares)")
 for name, (us, n) in sorted(tot.items(), key=lambda kv: -kv[1][0]):
     print(f"{us:10.1f} us {100 * us / total:5.1f}% x{n:4d}  {name}")
@@ -30,4 +30,8 @@ first = next((i for i, (n, _) in enumerate(seq) if n.startswith("void attn_fwd")
 if first is not None:
     print("first encoder block:")
     for n, us in seq[max(0, first - 2):first + 5]:
+        print(f"{us:11.1f} us  {n}")
+if len(sys.argv) > 2 and sys.argv[-1] == "--seq":
+    print("launch sequence:")
+    for n, us in seq:
         print(f"{us:11.1f} us  {n}")

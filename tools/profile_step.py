@@ -14,17 +14,25 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
-from unidepth_b200 import UniDepthV2  # noqa: E402
-from unidepth_b200.synthetic import synthetic_state_dict  # noqa: E402
+from unidepth_b200 import UniDepthV1, UniDepthV2  # noqa: E402
+from unidepth_b200.synthetic import synthetic_state_dict, synthetic_state_dict_v1  # noqa: E402
 
 warnings.simplefilter("ignore")
-B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
-cfg = json.load(open(os.path.join(ROOT, "tests", "golden", "config_v2_vitl14.json")))
-model = UniDepthV2(copy.deepcopy(cfg))
-model.load_state_dict(synthetic_state_dict(cfg, 0, device="cuda"), strict=True)
+# usage: profile_step.py [batch] [default|hires|v1]
+WL = sys.argv[2] if len(sys.argv) > 2 else "default"
+B = int(sys.argv[1]) if len(sys.argv) > 1 else {"default": 8, "hires": 4, "v1": 16}[WL]
+H, W = (1024, 1536) if WL == "hires" else (480, 640)
+if WL == "v1":
+    cfg = json.load(open(os.path.join(ROOT, "tests", "golden", "config_v1_cnvnxtl.json")))
+    model = UniDepthV1(copy.deepcopy(cfg))
+    model.load_state_dict(synthetic_state_dict_v1(cfg, 0, device="cuda"), strict=True)
+else:
+    cfg = json.load(open(os.path.join(ROOT, "tests", "golden", "config_v2_vitl14.json")))
+    model = UniDepthV2(copy.deepcopy(cfg))
+    model.load_state_dict(synthetic_state_dict(cfg, 0, device="cuda"), strict=True)
 model = model.to("cuda").eval()
 model.use_cuda_graph = False
-rgb = torch.randint(0, 256, (B, 3, 480, 640), dtype=torch.uint8, device="cuda")
+rgb = torch.randint(0, 256, (B, 3, H, W), dtype=torch.uint8, device="cuda")
 model.infer(rgb)
 torch.cuda.synchronize()
 torch.cuda.cudart().cudaProfilerStart()

@@ -223,6 +223,13 @@ EXPORTS = {
     "udb_v1_set_scalar": (i32, [vp, C.c_char_p, C.c_double]),
     "udb_v1_workspace_bytes": (C.c_size_t, [vp, i32, i32, i32]),
     "udb_infer_v1": (i32, [vp, C.POINTER(InferV1Args), vp]),
+    # peer-memory plumbing (multi-GPU gather)
+    "udb_p2p_alloc": (i32, [C.c_size_t, C.POINTER(vp), vp]),
+    "udb_p2p_open": (i32, [vp, C.POINTER(vp)]),
+    "udb_p2p_close": (i32, [vp]),
+    "udb_p2p_free": (i32, [vp]),
+    "udb_p2p_barrier": (i32, [vp, vp, i32, i32, C.c_uint32, vp, vp]),
+    "udb_p2p_copy": (i32, [vp, vp, C.c_size_t, vp]),
 }
 
 _lib = None

@@ -65,95 +65,176 @@ class PendingOutputs:
         if self._event is not None:
             torch.cuda.current_stream().wait_event(self._event)
             self._event = None
+        if isinstance(self._full, dict):      # PeerGather: already one tensor per key
+            return self._full
         return unpack_outputs(self._full, self._shapes)
 
 
-class P2PGather:
-    """All-gather of the packed outputs over NVLink peer memory with the COPY ENGINES: every rank packs
-    into a buffer that all peers have mapped (torch symmetric memory), a device-side barrier, then each
-    rank pulls the other ranks' buffers with plain device-to-device copies on a side stream.  No SM is
-    used by the transfer, which matters here: the GEMM kernels are persistent with one CTA per SM, so
-    an overlapping NCCL kernel that occupies even a few SMs stalls whole tile columns (measured at N=2:
-    in-flight NCCL all-gather 18.6 ms/step vs 18.0 ms compute alone).  Send buffers rotate (depth 2)."""
+class _DevView:
+    """Exposes a raw device pointer to torch through the CUDA array interface (no copy, no ownership)."""
 
-    def __init__(self, batch: int, feat: int, device, group=None, depth: int = 2):
-        import torch.distributed._symmetric_memory as symm_mem
+    def __init__(self, ptr: int, shape, typestr: str = "<f4"):
+        self.__cuda_array_interface__ = dict(shape=tuple(int(s) for s in shape), typestr=typestr, data=(int(ptr), False), version=3,
+                                             strides=None)
+
+
+class PeerGather:
+    """All-gather of the per-rank outputs over NVLink peer memory with the COPY ENGINES (include/udb.h `udb_p2p_*`):
+    every rank owns `depth` send slots in a cudaMalloc'ed buffer whose CUDA-IPC handle its peers have opened; a step is
+    (device-side barrier: all slots written) -> each rank pulls every peer's slot, key by key, straight into the final
+    per-key output tensors [world*B, ...] with plain device-to-device copies on a side stream -> (barrier: slot reusable).
+    No SM moves data and nothing is packed or unpacked: `views()` hands out tensors that alias the next slot, so `infer`
+    can write its outputs directly into it (UniDepthV2.output_buffers).  This matters here because the GEMM kernels are
+    persistent with one CTA per SM: a collective kernel that occupies even a few SMs stalls whole tile columns (measured:
+    in-flight NCCL all-gather 18.6 ms/step vs 18.0 ms compute alone at N=2)."""
+
+    def __init__(self, out_like: Dict[str, torch.Tensor], device, group=None, depth: int = 2):
+        import ctypes as C
+        from . import _cabi as cabi
+        self.cabi, self.C = cabi, C
         self.group = group if group is not None else dist.group.WORLD
         self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
-        self.shape = (batch, feat)
-        # NOT symm_mem.empty(): that allocates through an implicit torch.cuda.MemPool, and graphs captured
-        # afterwards then corrupt the memory of graphs captured before (observed: wrong replays of an
-        # older CUDA graph after a new capture); the plain p2p allocation has no such side effect
-        self.send = [symm_mem._SymmetricMemory.empty_strided_p2p((batch, feat), (feat, 1), torch.float32,
-                                                                 torch.device(device)) for _ in range(depth)]
-        self.hdl = [symm_mem.rendezvous(t, self.group) for t in self.send]
-        self.stream = torch.cuda.Stream(device=device)
-        self.last = [None] * depth      # event after which slot i may be overwritten
+        self.device = torch.device(device)
+        self.keys = _keys(out_like)
+        self.shapes = {k: tuple(out_like[k].shape) for k in self.keys}
+        self.batch = self.shapes[self.keys[0]][0]
+        self.offs, off = {}, 0
+        for k in self.keys:
+            self.offs[k] = off
+            n = 1
+            for d in self.shapes[k]:
+                n *= d
+            off += (n * 4 + 255) // 256 * 256          # bytes, every key 256-byte aligned inside a slot
+        self.slot_bytes = off
+        self.depth = depth
+        self.flags_off = depth * self.slot_bytes
+        total = self.flags_off + 1024                   # [world] uint32 flags + a timeout word at +512
+        lib = cabi.lib()
+        base, handle = C.c_void_p(), (C.c_char * 64)()
+        with torch.cuda.device(self.device):
+            cabi.check(lib.udb_p2p_alloc(total, C.byref(base), handle), "udb_p2p_alloc")
+        self.base = base.value
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle.raw), group=self.group)
+        self.peer = []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                self.peer.append(self.base)
+                continue
+            p = C.c_void_p()
+            buf = (C.c_char * 64).from_buffer_copy(h)
+            with torch.cuda.device(self.device):
+                cabi.check(lib.udb_p2p_open(buf, C.byref(p)), f"udb_p2p_open(rank {r})")
+            self.peer.append(p.value)
+        self.peer_flags = torch.tensor([p + self.flags_off for p in self.peer], dtype=torch.int64, device=self.device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.last = [None] * depth                      # event after which slot i may be overwritten
         self.i = 0
+        self.epoch = 0
+        self._views = [{k: torch.as_tensor(_DevView(self.base + s * self.slot_bytes + self.offs[k], self.shapes[k]), device=self.device)
+                        for k in self.keys} for s in range(depth)]
+        dist.barrier(group=self.group)                  # every rank has mapped every peer before the first device barrier
 
-    def start(self, out: Dict[str, torch.Tensor]) -> PendingOutputs:
-        slot = self.i % len(self.send)
+    def views(self) -> Dict[str, torch.Tensor]:
+        """Tensors aliasing the slot the NEXT start() sends (write the rank's outputs here to skip the staging copy).
+        The caller's stream is made to wait until every peer has pulled the slot's previous content."""
+        slot = self.i % self.depth
+        if self.last[slot] is not None:
+            torch.cuda.current_stream().wait_event(self.last[slot])
+        return self._views[slot]
+
+    def _barrier(self):
+        self.epoch += 1
+        C, lib = self.C, self.cabi.lib()
+        self.cabi.check(lib.udb_p2p_barrier(C.c_void_p(self.peer_flags.data_ptr()), C.c_void_p(self.base + self.flags_off), self.rank, self.world,
+                                            self.epoch, C.c_void_p(self.base + self.flags_off + 512), C.c_void_p(self.stream.cuda_stream)),
+                        "udb_p2p_barrier")
+
+    def start(self, out: Dict[str, torch.Tensor]) -> "PendingOutputs":
+        slot = self.i % self.depth
+        views = self.views()
         self.i += 1
         cur = torch.cuda.current_stream()
-        if self.last[slot] is not None:
-            cur.wait_event(self.last[slot])            # every peer has pulled the previous content
-        b = out["depth"].shape[0]
-        torch.cat([out[k].reshape(b, -1) for k in _keys(out)], dim=1, out=self.send[slot])
-        full = torch.empty((self.world * b, self.shape[1]), device=self.send[slot].device, dtype=torch.float32)
-        hdl = self.hdl[slot]
+        for k in self.keys:
+            if out[k].data_ptr() != views[k].data_ptr():
+                views[k].copy_(out[k])                  # outputs were not produced in place: one staging copy
+        b = self.batch
+        full = {k: torch.empty((self.world * b,) + self.shapes[k][1:], device=self.device, dtype=torch.float32) for k in self.keys}
+        C, lib = self.C, self.cabi.lib()
         self.stream.wait_stream(cur)
         with torch.cuda.stream(self.stream):
-            hdl.barrier()                              # all send buffers of this slot are complete
+            self._barrier()                             # all send slots of this step are complete
             for step in range(self.world):
-                r = (self.rank - step) % self.world
-                full[r * b:(r + 1) * b].copy_(hdl.get_buffer(r, self.shape, torch.float32), non_blocking=True)
-            hdl.barrier()                              # all pulls done: the slot may be reused
+                r = (self.rank - step) % self.world     # start with the local slot, then walk the ring
+                for k in self.keys:
+                    n = full[k][0].numel() * b * 4
+                    dst = full[k].data_ptr() + r * n
+                    self.cabi.check(lib.udb_p2p_copy(C.c_void_p(dst), C.c_void_p(self.peer[r] + slot * self.slot_bytes + self.offs[k]), n,
+                                                     C.c_void_p(self.stream.cuda_stream)), "udb_p2p_copy")
+            self._barrier()                             # all pulls done: the slot may be reused
             ev = torch.cuda.Event()
             ev.record(self.stream)
-        # no full.record_stream(): PendingOutputs keeps `full` alive and its wait() orders the consumer
-        # stream after the side stream, so the block is never freed with side-stream work pending
         self.last[slot] = ev
-        shapes = {k: torch.empty((0,) + tuple(out[k].shape[1:]), device="meta") for k in _keys(out)}
-        return PendingOutputs(None, full, None, shapes, event=ev)
+        return PendingOutputs(None, full, None, None, event=ev)
+
+    def timed_out(self) -> bool:
+        """True if a device barrier gave up waiting for a peer (synchronises)."""
+        torch.cuda.synchronize(self.device)
+        flag = torch.as_tensor(_DevView(self.base + self.flags_off + 512, (1,), "<i4"), device=self.device)
+        return bool(flag.item())
 
 
 def gather_mode() -> str:
-    """'nccl' (synchronous all_gather_into_tensor) or 'p2p' (copy-engine pulls over NVLink peer memory)."""
+    """'p2p' (default on NCCL process groups: copy-engine pulls over NVLink peer memory) or 'nccl' (UDB_GATHER=nccl:
+    one synchronous all_gather_into_tensor of the packed buffer)."""
     import os
-    return os.environ.get("UDB_GATHER", "nccl")
+    return os.environ.get("UDB_GATHER", "p2p")
 
 
 def gather_description() -> str:
     if _p2p_cache:
-        return ("one packed all-gather of the per-rank outputs per step: copy-engine pulls over NVLink peer memory on a side "
-                "stream, left in flight under the next step's compute (depth-1 pipeline); every gather completes inside the "
-                "timed region")
+        return ("all-gather of the per-rank outputs by copy-engine pulls over NVLink peer memory (CUDA IPC buffers, device-side "
+                "flag barrier, include/udb.h udb_p2p_*), on a side stream, left in flight under the next step's compute (depth-1 "
+                "pipeline); outputs are written straight into the send slot (no pack / unpack); every gather completes inside "
+                "the timed region")
     return "one packed NCCL all_gather_into_tensor of the per-rank outputs per step, synchronous, inside the timed region"
 
 
-_p2p_cache: Dict[tuple, "P2PGather"] = {}
+_p2p_cache: Dict[tuple, "PeerGather"] = {}
 _p2p_failed = [None]
 
 
 def p2p_gather_for(out: Dict[str, torch.Tensor], group=None):
-    """Cached P2PGather for this output signature, or None (then the NCCL path is used).
-    OPT-IN (UDB_GATHER=p2p), experimental: measured at N=2 it removes the gather from the step time
-    (99.0 % weak-scaling efficiency vs 98.4 % for the synchronous NCCL gather and 96.5 % for an in-flight
-    NCCL gather), but in tests/test_multigpu_gpu.py's sequence (gather, then capture of a LARGER CUDA
-    graph, then replay of the older graph) the older graph's replays return wrong values with this path
-    enabled and not with NCCL; not understood yet, so it is off by default."""
+    """Cached PeerGather for this output signature, or None (then the NCCL path is used: UDB_GATHER=nccl, CPU tensors,
+    or peer memory unavailable -- the reason is kept in _p2p_failed[0])."""
     if gather_mode() != "p2p" or _p2p_failed[0] is not None or not out["depth"].is_cuda:
         return None
-    b = out["depth"].shape[0]
-    feat = sum(out[k][0].numel() for k in _keys(out))
-    key = (b, feat, out["depth"].device.index)
+    key = tuple((k, tuple(out[k].shape)) for k in _keys(out)) + (out["depth"].device.index,)
     if key not in _p2p_cache:
+        ok = 1
         try:
-            _p2p_cache[key] = P2PGather(b, feat, out["depth"].device, group)
-        except Exception as e:      # no NVLink peer access / unsupported build: keep working over NCCL
+            pg = PeerGather(out, out["depth"].device, group)
+        except Exception as e:      # no peer access / IPC unavailable: keep working over NCCL
             _p2p_failed[0] = f"{type(e).__name__}: {e}"
+            ok, pg = 0, None
+        # all ranks must agree, or some would wait in a device barrier the others never enter
+        flag = torch.tensor([ok], device=out["depth"].device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag.item()) == 0:
+            _p2p_failed[0] = _p2p_failed[0] or "a peer could not set up peer memory"
             return None
+        _p2p_cache[key] = pg
     return _p2p_cache[key]
+
+
+def output_views(out_like: Dict[str, torch.Tensor]):
+    """The send-slot tensors of the PeerGather that serves outputs shaped like `out_like`, or None if there is none (yet):
+    assign them to `model.output_buffers` before `infer` so that the outputs land in the slot without a staging copy."""
+    if not _p2p_cache or not out_like["depth"].is_cuda:
+        return None
+    key = tuple((k, tuple(out_like[k].shape)) for k in _keys(out_like)) + (out_like["depth"].device.index,)
+    pg = _p2p_cache.get(key)
+    return pg.views() if pg is not None else None
 
 
 def gather_outputs(out: Dict[str, torch.Tensor], world: int, group=None, async_op: bool = False, counts=None):

@@ -64,6 +64,7 @@ class UniDepthV1(nn.Module, PyTorchModelHubMixin,
         self.image_shape = list(self.spec.image_shape)        # unidepthv1.py:447
         self.use_cuda_graph = True
         self.max_cached_graphs = 8
+        self.output_buffers = None      # see UniDepthV2.output_buffers
         self._engine = None
         self._packed: Optional[dict] = None
         self._packed_key = None
@@ -380,6 +381,11 @@ class UniDepthV1(nn.Module, PyTorchModelHubMixin,
             if K is not None:
                 entry["k"].copy_(K, non_blocking=True)
             entry["graph"].replay()
+            bufs = self.output_buffers
+            if bufs is not None:
+                for k, v in entry["out"].items():
+                    bufs[k].copy_(v)
+                return {k: bufs[k] for k in entry["out"]}
             return {k: v.clone() for k, v in entry["out"].items()}
 
     def forward(self, *args, **kwargs):

@@ -82,6 +82,9 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
         # runs in fp32; ~4x slower.  It shows that the default mode's residual against the fp32 reference is operand
         # rounding: the intrinsics (fp32 camera head on the encoder's cls tokens) then meet north_star's 1e-4.
         self.precision = "f16"
+        # optional dict of preallocated output tensors (same keys / shapes as infer's result): graph-mode infer copies its
+        # static outputs there instead of cloning them (parallel.PeerGather.views(): the multi-GPU send slot)
+        self.output_buffers = None
         self._engine = None
         self._engine_key = None
         # Bounded caches (LRU): the reference handles arbitrary shapes in constant memory, so a stream of
@@ -825,4 +828,9 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
             self._graphs.move_to_end(key)
         entry["inp"].copy_(rgb, non_blocking=True)
         entry["graph"].replay()
+        bufs = self.output_buffers
+        if bufs is not None:       # caller-provided destinations (e.g. the send slot of parallel.PeerGather): one copy, no clone
+            for k, v in entry["out"].items():
+                bufs[k].copy_(v)
+            return {k: bufs[k] for k in entry["out"]}
         return {k: v.clone() for k, v in entry["out"].items()}

@@ -364,9 +364,10 @@ int udb_v1_camera_intrinsics(const float* x4, const float* gt_k, int32_t B, int3
 
 /* Single-head cross attention with a handful of queries (camera head `aggregate`, decoder.py:95): q f32 [B*nq, D]
  * (+ q_pos [nq, D] when not NULL: the learned latents_pos, layers/attention.py:129-131; then scaled by `scale`),
- * kv f16 [B*nk, 2D] = (k | v), out f32 [B*nq, D]. */
-int udb_cross_attn_small(const float* q, const float* q_pos, const void* kv, float* out, int32_t B, int32_t nq, int32_t nk,
-                         int32_t D, float scale, void* stream);
+ * kv f16 [B*nk, 2D] = (k | v), out f32 [B*nq, D].  nq <= 4, D % 256 == 0; scratch: B*16*nq*(D+2) floats (the keys are split
+ * over 16 blocks per image, partial results are merged by a second kernel). */
+int udb_cross_attn_small(const float* q, const float* q_pos, const void* kv, float* out, float* scratch, int32_t B, int32_t nq,
+                         int32_t nk, int32_t D, float scale, void* stream);
 
 /* p[r, j] = softmax_j(scale * s[r, j]) over j < n_valid, f32 [rows, ld_in] -> f16 [rows, ld_out], columns >= n_valid zero
  * (the P operand of the dense single-head attentions aggregate_16 / prompt_camera, decoder.py:231-236). */

@@ -192,7 +192,8 @@ def test_small_attention_pieces_and_nystrom():
     q, pos = torch.randn(B * nq, D, generator=g).to(dev), torch.randn(nq, D, generator=g).to(dev)
     kv = torch.randn(B * nk, 2 * D, generator=g).to(dev).half()
     out = torch.empty(B * nq, D, device=dev)
-    cabi.check(lib.udb_cross_attn_small(_p(q), _p(pos), _p(kv), _p(out), B, nq, nk, D, D ** -0.5, _st()), "cross")
+    scratch = torch.empty(B * 16 * nq * (D + 2), device=dev)
+    cabi.check(lib.udb_cross_attn_small(_p(q), _p(pos), _p(kv), _p(out), _p(scratch), B, nq, nk, D, D ** -0.5, _st()), "cross")
     qq = (q.view(B, nq, D) + pos)
     kk, vv = kv.float().view(B, nk, 2 * D)[..., :D], kv.float().view(B, nk, 2 * D)[..., D:]
     ref = torch.softmax(qq @ kk.transpose(1, 2) * D ** -0.5, -1) @ vv

@@ -207,7 +207,7 @@ EXPORTS = {
     "udb_aa_resize_nhwc_f16": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),
     "udb_v1_rays_sh81": (i32, [C.POINTER(V1Rays), vp]),
     "udb_v1_camera_intrinsics": (i32, [vp, vp, i32, i32, i32, f32, i32, i32, i32, vp, vp, vp, vp]),
-    "udb_cross_attn_small": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, f32, vp]),
+    "udb_cross_attn_small": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp]),
     "udb_softmax_rows": (i32, [vp, vp, i64, i32, i32, i32, f32, vp]),
     "udb_add_f32": (i32, [vp, vp, vp, vp, i64, vp]),
     "udb_copy_rows_f32_to_f16": (i32, [vp, vp, i32, i32, i32, i64, i64, vp]),

@@ -350,8 +350,9 @@ static int run_v1(udb_engine_v1* e, const udb_infer_v1_args_t& a, Arena& ar, voi
       float* q = ar.f(static_cast<size_t>(R4) * hid);
       c.small_linear(xn, R4, hid, c.F(ag + "q_w"), hid, c.F(ag + "q_b"), UDB_ACT_NONE, nullptr, nullptr, q);
       float* at = ar.f(static_cast<size_t>(R4) * hid);
+      float* scratch = ar.f(static_cast<size_t>(B) * 16 * 4 * (hid + 2));
       if (!c.dry && !c.rc)
-        c.done(udb_cross_attn_small(q, c.F("cam.pos"), kv, at, B, 4, 4 * nq + 4, hid, 1.0f / sqrtf(static_cast<float>(hid)), st));
+        c.done(udb_cross_attn_small(q, c.F("cam.pos"), kv, at, scratch, B, 4, 4 * nq + 4, hid, 1.0f / sqrtf(static_cast<float>(hid)), st));
       float* t2 = ar.f(static_cast<size_t>(R4) * hid);
       c.small_linear(at, R4, hid, c.F(ag + "out_w"), hid, c.F(ag + "out_b"), UDB_ACT_NONE, c.F(ag + "ls1"), cl, t2);
       t = cam_mlp(c, ag + "mlp", t2, R4, hid, cf.expansion * hid, hid, t2, c.F(ag + "ls2"));

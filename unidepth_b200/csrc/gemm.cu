@@ -72,128 +72,56 @@ struct EpiWarp {
   int quad, grp, lane, r_in_tile;
 };
 
-// What an epilogue warp can do for its next tile BEFORE the accumulator is ready (no TMEM access): the per-row
-// addressing and, for f32 residuals, the global loads of the first 32-column chunk.  The residual comes from DRAM (the
-// f32 stream is 53 MB per image batch, evicted from L2 between two uses); issuing its loads ahead -- here for the first
-// chunk, and one chunk ahead inside epilogue_tile -- takes that latency off the critical path of the short-K GEMMs
-// (attn.proj: K = 1024, the epilogue is longer than the main loop).
-struct EpiPre {
-  uint32_t vmask;
-  bool valid;
-  long long out_off;
-  bool have_r0;
-  float4 r0[8];
-};
-
-template <int BN>
-__device__ __forceinline__ long long epi_col_off(const GemmArgs& p, const int n0) {
-  if (p.store_mode == UDB_STORE_CONVT) {
-    const int tap = n0 / p.ct_cout;
-    const int co = n0 % p.ct_cout;
-    const long long W2 = (long long)p.ct_w * p.ct_k + 2 * p.ct_pad;
-    return ((long long)(tap / p.ct_k) * W2 + (tap % p.ct_k)) * p.ct_cout + co;
-  }
-  return n0;
-}
-
-// residual rows of the 32-column chunk starting at column `c` of this warp's column group (rows in the for_rows order)
-template <int BN>
-__device__ __forceinline__ bool epi_issue_resid(const GemmArgs& p, const EpiWarp& w, const uint32_t vmask, const int nt, const int c,
-                                                float4 (&t)[8]) {
-  constexpr int kGroups = BN >= 64 ? 2 : 1;
-  constexpr int kColsPerGrp = BN / kGroups;
-  const int n0 = nt * BN + w.grp * kColsPerGrp + c;
-  if (c >= kColsPerGrp || n0 >= p.N) return false;
-  const int l4 = (w.lane & 7) * 4, rq = w.lane >> 3;
-  const float* rp = reinterpret_cast<const float*>(p.resid) + static_cast<uint32_t>(epi_col_off<BN>(p, n0)) + l4;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int rr = 4 * i + rq;
-    const bool ok = (vmask >> rr) & 1u;
-    t[i] = ok ? *reinterpret_cast<const float4*>(rp + w.roff_res[rr]) : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  return true;
-}
-
-template <int BN>
-__device__ __forceinline__ void epilogue_prepare(const GemmArgs& p, const EpiWarp& w, const int mt, const int nt, EpiPre& pre) {
-  constexpr int kGroups = BN >= 64 ? 2 : 1;
-  pre.have_r0 = false;
-  pre.vmask = 0;
-  pre.valid = false;
-  pre.out_off = 0;
-  if (w.grp >= kGroups) return;
-  const int r_in_tile = w.r_in_tile;
-  bool valid;
-  long long out_off = 0, res_off = 0;
-  const int m = mt * BM + r_in_tile;
-  if (p.store_mode == UDB_STORE_CONVTILE || p.store_mode == UDB_STORE_HEAD) {
-    const int per_img = p.conv_tx * p.conv_ty;
-    const int b = mt / per_img;
-    const int r = mt % per_img;
-    const int y = (r / p.conv_tx) * p.conv_TH + r_in_tile / p.conv_TW;
-    const int x = (r % p.conv_tx) * p.conv_TW + r_in_tile % p.conv_TW;
-    valid = (b < p.conv_B) && (y < p.conv_H) && (x < p.conv_W);
-    out_off = (((long long)b * p.conv_H + y) * p.conv_W + x) * p.ldc;
-    res_off = (((long long)b * p.conv_H + y) * p.conv_W + x) * p.ldr;
-  } else if (p.store_mode == UDB_STORE_CONVT) {
-    valid = m < p.M;
-    const int hw = p.ct_h * p.ct_w;
-    const int b = m / hw;
-    const int r = m % hw;
-    const int y = r / p.ct_w, x = r % p.ct_w;
-    const long long W2 = (long long)p.ct_w * p.ct_k + 2 * p.ct_pad;
-    const long long H2 = (long long)p.ct_h * p.ct_k + 2 * p.ct_pad;
-    out_off = ((b * H2 + (long long)y * p.ct_k + p.ct_pad) * W2 + (long long)x * p.ct_k + p.ct_pad) * p.ct_cout;
-    res_off = out_off;
-  } else {
-    valid = m < p.M;
-    long long orow = m;
-    if (p.rpg > 0) orow = (long long)(m / p.rpg) * p.gstride + (m % p.rpg) + p.roff;
-    out_off = orow * p.ldc;
-    res_off = (p.resid_mod > 0) ? ((long long)(m % p.resid_mod) + p.resid_roff) * p.ldr
-                                : orow * p.ldr;
-  }
-  pre.vmask = __ballot_sync(0xffffffffu, valid);
-  pre.valid = valid;
-  pre.out_off = out_off;
-  __syncwarp();       // the previous tile's readers of roff_* are done
-  w.roff_out[w.lane] = static_cast<uint32_t>(out_off);
-  w.roff_res[w.lane] = static_cast<uint32_t>(res_off);
-  __syncwarp();
-  if (p.resid && p.resid_f32 && p.store_mode != UDB_STORE_HEAD) pre.have_r0 = epi_issue_resid<BN>(p, w, pre.vmask, nt, 0, pre.r0);
-}
-
-// One accumulator tile (128 rows x BN columns, fp32 in TMEM at `t_acc`) -> global memory.
-// `mt` indexes this CTA's 128-row block (matrix rows mt*128.. or spatial conv tile mt), `nt` the
-// BN-wide column block.  Executed by the 8 epilogue warps; warp (quad, grp) owns TMEM lanes
-// [32*quad, +32) and column half `grp`.  `pre` comes from epilogue_prepare (same mt, nt).
 template <int BN>
 __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, const EpiWarp& w, const uint32_t t_acc,
-                                              const int mt, const int nt, EpiPre& pre) {
+                                              const int mt, const int nt) {
   constexpr int kGroups = BN >= 64 ? 2 : 1;
   constexpr int kColsPerGrp = BN / kGroups;
-  const int grp = w.grp, quad = w.quad, lane = w.lane;
+  const int grp = w.grp, quad = w.quad, lane = w.lane, r_in_tile = w.r_in_tile;
   float* T = w.T;
   uint32_t* roff_out = w.roff_out;
   uint32_t* roff_res = w.roff_res;
   if (grp < kGroups) {
-        const bool valid = pre.valid;
-        const long long out_off = pre.out_off;
-        const uint32_t vmask = pre.vmask;
-        const bool prefetch = p.resid && p.resid_f32 && p.store_mode != UDB_STORE_HEAD;
+        // ---- per-row addressing
+        bool valid;
+        long long out_off = 0, res_off = 0;
+        const int m = mt * BM + r_in_tile;
+        if (p.store_mode == UDB_STORE_CONVTILE || p.store_mode == UDB_STORE_HEAD) {
+          const int per_img = p.conv_tx * p.conv_ty;
+          const int b = mt / per_img;
+          const int r = mt % per_img;
+          const int y = (r / p.conv_tx) * p.conv_TH + r_in_tile / p.conv_TW;
+          const int x = (r % p.conv_tx) * p.conv_TW + r_in_tile % p.conv_TW;
+          valid = (b < p.conv_B) && (y < p.conv_H) && (x < p.conv_W);
+          out_off = (((long long)b * p.conv_H + y) * p.conv_W + x) * p.ldc;
+          res_off = (((long long)b * p.conv_H + y) * p.conv_W + x) * p.ldr;
+        } else if (p.store_mode == UDB_STORE_CONVT) {
+          valid = m < p.M;
+          const int hw = p.ct_h * p.ct_w;
+          const int b = m / hw;
+          const int r = m % hw;
+          const int y = r / p.ct_w, x = r % p.ct_w;
+          const long long W2 = (long long)p.ct_w * p.ct_k + 2 * p.ct_pad;
+          const long long H2 = (long long)p.ct_h * p.ct_k + 2 * p.ct_pad;
+          out_off = ((b * H2 + (long long)y * p.ct_k + p.ct_pad) * W2 + (long long)x * p.ct_k + p.ct_pad) * p.ct_cout;
+          res_off = out_off;
+        } else {
+          valid = m < p.M;
+          long long orow = m;
+          if (p.rpg > 0) orow = (long long)(m / p.rpg) * p.gstride + (m % p.rpg) + p.roff;
+          out_off = orow * p.ldc;
+          res_off = (p.resid_mod > 0) ? ((long long)(m % p.resid_mod) + p.resid_roff) * p.ldr
+                                      : orow * p.ldr;
+        }
+        const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+        roff_out[lane] = static_cast<uint32_t>(out_off);
+        roff_res[lane] = static_cast<uint32_t>(res_off);
+        __syncwarp();
         const uint32_t t_row = t_acc + (static_cast<uint32_t>(quad * 32) << 16);
 #pragma unroll 1
         for (int c = 0; c < kColsPerGrp; c += 32) {
           const int col = grp * kColsPerGrp + c;   // column inside the tile
           const int n0 = nt * BN + col;            // global column
-          // residual of THIS chunk was issued one chunk (or one tile) ago; issue the next chunk's loads now
-          float4 rcur[8];
-          if (prefetch) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) rcur[i] = pre.r0[i];
-            pre.have_r0 = epi_issue_resid<BN>(p, w, vmask, nt, c + 32, pre.r0);
-          }
           uint32_t r[32];
           tmem_ld_32x32b_x32(t_row + col, r);
           tmem_ld_wait();
@@ -232,7 +160,13 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, const EpiWarp& 
               v[4 * j] *= g4.x; v[4 * j + 1] *= g4.y; v[4 * j + 2] *= g4.z; v[4 * j + 3] *= g4.w;
             }
           }
-          const long long coff = epi_col_off<BN>(p, n0);
+          long long coff = n0;
+          if (p.store_mode == UDB_STORE_CONVT) {
+            const int tap = n0 / p.ct_cout;
+            const int co = n0 % p.ct_cout;
+            const long long W2 = (long long)p.ct_w * p.ct_k + 2 * p.ct_pad;
+            coff = ((long long)(tap / p.ct_k) * W2 + (tap % p.ct_k)) * p.ct_cout + co;
+          }
           // ---- residual / stores through the per-warp transpose tile T[32][TP]: in registers a thread
           //      owns a row; in global memory 8 lanes x 16 B (f32) or 8 B (f16) cover one 32-column row
           //      segment and one instruction covers 4 rows, so every access is contiguous.  All smem
@@ -255,11 +189,17 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, const EpiWarp& 
             }
           };
           if (p.resid) {
+            // all 8 row-segment loads of a lane are issued before the first use (latency-bound)
             if (p.resid_f32) {
+              const float* rp = reinterpret_cast<const float*>(p.resid) + c32 + l4;
+              float4 tmp[8];
+              int k = 0;
+              for_rows([&](int rr, bool ok) {
+                tmp[k++] = ok ? *reinterpret_cast<const float4*>(rp + roff_res[rr]) : make_float4(0.f, 0.f, 0.f, 0.f);
+              });
 #pragma unroll
-              for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(T + (4 * i + rq) * kTP + l4) = rcur[i];
+              for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(T + (4 * i + rq) * kTP + l4) = tmp[i];
             } else {
-              // all 8 row-segment loads of a lane are issued before the first use (latency-bound)
               const __half* rp = reinterpret_cast<const __half*>(p.resid) + c32 + l4;
               uint2 tmp[8];
               int k = 0;
@@ -473,12 +413,10 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const uint32_t aphase = (it >> 1) & 1;
       const int mt = tile / p.tiles_n;
       const int nt = tile % p.tiles_n;
-      EpiWarp ew_ctx{T, roff_out, roff_res, quad, grp, lane, r_in_tile};
-      EpiPre pre;
-      epilogue_prepare<BN>(p, ew_ctx, mt, nt, pre);      // addressing + first residual loads while the MMAs still run
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after_sync();
-      epilogue_tile<BN>(p, ew_ctx, tmem_base + as * BN, mt, nt, pre);
+      EpiWarp ew_ctx{T, roff_out, roff_res, quad, grp, lane, r_in_tile};
+      epilogue_tile<BN>(p, ew_ctx, tmem_base + as * BN, mt, nt);
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[as]);
@@ -524,11 +462,11 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
 // ---------------------------------------------------------------------------------------------
 template <int BN>
 struct Gemm2Cfg {
-  static constexpr int kStages = BN >= 256 ? 5 : 7;
+  static constexpr int kStages = BN >= 256 ? 5 : (BN >= 192 ? 6 : 7);
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = (BN / 2) * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kTmemCols = 2 * BN <= 256 ? 256 : 512;   // power of two (BN = 192: 384 columns used)
   static constexpr int kStagingBytes = kEpiWarps * (32 * kTP * 4 + 2 * 32 * 4);
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 256;
 };
@@ -673,11 +611,9 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t aphase = (it >> 1) & 1;
       const int mt = 2 * (tile / p.tiles_n) + (int)rank;
       const int nt = tile % p.tiles_n;
-      EpiPre pre;
-      epilogue_prepare<BN>(p, ctx, mt, nt, pre);          // addressing + first residual loads while the MMAs still run
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after_sync();
-      epilogue_tile<BN>(p, ctx, tmem_base + as * BN, mt, nt, pre);
+      epilogue_tile<BN>(p, ctx, tmem_base + as * BN, mt, nt);
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) {
@@ -751,12 +687,18 @@ extern "C" int udb_gemm_f16(const udb_gemm_t* g, void* stream) {
     set_error("udb_gemm_f16: out_split needs an f16 `out` with the ROWS store"); return 1;
   }
 
+  // CTA-pair kernel (cta_group::2) for the wide tiles; UDB_GEMM_PAIR=0 forces the single-CTA kernel
+  static const int pair_env = [] {
+    const char* e = getenv("UDB_GEMM_PAIR");
+    return e ? atoi(e) : 1;
+  }();
   // tile width: widest that divides the work sensibly
   int bn;
   if (g->store_mode == UDB_STORE_HEAD) {
     if (g->N != 32) { set_error("udb_gemm_f16: HEAD store needs N == 32"); return 1; }
     bn = 32;
   } else if (g->N % 256 == 0) bn = 256;
+  else if (g->N % 192 == 0 && pair_env != 0) bn = 192;      // ConvNeXt widths 192 / 384: 3 (or 6) times fewer passes over A than 64 / 128
   else if (g->N % 128 == 0) bn = 128;
   else if (g->N % 64 == 0) bn = 64;
   else bn = 32;
@@ -764,12 +706,7 @@ extern "C" int udb_gemm_f16(const udb_gemm_t* g, void* stream) {
     set_error("udb_gemm_f16: CONVT needs Cout %% 32 == 0"); return 1;
   }
   a.tiles_n = (g->N + bn - 1) / bn;
-  // CTA-pair kernel (cta_group::2) for the wide tiles; UDB_GEMM_PAIR=0 forces the single-CTA kernel
-  static const int pair_env = [] {
-    const char* e = getenv("UDB_GEMM_PAIR");
-    return e ? atoi(e) : 1;
-  }();
-  const bool use_pair = pair_env != 0 && (bn == 256 || bn == 128);
+  const bool use_pair = pair_env != 0 && (bn == 256 || bn == 192 || bn == 128);
 
   CUtensorMap tmA, tmB;
   if (g->a_mode == UDB_A_CONV3X3) {
@@ -817,7 +754,7 @@ extern "C" int udb_gemm_f16(const udb_gemm_t* g, void* stream) {
             2.0 * ((double)a.M * (g->a_mode == UDB_A_CONV3X3 ? g->conv_C : (g->a_split_k ? 2 * g->a_split_k : g->K)) + (double)g->N * g->K) +
                 (double)a.M * g->N * ((g->out ? (g->out_f32 ? 4 : 2) : 0) + (g->out2 ? 2 : 0) + (g->resid ? (g->resid_f32 ? 4 : 2) : 0)));
   if (use_pair) {
-    return bn == 256 ? launch_gemm2<256>(tmA, tmB, a, st) : launch_gemm2<128>(tmA, tmB, a, st);
+    return bn == 256 ? launch_gemm2<256>(tmA, tmB, a, st) : (bn == 192 ? launch_gemm2<192>(tmA, tmB, a, st) : launch_gemm2<128>(tmA, tmB, a, st));
   }
   switch (bn) {
     case 256: return launch_gemm<256>(tmA, tmB, a, st);

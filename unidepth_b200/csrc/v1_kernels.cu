@@ -112,53 +112,74 @@ __global__ void __launch_bounds__(256) v1_preprocess_kernel(const udb_v1_preproc
 // an [B,H,W,C] map into row (b, y/2, x/2), columns ((y&1)*2 + (x&1))*C + c of the k2 s2 downsample's im2col matrix
 // (odd trailing row / column dropped, as the strided conv does).
 // ------------------------------------------------------------------------------------------------------------------
-template <bool IN_F32, bool OUT_F32>
+template <bool IN_F32, bool OUT_F32, int R, int NV>
 __global__ void __launch_bounds__(256) layernorm_any_kernel(const udb_layernorm_any_t p) {
-  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  // one warp normalises R consecutive rows; all loads of the R rows are issued before the first reduction (narrow rows
+  // alone -- 192 channels = 384 B -- do not keep enough bytes in flight); NV = max float2 per lane per row
+  const long long row0 = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * R;
   const int lane = threadIdx.x & 31;
-  if (row >= p.rows) return;
+  if (row0 >= p.rows) return;
   const int nv = p.dim >> 6;   // float2 per lane
-  float2 x[24];
-  float s = 0.f;
+  float2 x[R][NV];
+  float s[R];
 #pragma unroll
-  for (int i = 0; i < 24; ++i) {
-    if (i < nv) {
-      const int e = (lane + 32 * i) * 2;
-      if (IN_F32) {
-        x[i] = *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(p.in) + row * p.ld_in + e);
-      } else {
-        x[i] = __half22float2(*reinterpret_cast<const __half2*>(reinterpret_cast<const __half*>(p.in) + row * p.ld_in + e));
+  for (int r = 0; r < R; ++r) {
+    const long long row = row0 + r < p.rows ? row0 + r : p.rows - 1;
+    s[r] = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (i < nv) {
+        const int e = (lane + 32 * i) * 2;
+        if (IN_F32) {
+          x[r][i] = *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(p.in) + row * p.ld_in + e);
+        } else {
+          x[r][i] = __half22float2(*reinterpret_cast<const __half2*>(reinterpret_cast<const __half*>(p.in) + row * p.ld_in + e));
+        }
       }
-      if (p.add) {
-        const float2 a = *reinterpret_cast<const float2*>(p.add + (row % p.add_mod) * p.dim + e);
-        x[i].x += a.x;
-        x[i].y += a.y;
-      }
-      s += x[i].x + x[i].y;
     }
   }
-  const float mean = wsum(s) / (float)p.dim;
-  float v = 0.f;
 #pragma unroll
-  for (int i = 0; i < 24; ++i)
-    if (i < nv) v += (x[i].x - mean) * (x[i].x - mean) + (x[i].y - mean) * (x[i].y - mean);
-  const float rstd = rsqrtf(wsum(v) / (float)p.dim + p.eps);
-  long long obase = row * p.ld_out;
-  if (p.s2d_w > 0) {
-    const int xw = (int)(row % p.s2d_w), yh = (int)((row / p.s2d_w) % p.s2d_h), b = (int)(row / ((long long)p.s2d_w * p.s2d_h));
-    const int oh = p.s2d_h >> 1, ow = p.s2d_w >> 1;
-    if ((yh >> 1) >= oh || (xw >> 1) >= ow) return;
-    obase = (((long long)b * oh + (yh >> 1)) * ow + (xw >> 1)) * p.ld_out + ((yh & 1) * 2 + (xw & 1)) * p.dim;
+  for (int r = 0; r < R; ++r) {
+    const long long row = row0 + r < p.rows ? row0 + r : p.rows - 1;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (i < nv) {
+        if (p.add) {
+          const float2 a = *reinterpret_cast<const float2*>(p.add + (row % p.add_mod) * p.dim + (lane + 32 * i) * 2);
+          x[r][i].x += a.x;
+          x[r][i].y += a.y;
+        }
+        s[r] += x[r][i].x + x[r][i].y;
+      }
+    }
   }
 #pragma unroll
-  for (int i = 0; i < 24; ++i) {
-    if (i < nv) {
-      const int e = (lane + 32 * i) * 2;
-      const float2 w = __ldg(reinterpret_cast<const float2*>(p.weight + e));
-      const float2 bb = __ldg(reinterpret_cast<const float2*>(p.bias + e));
-      const float y0 = (x[i].x - mean) * rstd * w.x + bb.x, y1 = (x[i].y - mean) * rstd * w.y + bb.y;
-      if (OUT_F32) *reinterpret_cast<float2*>(reinterpret_cast<float*>(p.out) + obase + e) = make_float2(y0, y1);
-      else *reinterpret_cast<uint32_t*>(reinterpret_cast<__half*>(p.out) + obase + e) = pack_half2(y0, y1);
+  for (int r = 0; r < R; ++r) {
+    const long long row = row0 + r;
+    const float mean = wsum(s[r]) / (float)p.dim;
+    float v = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      if (i < nv) v += (x[r][i].x - mean) * (x[r][i].x - mean) + (x[r][i].y - mean) * (x[r][i].y - mean);
+    const float rstd = rsqrtf(wsum(v) / (float)p.dim + p.eps);
+    if (row >= p.rows) continue;
+    long long obase = row * p.ld_out;
+    if (p.s2d_w > 0) {
+      const int xw = (int)(row % p.s2d_w), yh = (int)((row / p.s2d_w) % p.s2d_h), b = (int)(row / ((long long)p.s2d_w * p.s2d_h));
+      const int oh = p.s2d_h >> 1, ow = p.s2d_w >> 1;
+      if ((yh >> 1) >= oh || (xw >> 1) >= ow) continue;
+      obase = (((long long)b * oh + (yh >> 1)) * ow + (xw >> 1)) * p.ld_out + ((yh & 1) * 2 + (xw & 1)) * p.dim;
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (i < nv) {
+        const int e = (lane + 32 * i) * 2;
+        const float2 w = __ldg(reinterpret_cast<const float2*>(p.weight + e));
+        const float2 bb = __ldg(reinterpret_cast<const float2*>(p.bias + e));
+        const float y0 = (x[r][i].x - mean) * rstd * w.x + bb.x, y1 = (x[r][i].y - mean) * rstd * w.y + bb.y;
+        if (OUT_F32) *reinterpret_cast<float2*>(reinterpret_cast<float*>(p.out) + obase + e) = make_float2(y0, y1);
+        else *reinterpret_cast<uint32_t*>(reinterpret_cast<__half*>(p.out) + obase + e) = pack_half2(y0, y1);
+      }
     }
   }
 }
@@ -169,48 +190,57 @@ __global__ void __launch_bounds__(256) layernorm_any_kernel(const udb_layernorm_
 // the 14x22 halo is staged once in shared memory (2.4x read amplification instead of 49x), each thread slides along 8
 // consecutive x for one 4-channel group, so per dy it loads 14 inputs + 7 weights for 56 FMA4.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int DW_TH = 8, DW_TW = 16, DW_CB = 64, DW_HH = DW_TH + 6, DW_HW = DW_TW + 6;
+constexpr int DW_CB = 64;
+constexpr int DW_PS = DW_CB + 4;   // pixel stride in halves (136 B): keeps the 8-byte row reads of a warp on distinct banks
 
+// TW = tile width (16 or 8), tile height = 128 / TW: wide tiles have the smaller halo, narrow ones waste fewer pixels on the
+// small late-stage maps (28x38, 14x19); the launcher picks the shape with the least padded area.
+template <int TW>
 __global__ void __launch_bounds__(256) dwconv7_kernel(const __half* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                                                      __half* __restrict__ y, int H, int W, int C, int tiles_x) {
-  __shared__ __align__(16) __half tile[DW_HH * DW_HW * DW_CB];
-  const int tx0 = (blockIdx.x % tiles_x) * DW_TW, ty0 = (blockIdx.x / tiles_x) * DW_TH;
+  constexpr int TH = 128 / TW, HH = TH + 6, HW = TW + 6;
+  __shared__ __align__(16) __half tile[HH * HW * DW_PS];
+  const int tx0 = (blockIdx.x % tiles_x) * TW, ty0 = (blockIdx.x / tiles_x) * TH;
   const int c0 = blockIdx.y * DW_CB, b = blockIdx.z;
   const __half* xb = x + (long long)b * H * W * C;
-  for (int i = threadIdx.x; i < DW_HH * DW_HW * (DW_CB / 8); i += 256) {
+  for (int i = threadIdx.x; i < HH * HW * (DW_CB / 8); i += 256) {
     const int ch = i & 7, pix = i >> 3;
-    const int hy = pix / DW_HW, hx = pix % DW_HW;
+    const int hy = pix / HW, hx = pix - hy * HW;
     const int gy = ty0 + hy - 3, gx = tx0 + hx - 3;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = *reinterpret_cast<const uint4*>(xb + ((long long)gy * W + gx) * C + c0 + ch * 8);
-    *reinterpret_cast<uint4*>(tile + pix * DW_CB + ch * 8) = v;
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = __ldg(reinterpret_cast<const uint4*>(xb + ((long long)gy * W + gx) * C + c0 + ch * 8));
+    uint2* d = reinterpret_cast<uint2*>(tile + pix * DW_PS + ch * 8);      // 8-byte aligned (136 B pixel stride)
+    d[0] = make_uint2(v.x, v.y);
+    d[1] = make_uint2(v.z, v.w);
   }
   __syncthreads();
   const int cg = threadIdx.x & 15, pg = threadIdx.x >> 4;
-  const int r = pg >> 1, xh = (pg & 1) * 8;
-  float4 acc[8];
-  const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + c0 + cg * 4));
+  const int r = TW == 16 ? (pg >> 1) : pg, xh = TW == 16 ? (pg & 1) * 8 : 0;     // each thread: 8 consecutive x of one row
+  uint64_t acc[8][2];          // packed f32x2: (c0,c1), (c2,c3)
+  {
+    const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + c0 + cg * 4));
 #pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = bv;
+    for (int i = 0; i < 8; ++i) { acc[i][0] = pack2(bv.x, bv.y); acc[i][1] = pack2(bv.z, bv.w); }
+  }
 #pragma unroll 1
   for (int dy = 0; dy < 7; ++dy) {
-    float4 in[14];
+    uint64_t in[14][2];
 #pragma unroll
     for (int i = 0; i < 14; ++i) {
-      const uint2 u = *reinterpret_cast<const uint2*>(tile + ((r + dy) * DW_HW + xh + i) * DW_CB + cg * 4);
+      const uint2 u = *reinterpret_cast<const uint2*>(tile + ((r + dy) * HW + xh + i) * DW_PS + cg * 4);
       const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
       const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
-      in[i] = make_float4(a.x, a.y, c.x, c.y);
+      in[i][0] = pack2(a.x, a.y);
+      in[i][1] = pack2(c.x, c.y);
     }
 #pragma unroll
     for (int dx = 0; dx < 7; ++dx) {
       const float4 wv = __ldg(reinterpret_cast<const float4*>(w + (long long)(dy * 7 + dx) * C + c0 + cg * 4));
+      const uint64_t w0 = pack2(wv.x, wv.y), w1 = pack2(wv.z, wv.w);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        acc[i].x = fmaf(in[i + dx].x, wv.x, acc[i].x);
-        acc[i].y = fmaf(in[i + dx].y, wv.y, acc[i].y);
-        acc[i].z = fmaf(in[i + dx].z, wv.z, acc[i].z);
-        acc[i].w = fmaf(in[i + dx].w, wv.w, acc[i].w);
+        acc[i][0] = fma2(in[i + dx][0], w0, acc[i][0]);
+        acc[i][1] = fma2(in[i + dx][1], w1, acc[i][1]);
       }
     }
   }
@@ -219,9 +249,12 @@ __global__ void __launch_bounds__(256) dwconv7_kernel(const __half* __restrict__
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int gx = tx0 + xh + i;
-      if (gx < W)
-        *reinterpret_cast<uint2*>(y + (((long long)b * H + gy) * W + gx) * C + c0 + cg * 4) =
-            make_uint2(pack_half2(acc[i].x, acc[i].y), pack_half2(acc[i].z, acc[i].w));
+      if (gx < W) {
+        float a0, a1, a2, a3;
+        unpack2(acc[i][0], a0, a1);
+        unpack2(acc[i][1], a2, a3);
+        *reinterpret_cast<uint2*>(y + (((long long)b * H + gy) * W + gx) * C + c0 + cg * 4) = make_uint2(pack_half2(a0, a1), pack_half2(a2, a3));
+      }
     }
   }
 }
@@ -412,59 +445,106 @@ __global__ void v1_camera_intrinsics_kernel(const float* x4, const float* gt_k, 
   else { kp[0] = k[0]; kp[1] = k[4]; kp[2] = k[2]; kp[3] = k[5]; }
 }
 
-// 4-query cross attention of the camera head (decoder.py:95, AttentionBlock num_heads=1): q f32 [B*nq, D] (position term
-// already added), kv f16 [B*nk, 2D] (k | v), out f32 [B*nq, D].  One block per (b, query); scores staged in shared memory.
-__global__ void __launch_bounds__(256) cross_attn_small_kernel(const float* __restrict__ q, const float* __restrict__ q_pos,
-                                                              const __half* __restrict__ kv, float* __restrict__ out, int nq, int nk, int D,
-                                                              float scale) {
-  extern __shared__ float sc[];          // [nk] scores + [D] query + 8 reduction slots
-  float* qs = sc + nk;
-  float* red = qs + D;
-  const int b = blockIdx.y, qi = blockIdx.x;
+// 4-query cross attention of the camera head (decoder.py:95, AttentionBlock num_heads=1): q f32 [B*nq, D] (+ q_pos), kv f16
+// [B*nk, 2D] (k | v), out f32 [B*nq, D].  Keys are split over CA_SPLITS blocks per image (flash-decoding style): each block
+// reads its slice of K and V ONCE for all queries and writes a partial (max, sum, weighted V); a second kernel merges.
+constexpr int CA_SPLITS = 16, CA_MAXQ = 4;
+
+__global__ void __launch_bounds__(256) cross_attn_partial_kernel(const float* __restrict__ q, const float* __restrict__ q_pos,
+                                                                const __half* __restrict__ kv, float* __restrict__ part, int nq, int nk, int D,
+                                                                float scale) {
+  extern __shared__ float sm[];
+  const int chunk = (nk + CA_SPLITS - 1) / CA_SPLITS;
+  float* qs = sm;                       // [nq][D]
+  float* sc = qs + nq * D;              // [nq][chunk]
+  float* red = sc + nq * chunk;         // [nq][8] partial max / sum
+  const int b = blockIdx.y, sp = blockIdx.x;
+  const int j0 = sp * chunk, j1 = min(nk, j0 + chunk), n = max(j1 - j0, 0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int d = threadIdx.x; d < D; d += 256)
-    qs[d] = (q[((long long)b * nq + qi) * D + d] + (q_pos ? q_pos[(long long)qi * D + d] : 0.f)) * scale;
+  for (int i = threadIdx.x; i < nq * D; i += 256)
+    qs[i] = (q[(long long)b * nq * D + i] + (q_pos ? q_pos[i] : 0.f)) * scale;
   __syncthreads();
   const __half* kb = kv + (long long)b * nk * 2 * D;
-  float lmax = -INFINITY;
-  for (int j = warp; j < nk; j += 8) {
-    float a = 0.f;
-    for (int d = lane * 2; d < D; d += 64) {
-      const float2 kf = __half22float2(*reinterpret_cast<const __half2*>(kb + (long long)j * 2 * D + d));
-      a = fmaf(qs[d], kf.x, fmaf(qs[d + 1], kf.y, a));
+  for (int j = warp; j < n; j += 8) {
+    float a[CA_MAXQ] = {0.f, 0.f, 0.f, 0.f};
+    const __half* kr = kb + (long long)(j0 + j) * 2 * D;
+    for (int d = lane * 8; d < D; d += 256) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(kr + d));
+      const __half2* h = reinterpret_cast<const __half2*>(&u);
+      float kf[8];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) { const float2 f = __half22float2(h[t]); kf[2 * t] = f.x; kf[2 * t + 1] = f.y; }
+#pragma unroll
+      for (int qi = 0; qi < CA_MAXQ; ++qi)
+        if (qi < nq) {
+#pragma unroll
+          for (int t = 0; t < 8; ++t) a[qi] = fmaf(qs[qi * D + d + t], kf[t], a[qi]);
+        }
     }
-    a = wsum(a);
-    if (lane == 0) sc[j] = a;
-    lmax = fmaxf(lmax, a);
-  }
-  if (lane == 0) red[warp] = lmax;
-  __syncthreads();
-  float m = red[0];
 #pragma unroll
-  for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
-  __syncthreads();
-  float ls = 0.f;
-  for (int j = threadIdx.x; j < nk; j += 256) {
-    const float e = expf(sc[j] - m);
-    sc[j] = e;
-    ls += e;
+    for (int qi = 0; qi < CA_MAXQ; ++qi)
+      if (qi < nq) {
+        const float v = wsum(a[qi]);
+        if (lane == 0) sc[qi * chunk + j] = v;
+      }
   }
-  ls = wsum(ls);
-  if (lane == 0) red[warp] = ls;
   __syncthreads();
-  float tot = 0.f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) tot += red[i];
-  const float inv = 1.0f / tot;
+  // per query: max, exp, sum over this block's keys (warp qi handles query qi)
+  if (warp < nq) {
+    float m = -INFINITY;
+    for (int j = lane; j < n; j += 32) m = fmaxf(m, sc[warp * chunk + j]);
+    m = wmax(m);
+    float l = 0.f;
+    for (int j = lane; j < n; j += 32) {
+      const float e = expf(sc[warp * chunk + j] - m);
+      sc[warp * chunk + j] = e;
+      l += e;
+    }
+    l = wsum(l);
+    if (lane == 0) { red[warp * 2] = m; red[warp * 2 + 1] = l; }
+  }
+  __syncthreads();
+  float* pb = part + ((long long)(b * CA_SPLITS + sp) * nq) * (D + 2);
   for (int d = threadIdx.x * 2; d < D; d += 512) {
-    float a0 = 0.f, a1 = 0.f;
-    for (int j = 0; j < nk; ++j) {
-      const float2 vf = __half22float2(*reinterpret_cast<const __half2*>(kb + (long long)j * 2 * D + D + d));
-      a0 = fmaf(sc[j], vf.x, a0);
-      a1 = fmaf(sc[j], vf.y, a1);
+    float acc[CA_MAXQ][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+    for (int j = 0; j < n; ++j) {
+      const float2 vf = __half22float2(*reinterpret_cast<const __half2*>(kb + (long long)(j0 + j) * 2 * D + D + d));
+#pragma unroll
+      for (int qi = 0; qi < CA_MAXQ; ++qi)
+        if (qi < nq) {
+          const float pw = sc[qi * chunk + j];
+          acc[qi][0] = fmaf(pw, vf.x, acc[qi][0]);
+          acc[qi][1] = fmaf(pw, vf.y, acc[qi][1]);
+        }
     }
-    out[((long long)b * nq + qi) * D + d] = a0 * inv;
-    out[((long long)b * nq + qi) * D + d + 1] = a1 * inv;
+    for (int qi = 0; qi < nq; ++qi) {
+      pb[qi * (D + 2) + 2 + d] = acc[qi][0];
+      pb[qi * (D + 2) + 2 + d + 1] = acc[qi][1];
+    }
+  }
+  if (threadIdx.x < nq) {
+    pb[threadIdx.x * (D + 2)] = n > 0 ? red[threadIdx.x * 2] : -INFINITY;
+    pb[threadIdx.x * (D + 2) + 1] = n > 0 ? red[threadIdx.x * 2 + 1] : 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(256) cross_attn_merge_kernel(const float* __restrict__ part, float* __restrict__ out, int nq, int D) {
+  const int b = blockIdx.y, qi = blockIdx.x;
+  float m = -INFINITY;
+  for (int s = 0; s < CA_SPLITS; ++s) m = fmaxf(m, part[((long long)(b * CA_SPLITS + s) * nq + qi) * (D + 2)]);
+  float wgt[CA_SPLITS], tot = 0.f;
+#pragma unroll
+  for (int s = 0; s < CA_SPLITS; ++s) {
+    const float* pp = part + ((long long)(b * CA_SPLITS + s) * nq + qi) * (D + 2);
+    wgt[s] = expf(pp[0] - m);
+    tot += wgt[s] * pp[1];
+  }
+  const float inv = 1.0f / tot;
+  for (int d = threadIdx.x; d < D; d += 256) {
+    float a = 0.f;
+#pragma unroll
+    for (int s = 0; s < CA_SPLITS; ++s) a = fmaf(wgt[s], part[((long long)(b * CA_SPLITS + s) * nq + qi) * (D + 2) + 2 + d], a);
+    out[((long long)b * nq + qi) * D + d] = a * inv;
   }
 }
 
@@ -512,24 +592,31 @@ __global__ void copy_rows_f16_kernel(const float* __restrict__ src, __half* __re
 
 // 3x3 convolution with ONE output channel, zero padding, fused exp(clamp(., -10, 10)) (decoder.py:253,268,283,292-294
 // `out8/out4/out2`): NHWC f16 in, f32 plane out.  One warp per output pixel, lanes over channel pairs.
+template <int LPP>      // lanes per pixel = C / 8 (8, 16 or 32): each lane owns 8 channels (one 16-byte load per tap)
 __global__ void __launch_bounds__(256) conv3x3_c1_kernel(const __half* __restrict__ x, const float* __restrict__ w, float bias, float* __restrict__ out,
                                                         int B, int H, int W, int C) {
-  const long long pix = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  constexpr int PPW = 32 / LPP;                      // pixels per warp
   const int lane = threadIdx.x & 31;
-  if (pix >= (long long)B * H * W) return;
-  const int px = (int)(pix % W), py = (int)((pix / W) % H), b = (int)(pix / ((long long)W * H));
+  const int sub = lane % LPP;
+  const long long pix = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * PPW + lane / LPP;
+  const bool live = pix < (long long)B * H * W;
+  const long long pc = live ? pix : 0;
+  const int px = (int)(pc % W), py = (int)((pc / W) % H), b = (int)(pc / ((long long)W * H));
   float a = 0.f;
+#pragma unroll
   for (int t = 0; t < 9; ++t) {
     const int yy = py + t / 3 - 1, xx = px + t % 3 - 1;
     if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-    const __half* xp = x + (((long long)b * H + yy) * W + xx) * C;
-    for (int c = lane * 2; c < C; c += 64) {
-      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(xp + c));
-      a = fmaf(f.x, __ldg(w + t * C + c), fmaf(f.y, __ldg(w + t * C + c + 1), a));
-    }
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + (((long long)b * H + yy) * W + xx) * C + sub * 8));
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + t * C + sub * 8)), w1 = __ldg(reinterpret_cast<const float4*>(w + t * C + sub * 8 + 4));
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+    const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]), f2 = __half22float2(h[2]), f3 = __half22float2(h[3]);
+    a = fmaf(f0.x, w0.x, fmaf(f0.y, w0.y, fmaf(f1.x, w0.z, fmaf(f1.y, w0.w, a))));
+    a = fmaf(f2.x, w1.x, fmaf(f2.y, w1.y, fmaf(f3.x, w1.z, fmaf(f3.y, w1.w, a))));
   }
-  a = wsum(a);
-  if (lane == 0) out[pix] = expf(fminf(fmaxf(a + bias, -10.0f), 10.0f));
+#pragma unroll
+  for (int o = LPP / 2; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if (live && sub == 0) out[pix] = expf(fminf(fmaxf(a + bias, -10.0f), 10.0f));
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -611,7 +698,7 @@ __global__ void __launch_bounds__(256) eye_minus_kernel(const float* __restrict_
 }
 
 // batched small matmul, f32:  C = diag * I + alpha * (A @ B), A [M,K], B [K,N] (f32, or f16 with row stride ldb),
-// C [M,N] f32 or f16 with row stride ldc.  32x32 output tile per block, 256 threads (2x2 per thread... 4 outputs).
+// C [M,N] f32 or f16 with row stride ldc.
 struct BmmArgs {
   const float* A; long long sA; int lda;
   const void* Bp; long long sB1, sB2; int ldb; int b_f16; int inner;   // batch index bh -> (bh / inner, bh % inner) for B and C strides
@@ -620,44 +707,59 @@ struct BmmArgs {
   float alpha, diag;
 };
 __global__ void __launch_bounds__(256) bmm_f32_kernel(const BmmArgs p) {
-  __shared__ float As[32][33], Bs[32][33];
+  // 64 x 64 output tile per block, 4 x 4 per thread, K in steps of 16 through shared memory
+  __shared__ float As[16][64 + 4], Bs[16][64 + 4];
   const int bh = blockIdx.z, o = bh / p.inner, i2 = bh % p.inner;
   const float* A = p.A + (long long)bh * p.sA;
-  const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // ty 0..7: rows ty, ty+8, ty+16, ty+24
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int k0 = 0; k0 < p.K; k0 += 32) {
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;      // outputs rows ty*4.., cols tx*4..
+  float acc[4][4];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int mm = m0 + ty + 8 * r, kk = k0 + tx;
-      As[ty + 8 * r][tx] = (mm < p.M && kk < p.K) ? A[(long long)mm * p.lda + kk] : 0.f;
-      const int kr = k0 + ty + 8 * r, nn = n0 + tx;
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < p.K; k0 += 16) {
+    // A tile 64 x 16 (stored transposed [k][m]); B tile 16 x 64
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int idx = threadIdx.x + 256 * t;             // 1024 elements each
+      const int am = idx >> 4, ak = idx & 15;
+      const int mm = m0 + am, kk = k0 + ak;
+      As[ak][am] = (mm < p.M && kk < p.K) ? A[(long long)mm * p.lda + kk] : 0.f;
+      const int bk = idx >> 6, bn = idx & 63;
+      const int kr = k0 + bk, nn = n0 + bn;
       float bv = 0.f;
       if (kr < p.K && nn < p.N) {
         const long long off = o * p.sB1 + i2 * p.sB2 + (long long)kr * p.ldb + nn;
         bv = p.b_f16 ? __half2float(reinterpret_cast<const __half*>(p.Bp)[off]) : reinterpret_cast<const float*>(p.Bp)[off];
       }
-      Bs[ty + 8 * r][tx] = bv;
+      Bs[bk][bn] = bv;
     }
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      const float bv = Bs[k][tx];
+    for (int k = 0; k < 16; ++k) {
+      const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float a[4] = {av.x, av.y, av.z, av.w}, bb[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
-      for (int r = 0; r < 4; ++r) acc[r] = fmaf(As[ty + 8 * r][k], bv, acc[r]);
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int mm = m0 + ty + 8 * r, nn = n0 + tx;
-    if (mm < p.M && nn < p.N) {
-      const float v = p.alpha * acc[r] + (mm == nn ? p.diag : 0.f);
-      const long long off = o * p.sC1 + i2 * p.sC2 + (long long)mm * p.ldc + nn;
-      if (p.c_f16) reinterpret_cast<__half*>(p.C)[off] = __float2half_rn(v);
-      else reinterpret_cast<float*>(p.C)[off] = v;
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int mm = m0 + ty * 4 + i, nn = n0 + tx * 4 + j;
+      if (mm < p.M && nn < p.N) {
+        const float v = p.alpha * acc[i][j] + (mm == nn ? p.diag : 0.f);
+        const long long off = o * p.sC1 + i2 * p.sC2 + (long long)mm * p.ldc + nn;
+        if (p.c_f16) reinterpret_cast<__half*>(p.C)[off] = __float2half_rn(v);
+        else reinterpret_cast<float*>(p.C)[off] = v;
+      }
     }
-  }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -733,21 +835,37 @@ int udb_v1_preprocess(const udb_v1_preprocess_t* p, void* stream) {
 int udb_layernorm_any(const udb_layernorm_any_t* p, void* stream) {
   if (p->dim % 64 || p->dim > 1536 || p->dim <= 0) { set_error("udb_layernorm_any: dim %d unsupported (multiple of 64, <= 1536)", p->dim); return 1; }
   if (p->rows <= 0) return 0;
-  const int grid = (int)((p->rows + 7) / 8);
   note_work(0.0, (double)p->rows * p->dim * ((p->in_f32 ? 4 : 2) + (p->out_f32 ? 4 : 2)));
-  if (p->in_f32 && p->out_f32) layernorm_any_kernel<true, true><<<grid, 256, 0, ST(stream)>>>(*p);
-  else if (p->in_f32) layernorm_any_kernel<true, false><<<grid, 256, 0, ST(stream)>>>(*p);
-  else if (p->out_f32) layernorm_any_kernel<false, true><<<grid, 256, 0, ST(stream)>>>(*p);
-  else layernorm_any_kernel<false, false><<<grid, 256, 0, ST(stream)>>>(*p);
+  // rows per warp by width: 4 up to 256 channels, 2 up to 768, 1 beyond (registers: R * dim / 32 floats)
+#define UDB_LN_ANY(R_, NV_)                                                                                        \
+  do {                                                                                                             \
+    const int grid = (int)((p->rows + 8 * (R_) - 1) / (8 * (R_)));                                                 \
+    if (p->in_f32 && p->out_f32) layernorm_any_kernel<true, true, R_, NV_><<<grid, 256, 0, ST(stream)>>>(*p);     \
+    else if (p->in_f32) layernorm_any_kernel<true, false, R_, NV_><<<grid, 256, 0, ST(stream)>>>(*p);             \
+    else if (p->out_f32) layernorm_any_kernel<false, true, R_, NV_><<<grid, 256, 0, ST(stream)>>>(*p);            \
+    else layernorm_any_kernel<false, false, R_, NV_><<<grid, 256, 0, ST(stream)>>>(*p);                           \
+  } while (0)
+  if (p->dim <= 256) UDB_LN_ANY(4, 4);
+  else if (p->dim <= 768) UDB_LN_ANY(2, 12);
+  else UDB_LN_ANY(1, 24);
+#undef UDB_LN_ANY
   return check_launch("layernorm_any_kernel");
 }
 
 int udb_dwconv7_nhwc_f16(const void* x, const float* w, const float* bias, void* y, int32_t B, int32_t H, int32_t W, int32_t C, void* stream) {
   if (C % DW_CB) { set_error("udb_dwconv7_nhwc_f16: C=%d must be a multiple of 64", C); return 1; }
-  const int tx = (W + DW_TW - 1) / DW_TW, ty = (H + DW_TH - 1) / DW_TH;
-  dim3 grid(tx * ty, C / DW_CB, B);
+  // 16x8 or 8x16 (W x H) pixel tiles: whichever pads the map less
+  const long long area16 = (long long)((W + 15) / 16) * ((H + 7) / 8), area8 = (long long)((W + 7) / 8) * ((H + 15) / 16);
   note_work(2.0 * 49 * B * H * W * C, 4.0 * B * H * W * C);
-  dwconv7_kernel<<<grid, 256, 0, ST(stream)>>>(reinterpret_cast<const __half*>(x), w, bias, reinterpret_cast<__half*>(y), H, W, C, tx);
+  const __half* xh = reinterpret_cast<const __half*>(x);
+  __half* yh = reinterpret_cast<__half*>(y);
+  if (area16 <= area8) {
+    const int tx = (W + 15) / 16, ty = (H + 7) / 8;
+    dwconv7_kernel<16><<<dim3(tx * ty, C / DW_CB, B), 256, 0, ST(stream)>>>(xh, w, bias, yh, H, W, C, tx);
+  } else {
+    const int tx = (W + 7) / 8, ty = (H + 15) / 16;
+    dwconv7_kernel<8><<<dim3(tx * ty, C / DW_CB, B), 256, 0, ST(stream)>>>(xh, w, bias, yh, H, W, C, tx);
+  }
   return check_launch("dwconv7_kernel");
 }
 
@@ -785,21 +903,26 @@ int udb_v1_camera_intrinsics(const float* x4, const float* gt_k, int32_t B, int3
   return check_launch("v1_camera_intrinsics_kernel");
 }
 
-int udb_cross_attn_small(const float* q, const float* q_pos, const void* kv, float* out, int32_t B, int32_t nq, int32_t nk, int32_t D, float scale,
-                         void* stream) {
-  const size_t smem = (size_t)(nk + D + 8) * 4;
-  if (smem > 200 * 1024 || D % 64) { set_error("udb_cross_attn_small: nk=%d D=%d unsupported", nk, D); return 1; }
+int udb_cross_attn_small(const float* q, const float* q_pos, const void* kv, float* out, float* scratch, int32_t B, int32_t nq, int32_t nk,
+                         int32_t D, float scale, void* stream) {
+  if (nq < 1 || nq > CA_MAXQ || D % 256 || !scratch) { set_error("udb_cross_attn_small: nq=%d D=%d unsupported (nq <= 4, D %% 256 == 0)", nq, D); return 1; }
+  const int chunk = (nk + CA_SPLITS - 1) / CA_SPLITS;
+  const size_t smem = (size_t)(nq * D + nq * chunk + 16) * 4;
+  if (smem > 200 * 1024) { set_error("udb_cross_attn_small: nk=%d too large", nk); return 1; }
   static std::atomic<size_t> set_for[64];
   int dev = 0;
   cudaGetDevice(&dev);
   if (smem > 48 * 1024 && smem > set_for[dev & 63].load()) {
-    if (cudaFuncSetAttribute(cross_attn_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(cross_attn_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
       set_error("udb_cross_attn_small: cudaFuncSetAttribute failed"); return 1;
     }
     set_for[dev & 63].store(smem);
   }
-  cross_attn_small_kernel<<<dim3(nq, B), 256, smem, ST(stream)>>>(q, q_pos, reinterpret_cast<const __half*>(kv), out, nq, nk, D, scale);
-  return check_launch("cross_attn_small_kernel");
+  note_work(4.0 * B * nq * (double)nk * D, 4.0 * B * nk * D);
+  cross_attn_partial_kernel<<<dim3(CA_SPLITS, B), 256, smem, ST(stream)>>>(q, q_pos, reinterpret_cast<const __half*>(kv), scratch, nq, nk, D, scale);
+  if (check_launch("cross_attn_partial_kernel")) return 1;
+  cross_attn_merge_kernel<<<dim3(nq, B), 256, 0, ST(stream)>>>(scratch, out, nq, D);
+  return check_launch("cross_attn_merge_kernel");
 }
 
 int udb_softmax_rows(const float* s, void* p, int64_t rows, int32_t n_valid, int32_t ld_in, int32_t ld_out, float scale, void* stream) {
@@ -823,9 +946,15 @@ int udb_copy_rows_f32_to_f16(const float* src, void* dst, int32_t groups, int32_
 }
 
 int udb_conv3x3_c1_exp(const void* x, const float* w, float bias, float* out, int32_t B, int32_t H, int32_t W, int32_t C, void* stream) {
-  if (C % 2) { set_error("udb_conv3x3_c1_exp: C must be even"); return 1; }
+  if (C != 64 && C != 128 && C != 256) { set_error("udb_conv3x3_c1_exp: C=%d unsupported (64, 128 or 256)", C); return 1; }
   const long long px = (long long)B * H * W;
-  conv3x3_c1_kernel<<<(int)((px + 7) / 8), 256, 0, ST(stream)>>>(reinterpret_cast<const __half*>(x), w, bias, out, B, H, W, C);
+  const int lpp = C / 8, ppb = 8 * (32 / lpp);
+  const int grid = (int)((px + ppb - 1) / ppb);
+  note_work(2.0 * px * 9 * C, 2.0 * px * C + 4.0 * px);
+  const __half* xh = reinterpret_cast<const __half*>(x);
+  if (lpp == 8) conv3x3_c1_kernel<8><<<grid, 256, 0, ST(stream)>>>(xh, w, bias, out, B, H, W, C);
+  else if (lpp == 16) conv3x3_c1_kernel<16><<<grid, 256, 0, ST(stream)>>>(xh, w, bias, out, B, H, W, C);
+  else conv3x3_c1_kernel<32><<<grid, 256, 0, ST(stream)>>>(xh, w, bias, out, B, H, W, C);
   return check_launch("conv3x3_c1_kernel");
 }
 
@@ -854,7 +983,7 @@ int udb_nystrom_k2_pinv(const void* landmarks, float* k2, float* z, float* tmp, 
     a.Bp = Bm; a.sB1 = mm; a.sB2 = 0; a.ldb = m; a.b_f16 = 0; a.inner = 1;
     a.C = C; a.sC1 = mm; a.sC2 = 0; a.ldc = m; a.c_f16 = 0;
     a.M = m; a.N = m; a.K = m; a.alpha = alpha; a.diag = diag;
-    bmm_f32_kernel<<<dim3(m / 32, m / 32, nb), 256, 0, ST(stream)>>>(a);
+    bmm_f32_kernel<<<dim3(m / 64, m / 64, nb), 256, 0, ST(stream)>>>(a);
     return check_launch("bmm_f32_kernel");
   };
   float* Z = z;
@@ -885,7 +1014,7 @@ int udb_nystrom_zk3(const float* z, const void* k3, int32_t ldk3, void* out, int
   a.Bp = k3; a.sB1 = (long long)m * ldk3; a.sB2 = 64; a.ldb = ldk3; a.b_f16 = 1; a.inner = heads;
   a.C = out; a.sC1 = (long long)m * ldo; a.sC2 = 64; a.ldc = ldo; a.c_f16 = 1;
   a.M = m; a.N = 64; a.K = m; a.alpha = 1.f; a.diag = 0.f;
-  bmm_f32_kernel<<<dim3(2, m / 32, B * heads), 256, 0, ST(stream)>>>(a);
+  bmm_f32_kernel<<<dim3(1, m / 64, B * heads), 256, 0, ST(stream)>>>(a);
   return check_launch("bmm_f32_kernel");
 }
 

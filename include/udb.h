@@ -107,6 +107,20 @@ typedef struct udb_gemm_t {
    * split operand for the next GEMM. */
   int32_t a_split_k;
   int32_t out_split;
+  /* Fused LayerNorm (the north_star's "fused LayerNorm + QKV projection"; reference metadinov2/block.py:84-109: the
+   * LayerNorm that follows a residual update never runs as its own pass).
+   * PRODUCER (ln_stats_out != NULL, ROWS store): besides its normal outputs the GEMM writes, for every output row and
+   * every (column tile, column half) part, float2 {mean, centred sum of squares} of the values it stored:
+   * ln_stats_out[(row * ln_parts + part)], ln_parts = (N / tile width) * 2, ln_part_cols = tile width / 2 (the call
+   * fails if the caller's ln_parts / ln_part_cols do not match the tiling).  Use out2 for the f16 copy of the rows.
+   * CONSUMER (ln_stats_in != NULL): A is that un-normalised f16 copy, W holds W * diag(ln_weight); the epilogue merges the
+   * row's parts into mean / rstd (eps = ln_eps) and computes rstd * (acc - mean * ln_c1[n]) + bias[n], with
+   * ln_c1[n] = sum_k W'[n,k] and bias = W ln_bias + linear bias -- algebraically LayerNorm followed by the Linear. */
+  float* ln_stats_out;
+  const float* ln_stats_in;
+  const float* ln_c1;
+  int32_t ln_parts, ln_part_cols;
+  float ln_eps;
 } udb_gemm_t;
 
 int udb_gemm_f16(const udb_gemm_t* g, void* stream);
@@ -210,6 +224,10 @@ int udb_posembed_bicubic(const float* grid, int32_t m, int32_t dim, float* out, 
 /* x[b, 0, :] = cls_token + pos_embed[0]   (dinov2.py:314-315); x f32 [B, T, D]. */
 int udb_set_cls_rows(float* x, const float* cls_token, const float* pos0, int32_t B, int32_t T,
                      int32_t D, void* stream);
+/* Same, for the fused-LayerNorm encoder (udb_gemm_t.ln_*): also writes the f16 copy of the cls rows and their per-part
+ * {mean, centred sum of squares} (parts * part_cols == D, the producer GEMMs' tiling). */
+int udb_set_cls_rows_ln(float* x, void* x16, float* stats, const float* cls_token, const float* pos0, int32_t B, int32_t T,
+                        int32_t D, int32_t parts, int32_t part_cols, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Small fp32 dense layer for the 4-token camera head (unidepthv2/decoder.py:101-111), kept in

@@ -242,3 +242,48 @@ def test_split_f16_gemm_layernorm_attention():
     err = ((rec.double().transpose(1, 2) - aref).abs().max() / aref.abs().max()).item()
     print(f"split attention max err: {err:.2e}")
     assert err < 1e-5
+
+
+@pytest.mark.parametrize("D", [1024, 768, 384])
+def test_fused_layernorm_producer_consumer(D):
+    """udb_gemm_t.ln_*: a residual-updating GEMM writes per-part row statistics + the f16 copy of its rows; the next GEMM
+    applies LayerNorm algebraically in its epilogue.  Reference: LayerNorm(x) @ W^T + b in float64 on the producer's f32 output."""
+    from unidepth_b200 import ops
+    dev = _dev()
+    g = torch.Generator(device="cpu").manual_seed(D)
+    M, K0, N2 = 1500, 256, 640
+    bn = 256 if D % 256 == 0 else (192 if D % 192 == 0 else 128)
+    parts, pc = D // bn * 2, bn // 2
+    a = torch.randn(M, K0, generator=g).to(dev).half()
+    w0 = (torch.randn(D, K0, generator=g) / 16).to(dev).half()
+    x_in = (torch.randn(M, D, generator=g) * 1.5 + 0.3).to(dev)            # residual stream with a non-zero mean
+    gamma = torch.rand(D, generator=g).to(dev)
+    x = x_in.clone()
+    x16 = torch.empty(M, D, device=dev, dtype=torch.float16)
+    stats = torch.zeros(M, parts, 2, device=dev)
+    ops.gemm(a, w0, gamma=gamma, resid=x, out=x, out2=x16, out2_leaky=False, ln_stats_out=stats, ln_parts=parts, ln_part_cols=pc)
+    xr = x_in.double() + gamma.double() * (a.double() @ w0.double().T)
+    assert (x.double() - xr).abs().max().item() < 2e-4
+    assert (x16.float() - x).abs().max().item() <= 2.0 ** -10 * x.abs().max().item()
+    # merged statistics == row mean / variance
+    mean_p, m2_p = stats[..., 0].double(), stats[..., 1].double()
+    mean = mean_p.mean(1)
+    var = (m2_p.sum(1) + pc * ((mean_p - mean[:, None]) ** 2).sum(1)) / D
+    assert (mean - x.double().mean(1)).abs().max().item() < 1e-5
+    assert ((var - x.double().var(1, unbiased=False)).abs() / x.double().var(1, unbiased=False)).max().item() < 1e-5
+    # consumer
+    lnw, lnb = (1 + 0.2 * torch.randn(D, generator=g)).to(dev), (0.1 * torch.randn(D, generator=g)).to(dev)
+    w1 = (torch.randn(N2, D, generator=g) / 32).to(dev)
+    b1 = torch.randn(N2, generator=g).to(dev)
+    wf = (w1 * lnw).half()
+    c1 = wf.float().sum(1).contiguous()
+    c2 = (w1 @ lnb + b1).contiguous()
+    y = ops.gemm(x16, wf.contiguous(), bias=c2, out_dtype=torch.float32, ln_stats_in=stats, ln_c1=c1, ln_parts=parts, ln_part_cols=pc,
+                 ln_eps=1e-6)
+    ref = torch.nn.functional.layer_norm(x.double(), (D,), lnw.double(), lnb.double(), 1e-6) @ w1.double().T + b1.double()
+    err = ((y.double() - ref).abs().max() / ref.abs().max()).item()
+    h = torch.nn.functional.layer_norm(x, (D,), lnw, lnb, 1e-6).half()
+    plain = ops.gemm(h, w1.half().contiguous(), bias=b1, out_dtype=torch.float32)
+    err_plain = ((plain.double() - ref).abs().max() / ref.abs().max()).item()
+    print(f"fused LN->Linear D={D}: max err / max|ref| {err:.2e} (stand-alone LayerNorm + GEMM: {err_plain:.2e})")
+    assert err < 3 * max(err_plain, 3e-4)

@@ -43,7 +43,7 @@ def test_ctypes_structs_match_c_layout():
                "udb_v1_preprocess_t": _cabi.V1Preprocess, "udb_layernorm_any_t": _cabi.LayerNormAny, "udb_v1_rays_t": _cabi.V1Rays,
                "udb_v1_postprocess_t": _cabi.V1Postprocess, "udb_v1_config_t": _cabi.V1Config, "udb_infer_v1_args_t": _cabi.InferV1Args,
                "udb_profile_entry_t": _cabi.ProfileEntry}
-    last = {"udb_gemm_t": "out_split", "udb_conv_halo_t": "head_out", "udb_attn_t": "lo_off_o", "udb_layernorm_t": "out_split", "udb_preprocess_t": "split",
+    last = {"udb_gemm_t": "ln_eps", "udb_conv_halo_t": "head_out", "udb_attn_t": "lo_off_o", "udb_layernorm_t": "out_split", "udb_preprocess_t": "split",
             "udb_small_linear_t": "ldr", "udb_ray_embed_t": "out_f32", "udb_postprocess_t": "out_rays",
             "udb_config_t": "pixels_max", "udb_geometry_t": "factor", "udb_infer_args_t": "depth_features",
             "udb_v1_preprocess_t": "patches", "udb_layernorm_any_t": "s2d_w", "udb_v1_rays_t": "sh_k", "udb_v1_postprocess_t": "out_points",

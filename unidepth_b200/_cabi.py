@@ -30,6 +30,7 @@ class Gemm(C.Structure):
         ("ct_k", i32), ("ct_cout", i32), ("ct_h", i32), ("ct_w", i32), ("ct_pad", i32),
         ("head_w", vp), ("head_b", f32), ("head_add", f32),
         ("a_split_k", i32), ("out_split", i32),
+        ("ln_stats_out", vp), ("ln_stats_in", vp), ("ln_c1", vp), ("ln_parts", i32), ("ln_part_cols", i32), ("ln_eps", f32),
     ]
 
 
@@ -181,6 +182,7 @@ EXPORTS = {
     "udb_preprocess_patchify": (i32, [C.POINTER(Preprocess), vp]),
     "udb_posembed_bicubic": (i32, [vp, i32, i32, vp, i32, i32, vp]),
     "udb_set_cls_rows": (i32, [vp, vp, vp, i32, i32, i32, vp]),
+    "udb_set_cls_rows_ln": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "udb_small_linear_f32": (i32, [C.POINTER(SmallLinear), vp]),
     "udb_camera_attn4_f32": (i32, [vp, vp, vp, vp, i32, i32, i32, vp]),
     "udb_camera_intrinsics": (i32, [vp, i32, i32, i32, f32, i32, i32, vp, vp, vp, vp]),

@@ -255,6 +255,33 @@ __global__ void set_cls_rows_kernel(float* x, const float* cls, const float* pos
   x[(long long)b * T * D + d] = cls[d] + pos0[d];
 }
 
+// cls rows for the fused-LayerNorm encoder: besides x (f32) also the f16 copy and the per-part {mean, centred sum of
+// squares} the consumer GEMM merges (udb_gemm_t.ln_stats_in).  One block per image, warp w handles parts w, w+8, ...
+__global__ void __launch_bounds__(256) set_cls_rows_ln_kernel(float* x, __half* x16, float* stats, const float* cls, const float* pos0, int T, int D,
+                                                             int parts, int part_cols) {
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)b * T;
+  for (int pt = warp; pt < parts; pt += 8) {
+    float s = 0.f;
+    for (int c = lane; c < part_cols; c += 32) {
+      const int d = pt * part_cols + c;
+      const float v = cls[d] + pos0[d];
+      x[row * D + d] = v;
+      x16[row * D + d] = __float2half_rn(v);
+      s += v;
+    }
+    const float mean = warp_sum(s) / (float)part_cols;
+    float m2 = 0.f;
+    for (int c = lane; c < part_cols; c += 32) {
+      const int d = pt * part_cols + c;
+      const float dl = cls[d] + pos0[d] - mean;
+      m2 += dl * dl;
+    }
+    m2 = warp_sum(m2);
+    if (lane == 0) reinterpret_cast<float2*>(stats)[row * parts + pt] = make_float2(mean, m2);
+  }
+}
+
 // ------------------------------------------------------------------------------------ camera head (fp32)
 // one warp per output feature and 8 rows (the 32-row camera head is latency bound: favour many
 // small warps over reuse); lanes stride over K with 128-bit loads when K % 128 == 0
@@ -627,6 +654,13 @@ extern "C" int udb_posembed_bicubic(const float* grid, int32_t m, int32_t dim, f
 extern "C" int udb_set_cls_rows(float* x, const float* cls_token, const float* pos0, int32_t B, int32_t T, int32_t D, void* stream) {
   set_cls_rows_kernel<<<(B * D + 255) / 256, 256, 0, ST(stream)>>>(x, cls_token, pos0, B, T, D);
   return check_launch("set_cls_rows_kernel");
+}
+
+extern "C" int udb_set_cls_rows_ln(float* x, void* x16, float* stats, const float* cls_token, const float* pos0, int32_t B, int32_t T, int32_t D,
+                                   int32_t parts, int32_t part_cols, void* stream) {
+  if (parts * part_cols != D) { set_error("udb_set_cls_rows_ln: parts * part_cols != D"); return 1; }
+  set_cls_rows_ln_kernel<<<B, 256, 0, ST(stream)>>>(x, reinterpret_cast<__half*>(x16), stats, cls_token, pos0, T, D, parts, part_cols);
+  return check_launch("set_cls_rows_ln_kernel");
 }
 
 extern "C" int udb_small_linear_f32(const udb_small_linear_t* p, void* stream) {

@@ -93,6 +93,14 @@ static int run(udb_engine* e, const udb_infer_args_t& a, const udb_geometry_t& g
   // cls tokens / camera head are fp32 anyway, so the intrinsics then carry no f16 operand rounding at all.
   const bool sp = e->scalars.count("precision") && e->scalars["precision"] == 1.0;
   const int sx = sp ? 2 : 1;
+  // Fused LayerNorm (udb_set_scalar("fuse_ln", 1), default f16 mode): norm1 / norm2 never run as their own pass.  The GEMM
+  // that updates the residual stream (patch embed, attn.proj, mlp.fc2) also writes the f16 copy of its rows and their
+  // per-part statistics; qkv / fc1 read that copy with LayerNorm-folded weights (udb_gemm_t.ln_*; block.py:84-109).
+  const bool fuse = !sp && e->scalars.count("fuse_ln") && e->scalars["fuse_ln"] == 1.0;
+  const int ln_bn = D % 256 == 0 ? 256 : (D % 192 == 0 ? 192 : (D % 128 == 0 ? 128 : 64));   // udb_gemm_f16's tile width for N = D
+  const int ln_parts = D / ln_bn * 2, ln_pc = ln_bn / 2;
+  __half* x16 = fuse ? ar.h(BT * D) : nullptr;
+  float* stats = fuse ? ar.f(BT * ln_parts * 2) : nullptr;
   __half* patches = ar.h(BN * 640 * sx);
   if (!c.dry) {
     udb_preprocess_t p;
@@ -109,8 +117,11 @@ static int run(udb_engine* e, const udb_infer_args_t& a, const udb_geometry_t& g
     q.bias = c.F("patch_b"); q.resid = tb.pos; q.resid_f32 = 1; q.ldr = D; q.out = x; q.out_f32 = 1;
     q.rows_per_group = N; q.group_stride = T; q.row_offset = 1; q.resid_mod = N; q.resid_row_offset = 1;
     if (sp) c.expect2("patch_w", D, 3 * 640);
+    if (fuse) { q.out2 = x16; q.out2_leaky = 0; q.ln_stats_out = stats; q.ln_parts = ln_parts; q.ln_part_cols = ln_pc; }
     c.gemm(q);
-    if (!c.dry && !c.rc) c.done(udb_set_cls_rows(x, c.F("cls"), tb.pos, B, T, D, st));
+    if (!c.dry && !c.rc)
+      c.done(fuse ? udb_set_cls_rows_ln(x, x16, stats, c.F("cls"), tb.pos, B, T, D, ln_parts, ln_pc, st)
+                  : udb_set_cls_rows(x, c.F("cls"), tb.pos, B, T, D, st));
   }
 
   // ---- a5-a8: transformer blocks, taps through the final norm
@@ -120,7 +131,7 @@ static int run(udb_engine* e, const udb_infer_args_t& a, const udb_geometry_t& g
   for (int l = 0; l < 4; ++l) { feats[l] = ar.h(BN * D); clss[l] = ar.f(static_cast<size_t>(B) * D); }
   {
     const size_t m = ar.mark();
-    __half* h = ar.h(BT * D * sx);
+    __half* h = fuse ? nullptr : ar.h(BT * D * sx);
     __half* qkv = ar.h(BT * 3 * D * sx);
     __half* att = ar.h(BT * D * sx);
     __half* mid = ar.h(BT * 4 * D * sx);
@@ -130,21 +141,37 @@ static int run(udb_engine* e, const udb_infer_args_t& a, const udb_geometry_t& g
       const std::string b = idx("blocks.%d.", i);
       if (sp) { c.expect2(b + "qkv_w", 3 * D, 3 * D); c.expect2(b + "proj_w", D, 3 * D); c.expect2(b + "fc1_w", 4 * D, 3 * D);
                 c.expect2(b + "fc2_w", D, 12 * D); }
-      c.layernorm(x, 1, h, 0, c.F(b + "n1w"), c.F(b + "n1b"), static_cast<int>(BT), D, 1e-6f, 0, 0, 0, 0, sp ? D : 0);
-      { Ctx::G q{h, c.H(b + "qkv_w"), static_cast<int>(BT), 3 * D, D * kx}; q.lda = D * sx; q.a_split_k = sp ? D : 0;
-        q.bias = c.F(b + "qkv_b"); q.out = qkv; q.ldc = 3 * D * sx; q.out_split = sp ? 3 * D : 0; c.gemm(q); }
+      if (fuse) {
+        Ctx::G q{x16, c.H(b + "qkv_wf"), static_cast<int>(BT), 3 * D, D};
+        q.bias = c.F(b + "qkv_c2"); q.ln_stats_in = stats; q.ln_c1 = c.F(b + "qkv_c1"); q.ln_parts = ln_parts; q.ln_part_cols = ln_pc;
+        q.ln_eps = 1e-6f; q.out = qkv; c.gemm(q);
+      } else {
+        c.layernorm(x, 1, h, 0, c.F(b + "n1w"), c.F(b + "n1b"), static_cast<int>(BT), D, 1e-6f, 0, 0, 0, 0, sp ? D : 0);
+        Ctx::G q{h, c.H(b + "qkv_w"), static_cast<int>(BT), 3 * D, D * kx}; q.lda = D * sx; q.a_split_k = sp ? D : 0;
+        q.bias = c.F(b + "qkv_b"); q.out = qkv; q.ldc = 3 * D * sx; q.out_split = sp ? 3 * D : 0; c.gemm(q);
+      }
       c.attention(qkv, qkv, qkv, att, B, cf.enc_heads, T, T, 3 * D * sx, 3 * D * sx, 3 * D * sx, D * sx, 0, D, 2 * D, 0.125f,
                   sp ? 3 * D : 0, sp ? D : 0);
       { Ctx::G q{att, c.H(b + "proj_w"), static_cast<int>(BT), D, D * kx}; q.lda = D * sx; q.a_split_k = sp ? D : 0;
         q.bias = c.F(b + "proj_b"); q.gamma = c.F(b + "ls1");
-        q.resid = x; q.resid_f32 = 1; q.out = x; q.out_f32 = 1; c.gemm(q); }
-      c.layernorm(x, 1, h, 0, c.F(b + "n2w"), c.F(b + "n2b"), static_cast<int>(BT), D, 1e-6f, 0, 0, 0, 0, sp ? D : 0);
-      { Ctx::G q{h, c.H(b + "fc1_w"), static_cast<int>(BT), 4 * D, D * kx}; q.lda = D * sx; q.a_split_k = sp ? D : 0;
+        q.resid = x; q.resid_f32 = 1; q.out = x; q.out_f32 = 1;
+        if (fuse) { q.out2 = x16; q.out2_leaky = 0; q.ln_stats_out = stats; q.ln_parts = ln_parts; q.ln_part_cols = ln_pc; }
+        c.gemm(q); }
+      if (fuse) {
+        Ctx::G q{x16, c.H(b + "fc1_wf"), static_cast<int>(BT), 4 * D, D};
+        q.bias = c.F(b + "fc1_c2"); q.ln_stats_in = stats; q.ln_c1 = c.F(b + "fc1_c1"); q.ln_parts = ln_parts; q.ln_part_cols = ln_pc;
+        q.ln_eps = 1e-6f; q.act = UDB_ACT_GELU; q.out = mid; c.gemm(q);
+      } else {
+        c.layernorm(x, 1, h, 0, c.F(b + "n2w"), c.F(b + "n2b"), static_cast<int>(BT), D, 1e-6f, 0, 0, 0, 0, sp ? D : 0);
+        Ctx::G q{h, c.H(b + "fc1_w"), static_cast<int>(BT), 4 * D, D * kx}; q.lda = D * sx; q.a_split_k = sp ? D : 0;
         q.bias = c.F(b + "fc1_b"); q.act = UDB_ACT_GELU;
-        q.out = mid; q.ldc = 4 * D * sx; q.out_split = sp ? 4 * D : 0; c.gemm(q); }
+        q.out = mid; q.ldc = 4 * D * sx; q.out_split = sp ? 4 * D : 0; c.gemm(q);
+      }
       { Ctx::G q{mid, c.H(b + "fc2_w"), static_cast<int>(BT), D, 4 * D * kx}; q.lda = 4 * D * sx; q.a_split_k = sp ? 4 * D : 0;
         q.bias = c.F(b + "fc2_b"); q.gamma = c.F(b + "ls2");
-        q.resid = x; q.resid_f32 = 1; q.out = x; q.out_f32 = 1; c.gemm(q); }
+        q.resid = x; q.resid_f32 = 1; q.out = x; q.out_f32 = 1;
+        if (fuse) { q.out2 = x16; q.out2_leaky = 0; q.ln_stats_out = stats; q.ln_parts = ln_parts; q.ln_part_cols = ln_pc; }
+        c.gemm(q); }
       if (tap < 4 && i + 1 == cf.taps[tap]) {
         c.layernorm(x, 1, feats[tap], 0, c.F("norm_w"), c.F("norm_b"), static_cast<int>(BN), D, 1e-5f, N, T, 1);
         c.layernorm(x, 1, clss[tap], 1, c.F("norm_w"), c.F("norm_b"), B, D, 1e-5f, 1, T, 0);

@@ -109,6 +109,8 @@ struct Ctx {
     long long ldr = 0; void* out = nullptr; int out_f32 = 0; long long ldc = 0; void* out2 = nullptr; int out2_leaky = 1;
     int act = UDB_ACT_NONE; int rows_per_group = 0, group_stride = 0, row_offset = 0, resid_mod = 0, resid_row_offset = 0;
     int a_split_k = 0, out_split = 0;    // split-f16 precise mode (udb_gemm_t)
+    float* ln_stats_out = nullptr; const float* ln_stats_in = nullptr; const float* ln_c1 = nullptr;   // fused LayerNorm (udb_gemm_t.ln_*)
+    int ln_parts = 0, ln_part_cols = 0; float ln_eps = 0.f;
   };
   void gemm(const G& q) {
     if (dry || rc) return;
@@ -125,6 +127,8 @@ struct Ctx {
     g.rows_per_group = q.rows_per_group; g.group_stride = q.group_stride; g.row_offset = q.row_offset;
     g.resid_mod = q.resid_mod; g.resid_row_offset = q.resid_row_offset;
     g.a_split_k = q.a_split_k; g.out_split = q.out_split;
+    g.ln_stats_out = q.ln_stats_out; g.ln_stats_in = q.ln_stats_in; g.ln_c1 = q.ln_c1;
+    g.ln_parts = q.ln_parts; g.ln_part_cols = q.ln_part_cols; g.ln_eps = q.ln_eps;
     done(udb_gemm_f16(&g, st));
   }
   // ConvTranspose2d with kernel == stride == k as a GEMM with a pixel-shuffle store (ops.conv_transpose_ks)

@@ -46,6 +46,15 @@ struct GemmArgs {
   float head_b, head_add;
   int a_wrap;      // split-f16 operands: k-blocks at or beyond this element offset re-read A from (k - a_wrap); 0 = off
   int out_split;   // f16 `out`: lo half stored out_split elements to the right; 0 = off
+  // Fused LayerNorm (udb_gemm_t.ln_*): a PRODUCER writes, per output row and per (column tile, column half), the mean and
+  // the centred sum of squares of the values it stores; a CONSUMER whose A operand is the un-normalised f16 copy of those
+  // rows merges the partials and applies  v = rstd * (acc - mean * c1[n]) + bias[n]  (weights pre-multiplied by the
+  // LayerNorm scale, c1 = their row sums, bias = W ln_bias + bias).
+  float* stats_out;
+  const float* ln_stats;
+  const float* ln_c1;
+  int ln_parts, ln_part_cols;
+  float ln_eps;
 };
 
 template <int BN>
@@ -118,6 +127,23 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, const EpiWarp& 
         roff_res[lane] = static_cast<uint32_t>(res_off);
         __syncwarp();
         const uint32_t t_row = t_acc + (static_cast<uint32_t>(quad * 32) << 16);
+        // fused LayerNorm, consumer side: merge this row's partial statistics (equal counts: plain mean of the means,
+        // M2 = sum M2_p + n_p * sum (mean_p - mean)^2)
+        float ln_mean = 0.f, ln_rstd = 1.f;
+        if (p.ln_stats) {
+          const float2* sp = reinterpret_cast<const float2*>(p.ln_stats) + (long long)(valid ? m : 0) * p.ln_parts;
+          float ms = 0.f, m2 = 0.f;
+          for (int q = 0; q < p.ln_parts; ++q) ms += sp[q].x;
+          ln_mean = ms / (float)p.ln_parts;
+          for (int q = 0; q < p.ln_parts; ++q) {
+            const float2 t = sp[q];
+            m2 += t.y + (float)p.ln_part_cols * (t.x - ln_mean) * (t.x - ln_mean);
+          }
+          ln_rstd = rsqrtf(m2 / (float)(p.ln_parts * p.ln_part_cols) + p.ln_eps);
+        }
+        // fused LayerNorm, producer side: running (pivot-shifted) sums over this thread's columns of the tile
+        float st_pivot = 0.f, st_s1 = 0.f, st_s2 = 0.f;
+        bool st_first = true;
 #pragma unroll 1
         for (int c = 0; c < kColsPerGrp; c += 32) {
           const int col = grp * kColsPerGrp + c;   // column inside the tile
@@ -129,6 +155,18 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, const EpiWarp& 
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.ln_stats) {
+            const float4* cp = reinterpret_cast<const float4*>(p.ln_c1 + n0);
+            const float mr = ln_mean * ln_rstd;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 c4 = __ldg(cp + j);
+              v[4 * j] = fmaf(v[4 * j], ln_rstd, -mr * c4.x);
+              v[4 * j + 1] = fmaf(v[4 * j + 1], ln_rstd, -mr * c4.y);
+              v[4 * j + 2] = fmaf(v[4 * j + 2], ln_rstd, -mr * c4.z);
+              v[4 * j + 3] = fmaf(v[4 * j + 3], ln_rstd, -mr * c4.w);
+            }
+          }
           if (p.bias) {
             const float4* bp = reinterpret_cast<const float4*>(p.bias + n0);
 #pragma unroll
@@ -221,6 +259,15 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, const EpiWarp& 
             }
             __syncwarp();
           }
+          if (p.stats_out) {
+            if (st_first) { st_pivot = v[0]; st_first = false; }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float dlt = v[j] - st_pivot;
+              st_s1 += dlt;
+              st_s2 = fmaf(dlt, dlt, st_s2);
+            }
+          }
           if (p.out) {
             stage_rows(v);
             __syncwarp();
@@ -268,6 +315,13 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, const EpiWarp& 
             });
             __syncwarp();
           }
+        }
+        if (p.stats_out && valid && !st_first) {
+          const float n = (float)kColsPerGrp;
+          const float mean_p = st_pivot + st_s1 / n;
+          const float m2_p = fmaxf(st_s2 - st_s1 * st_s1 / n, 0.f);
+          const long long orow = out_off / p.ldc;
+          reinterpret_cast<float2*>(p.stats_out)[orow * (p.tiles_n * kGroups) + nt * kGroups + grp] = make_float2(mean_p, m2_p);
         }
       }
 }
@@ -683,6 +737,14 @@ extern "C" int udb_gemm_f16(const udb_gemm_t* g, void* stream) {
     }
     a.a_wrap = 2 * g->a_split_k;
   }
+  a.stats_out = g->ln_stats_out; a.ln_stats = g->ln_stats_in; a.ln_c1 = g->ln_c1; a.ln_eps = g->ln_eps;
+  a.ln_parts = g->ln_parts; a.ln_part_cols = g->ln_part_cols;
+  if ((g->ln_stats_out || g->ln_stats_in) && g->store_mode != UDB_STORE_ROWS) {
+    set_error("udb_gemm_f16: fused LayerNorm statistics need the ROWS store"); return 1;
+  }
+  if (g->ln_stats_in && (!g->ln_c1 || g->ln_parts <= 0 || g->ln_part_cols <= 0 || g->rows_per_group > 0)) {
+    set_error("udb_gemm_f16: ln_stats_in needs ln_c1, ln_parts, ln_part_cols and an identity row map"); return 1;
+  }
   if (g->out_split && (g->out_f32 || !g->out || g->store_mode != UDB_STORE_ROWS)) {
     set_error("udb_gemm_f16: out_split needs an f16 `out` with the ROWS store"); return 1;
   }
@@ -706,6 +768,14 @@ extern "C" int udb_gemm_f16(const udb_gemm_t* g, void* stream) {
     set_error("udb_gemm_f16: CONVT needs Cout %% 32 == 0"); return 1;
   }
   a.tiles_n = (g->N + bn - 1) / bn;
+  if (g->ln_stats_out) {
+    const int groups = bn >= 64 ? 2 : 1;
+    if (g->N % bn || g->ln_parts != a.tiles_n * groups || g->ln_part_cols != bn / groups) {
+      set_error("udb_gemm_f16: ln_stats_out with N=%d runs as %d parts of %d columns (caller said %d x %d)", g->N, a.tiles_n * groups,
+                bn / groups, g->ln_parts, g->ln_part_cols);
+      return 1;
+    }
+  }
   const bool use_pair = pair_env != 0 && (bn == 256 || bn == 192 || bn == 128);
 
   CUtensorMap tmA, tmB;

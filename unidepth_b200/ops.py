@@ -56,7 +56,8 @@ def _is32(t):
 def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, act=ACT_NONE, gamma=None, resid=None,
          out: Optional[torch.Tensor] = None, out_dtype=f16, out2: Optional[torch.Tensor] = None, out2_leaky=True,
          rows_per_group=0, group_stride=0, row_offset=0, resid_mod=0, resid_row_offset=0,
-         out_rows: Optional[int] = None, a_split_k: int = 0, out_split: bool = False):
+         out_rows: Optional[int] = None, a_split_k: int = 0, out_split: bool = False,
+         ln_stats_out=None, ln_stats_in=None, ln_c1=None, ln_parts: int = 0, ln_part_cols: int = 0, ln_eps: float = 0.0):
     """out[row(m), :] = resid + gamma * act(a @ w.T + bias).  a f16 [M,K], w f16 [N,K].
     Split-f16 mode (udb_gemm_t.a_split_k = K1): a is [M, 2*K1] = [hi | lo], w is [N, 3*K1] = [hi | hi | lo];
     out_split: the f16 output is written as [M, 2N] = [hi | lo]."""
@@ -85,6 +86,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, act=ACT_NONE, gamma=Non
     g.rows_per_group, g.group_stride, g.row_offset = rows_per_group, group_stride, row_offset
     g.resid_mod, g.resid_row_offset = resid_mod, resid_row_offset
     g.a_split_k, g.out_split = a_split_k, (N if out_split else 0)
+    g.ln_stats_out, g.ln_stats_in, g.ln_c1 = _ptr(ln_stats_out), _ptr(ln_stats_in), _ptr(ln_c1)
+    g.ln_parts, g.ln_part_cols, g.ln_eps = ln_parts, ln_part_cols, ln_eps
     cabi.check(_launch("gemm_f16_kernel", 2.0 * M * N * K, lambda: cabi.lib().udb_gemm_f16(C.byref(g), _stream())),
                "udb_gemm_f16")
     return out

@@ -85,6 +85,9 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
         # optional dict of preallocated output tensors (same keys / shapes as infer's result): graph-mode infer copies its
         # static outputs there instead of cloning them (parallel.PeerGather.views(): the multi-GPU send slot)
         self.output_buffers = None
+        # Fused LayerNorm (north_star: "fused LayerNorm + QKV projection"): norm1 / norm2 of the encoder blocks are folded
+        # into the qkv / fc1 GEMMs (include/udb.h udb_gemm_t.ln_*), no stand-alone LayerNorm pass.  Engine path, f16 mode.
+        self.fuse_ln = True
         self._engine = None
         self._engine_key = None
         # Bounded caches (LRU): the reference handles arbitrary shapes in constant memory, so a stream of
@@ -130,8 +133,11 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
             return model
 
     # ------------------------------------------------------------------ weight packing
+    def _fuse(self) -> bool:
+        return bool(self.fuse_ln and self.use_engine and self.precision == "f16")
+
     def _fingerprint(self):
-        return (self.precision,) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+        return (self.precision, self._fuse()) + tuple((p.data_ptr(), p._version) for p in self.parameters())
 
     def _pack(self):
         """One-time (per weight version) repack into kernel operand layouts."""
@@ -160,7 +166,16 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
             lo = (w - hi.to(f32)).to(f16)
             return torch.cat([hi, hi, lo], dim=1).contiguous()
 
-        P: dict = {"split": split}
+        fuse = self._fuse()
+
+        def ln_fold(w, b, lnw, lnb):
+            """LayerNorm folded into the Linear that follows it:  LN(x) W^T + b = rstd (x W'^T - mean c1) + c2  with
+            W' = W diag(ln_w) (f16, what the MMA multiplies), c1 = row sums of the ROUNDED W', c2 = W ln_b + b."""
+            w, b, lnw, lnb = w.float(), b.float(), lnw.float(), lnb.float()
+            wf = (w * lnw.unsqueeze(0)).to(f16)
+            return wf.contiguous(), wf.float().sum(dim=1).contiguous(), (w @ lnb + b).contiguous()
+
+        P: dict = {"split": split, "fuse_ln": fuse}
         d, hid = s.embed_dim, s.hidden
         # The attention kernel works on 64-wide heads.  Narrower decoder heads (ViT-S: 256/8 = 32) are
         # zero-padded to 64 in the packed q / kv / out weights: padded q,k columns add 0 to q.k, padded
@@ -189,6 +204,14 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
         P["blocks"] = []
         for i in range(s.depth):
             b = f"{pe}blocks.{i}."
+            if fuse:
+                qw, qc1, qc2 = ln_fold(sd[b + "attn.qkv.weight"], sd[b + "attn.qkv.bias"], sd[b + "norm1.weight"], sd[b + "norm1.bias"])
+                fw, fc1, fc2 = ln_fold(sd[b + "mlp.fc1.weight"], sd[b + "mlp.fc1.bias"], sd[b + "norm2.weight"], sd[b + "norm2.bias"])
+                P["blocks"].append(dict(
+                    qkv_wf=qw, qkv_c1=qc1, qkv_c2=qc2, fc1_wf=fw, fc1_c1=fc1, fc1_c2=fc2,
+                    proj_w=h16(sd[b + "attn.proj.weight"]), proj_b=c32(sd[b + "attn.proj.bias"]), ls1=c32(sd[b + "ls1.gamma"]),
+                    fc2_w=h16(sd[b + "mlp.fc2.weight"]), fc2_b=c32(sd[b + "mlp.fc2.bias"]), ls2=c32(sd[b + "ls2.gamma"])))
+                continue
             P["blocks"].append(dict(
                 n1w=c32(sd[b + "norm1.weight"]), n1b=c32(sd[b + "norm1.bias"]),
                 qkv_w=enc16(sd[b + "attn.qkv.weight"]), qkv_b=c32(sd[b + "attn.qkv.bias"]),
@@ -339,6 +362,7 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
                   "ln_ones", "ln_zeros"):
             T[k] = P[k]
         S["precision"] = 1.0 if P.get("split") else 0.0
+        S["fuse_ln"] = 1.0 if P.get("fuse_ln") else 0.0
         for i, blk in enumerate(P["blocks"]):
             for k, v in blk.items():
                 T[f"blocks.{i}.{k}"] = v

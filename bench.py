@@ -241,7 +241,7 @@ def main():
     ap.add_argument("--workload", default="default", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (default: the workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-fuse-ln", action="store_true", help="A/B: run norm1 / norm2 as stand-alone LayerNorm kernels")
+    ap.add_argument("--fuse-ln", action="store_true", help="A/B: fold norm1 / norm2 into the qkv / fc1 GEMMs (UniDepthV2.fuse_ln)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
@@ -279,7 +279,7 @@ def main():
         model.load_state_dict(synthetic_state_dict(cfg, 0, device=dev), strict=True)   # same seed on every rank
         model = model.to(dev).eval()
         model.resolution_level = None
-        model.fuse_ln = not args.no_fuse_ln
+        model.fuse_ln = bool(args.fuse_ln)
     B = args.batch or W["batch"]
     g = torch.Generator().manual_seed(rank)
     rgb_host = torch.randint(0, 256, (B, 3, H_in, W_in), dtype=torch.uint8, generator=g).pin_memory()
@@ -492,7 +492,7 @@ def main():
             "dtype": "f16 operands, f32 accumulate/residual", "data": "synthetic",
             "config": {"workload": W["desc"], "global_batch": B * world, "parallelism": f"dp{world}",
                        "l2": "per-step working set (f16 weights 0.4-0.7 GB + activations > 4 GB) exceeds the 126 MB L2",
-                       "fused_layernorm": (not is_v1) and (not args.no_fuse_ln),
+                       "fused_layernorm": (not is_v1) and bool(args.fuse_ln),
                        "cuda_graph": True, "engine": ("udb_infer_v1" if is_v1 else "udb_infer_v2") + " (one C call per infer)",
                        **({"collective": parallel.gather_description()} if world > 1 else {})},
             "e2e": {"value": total_images / (ms_e2e / 1000.0), "unit": "images/s",

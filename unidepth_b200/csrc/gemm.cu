@@ -81,7 +81,8 @@ struct EpiWarp {
   int quad, grp, lane, r_in_tile;
 };
 
-template <int BN>
+// LNF: compile the fused-LayerNorm producer / consumer code in (udb_gemm_t.ln_*); the default instantiation does not carry it.
+template <int BN, bool LNF = false>
 __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, const EpiWarp& w, const uint32_t t_acc,
                                               const int mt, const int nt) {
   constexpr int kGroups = BN >= 64 ? 2 : 1;
@@ -130,7 +131,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, const EpiWarp& 
         // fused LayerNorm, consumer side: merge this row's partial statistics (equal counts: plain mean of the means,
         // M2 = sum M2_p + n_p * sum (mean_p - mean)^2)
         float ln_mean = 0.f, ln_rstd = 1.f;
-        if (p.ln_stats) {
+        if (LNF && p.ln_stats) {
           const float2* sp = reinterpret_cast<const float2*>(p.ln_stats) + (long long)(valid ? m : 0) * p.ln_parts;
           float ms = 0.f, m2 = 0.f;
           for (int q = 0; q < p.ln_parts; ++q) ms += sp[q].x;
@@ -155,7 +156,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, const EpiWarp& 
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (p.ln_stats) {
+          if (LNF && p.ln_stats) {
             const float4* cp = reinterpret_cast<const float4*>(p.ln_c1 + n0);
             const float mr = ln_mean * ln_rstd;
 #pragma unroll
@@ -259,7 +260,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, const EpiWarp& 
             }
             __syncwarp();
           }
-          if (p.stats_out) {
+          if (LNF && p.stats_out) {
             if (st_first) { st_pivot = v[0]; st_first = false; }
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -316,7 +317,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, const EpiWarp& 
             __syncwarp();
           }
         }
-        if (p.stats_out && valid && !st_first) {
+        if (LNF && p.stats_out && valid && !st_first) {
           const float n = (float)kColsPerGrp;
           const float mean_p = st_pivot + st_s1 / n;
           const float m2_p = fmaxf(st_s2 - st_s1 * st_s1 / n, 0.f);
@@ -525,7 +526,7 @@ struct Gemm2Cfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 256;
 };
 
-template <int BN>
+template <int BN, bool LNF>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmArgs p) {
@@ -667,7 +668,7 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int nt = tile % p.tiles_n;
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after_sync();
-      epilogue_tile<BN>(p, ctx, tmem_base + as * BN, mt, nt);
+      epilogue_tile<BN, LNF>(p, ctx, tmem_base + as * BN, mt, nt);
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) {
@@ -685,12 +686,12 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-template <int BN>
+template <int BN, bool LNF>
 static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, cudaStream_t st) {
   using Cfg = Gemm2Cfg<BN>;
   static std::atomic<uint64_t> attr_mask{0};
   if (first_on_device(attr_mask)) {
-    cudaError_t e = cudaFuncSetAttribute(gemm2_f16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm2_f16_kernel<BN, LNF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
     if (e != cudaSuccess) {
       set_error("gemm2: cudaFuncSetAttribute(%d B smem): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
@@ -700,7 +701,7 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ge
   const int tiles = ((a.tiles_m + 1) / 2) * a.tiles_n;
   const int max_pairs = num_sms() / 2;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
-  cudaError_t e = launch_ex(gemm2_f16_kernel<BN>, dim3(2 * pairs), dim3(kThreads), Cfg::kSmemBytes, st, 2, tmA, tmB, a);
+  cudaError_t e = launch_ex(gemm2_f16_kernel<BN, LNF>, dim3(2 * pairs), dim3(kThreads), Cfg::kSmemBytes, st, 2, tmA, tmB, a);
   if (e != cudaSuccess) {
     set_error("gemm2_f16_kernel launch: %s", cudaGetErrorString(e));
     return 1;
@@ -823,8 +824,13 @@ extern "C" int udb_gemm_f16(const udb_gemm_t* g, void* stream) {
   note_work(2.0 * a.M * (double)g->N * g->K,
             2.0 * ((double)a.M * (g->a_mode == UDB_A_CONV3X3 ? g->conv_C : (g->a_split_k ? 2 * g->a_split_k : g->K)) + (double)g->N * g->K) +
                 (double)a.M * g->N * ((g->out ? (g->out_f32 ? 4 : 2) : 0) + (g->out2 ? 2 : 0) + (g->resid ? (g->resid_f32 ? 4 : 2) : 0)));
+  const bool lnf = g->ln_stats_out || g->ln_stats_in;
+  if (lnf && !use_pair) { set_error("udb_gemm_f16: fused LayerNorm needs the CTA-pair kernel (N %% 128 == 0)"); return 1; }
   if (use_pair) {
-    return bn == 256 ? launch_gemm2<256>(tmA, tmB, a, st) : (bn == 192 ? launch_gemm2<192>(tmA, tmB, a, st) : launch_gemm2<128>(tmA, tmB, a, st));
+    if (lnf) return bn == 256 ? launch_gemm2<256, true>(tmA, tmB, a, st) : (bn == 192 ? launch_gemm2<192, true>(tmA, tmB, a, st)
+                                                                                      : launch_gemm2<128, true>(tmA, tmB, a, st));
+    return bn == 256 ? launch_gemm2<256, false>(tmA, tmB, a, st) : (bn == 192 ? launch_gemm2<192, false>(tmA, tmB, a, st)
+                                                                               : launch_gemm2<128, false>(tmA, tmB, a, st));
   }
   switch (bn) {
     case 256: return launch_gemm<256>(tmA, tmB, a, st);

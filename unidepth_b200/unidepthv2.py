@@ -85,9 +85,12 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
         # optional dict of preallocated output tensors (same keys / shapes as infer's result): graph-mode infer copies its
         # static outputs there instead of cloning them (parallel.PeerGather.views(): the multi-GPU send slot)
         self.output_buffers = None
-        # Fused LayerNorm (north_star: "fused LayerNorm + QKV projection"): norm1 / norm2 of the encoder blocks are folded
-        # into the qkv / fc1 GEMMs (include/udb.h udb_gemm_t.ln_*), no stand-alone LayerNorm pass.  Engine path, f16 mode.
-        self.fuse_ln = True
+        # Fused LayerNorm (north_star: "fused LayerNorm + QKV projection"): norm1 / norm2 of the encoder blocks folded into
+        # the qkv / fc1 GEMMs (include/udb.h udb_gemm_t.ln_*), no stand-alone LayerNorm pass.  Engine path, f16 mode.
+        # OFF by default: measured on the B200 (same box, profiles/r02_fused_ln_ab.txt) it removes 0.89 ms of LayerNorm
+        # kernels per 8-image step but adds 1.30 ms to the GEMMs (the producers' extra f16 store + row statistics land in
+        # the attn.proj epilogue, which is already longer than its K=1024 main loop): 18.39 vs 18.02 ms/step.
+        self.fuse_ln = False
         self._engine = None
         self._engine_key = None
         # Bounded caches (LRU): the reference handles arbitrary shapes in constant memory, so a stream of

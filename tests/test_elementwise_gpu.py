@@ -172,3 +172,43 @@ def test_layernorm_zero_padded_channels():
         ref = F.layer_norm(x[:, :valid].float(), (valid,), None, None, 1e-5)
         assert _err(got[:, :valid], ref, f"ln {valid} of {dim}") < 8e-3
         assert float(got[:, valid:].abs().max()) == 0.0
+
+
+def test_peer_gather_single_rank():
+    """parallel.PeerGather with a one-rank NCCL group: the send-slot views alias the CUDA-IPC buffer (writes through them are
+    what start() sends), slots rotate, outputs written elsewhere are staged by one copy, permuted outputs come back with the
+    same values.  (The cross-process part -- IPC mapping and the device barrier -- is tests/test_multigpu_gpu.py.)"""
+    import os
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from unidepth_b200 import parallel
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29655")
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    created = not dist.is_initialized()
+    if created:
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=dev)
+    try:
+        g = torch.Generator().manual_seed(0)
+        mk = lambda: {"intrinsics": torch.randn(3, 3, 3, generator=g).to(dev), "depth": torch.randn(3, 1, 20, 30, generator=g).to(dev),
+                      "depth_features": torch.randn(3, 5, 7, 16, generator=g).to(dev).permute(0, 3, 1, 2)}
+        a = mk()
+        pg = parallel.PeerGather(a, dev)
+        for step in range(5):
+            src = mk()
+            if step % 2:            # produced in place: write through the views
+                v = pg.views()
+                for k in src:
+                    v[k].copy_(src[k])
+                got = pg.start(v).wait()
+            else:                   # produced elsewhere: start() stages it
+                got = pg.start(src).wait()
+            torch.cuda.synchronize()
+            for k in src:
+                assert got[k].is_contiguous() and torch.equal(got[k], src[k].contiguous()), (step, k)
+        assert not pg.timed_out()
+    finally:
+        if created:
+            dist.destroy_process_group()

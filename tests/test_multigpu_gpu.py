@@ -32,15 +32,23 @@ m = m.to(dev).eval()
 g = torch.Generator().manual_seed(7)
 rgb = torch.randint(0, 256, (4, 3, 240, 320), dtype=torch.uint8, generator=g)
 import warnings; warnings.simplefilter("ignore")
-full = infer_sharded(m, rgb)
+def same(got, tag):
+    bad = [k for k in single if not torch.equal(got[k].float(), single[k].float())]
+    if bad:
+        k = bad[0]
+        d = (got[k].float() - single[k].float()).abs()
+        print(f"rank {rank}: MISMATCH in {tag}: keys {bad}; {k}: max abs diff {d.max().item():.3e}, "
+              f"per-image max {[round(x, 6) for x in d.flatten(1).max(1).values.tolist()]}", flush=True)
+    return not bad
+
 single = m.infer(rgb)
-ok = all(torch.equal(full[k].float(), single[k].float()) for k in single)
+full = infer_sharded(m, rgb)
+ok = same(full, "first synchronous gather")
 # pipelined form: three gathers in flight one after the other, replays of the older (B=2) graph after the
 # capture of the larger (B=4) one
 pend = [infer_sharded(m, rgb, async_op=True) for _ in range(3)]
-for p in pend:
-    got = p.wait()
-    ok &= all(torch.equal(got[k].float(), single[k].float()) for k in single)
+for i, p in enumerate(pend):
+    ok &= same(p.wait(), f"pipelined gather {i}")
 # outputs produced straight into the send slot (model.output_buffers = the slot's views): no staging copy
 lo, hi = shard_bounds(4, rank, world)
 loc = m.infer(rgb[lo:hi])
@@ -48,13 +56,14 @@ in_slot = 0
 for _ in range(3):
     m.output_buffers = parallel.output_views(loc)
     in_slot += m.output_buffers is not None
-    got = infer_sharded(m, rgb)
-    ok &= all(torch.equal(got[k].float(), single[k].float()) for k in single)
+    ok &= same(infer_sharded(m, rgb), "gather of outputs written in place")
 m.output_buffers = None
 mode = parallel.gather_mode()
 if mode == "p2p":
-    ok &= parallel._p2p_failed[0] is None and len(parallel._p2p_cache) > 0 and in_slot == 3
-    ok &= all(not pg.timed_out() for pg in parallel._p2p_cache.values())
+    setup_ok = parallel._p2p_failed[0] is None and len(parallel._p2p_cache) > 0 and in_slot == 3
+    no_timeout = all(not pg.timed_out() for pg in parallel._p2p_cache.values())
+    print(f"rank {rank}: p2p set up {setup_ok} (in-slot steps {in_slot}), no barrier timeout {no_timeout}", flush=True)
+    ok &= setup_ok and no_timeout
 print(f"rank {rank}: mode {mode} (p2p objects {len(parallel._p2p_cache)}, failure {parallel._p2p_failed[0]}), "
       f"gathered == single-GPU: {ok}", flush=True)
 dist.destroy_process_group()

@@ -164,8 +164,12 @@ class PeerGather:
         self.stream.wait_stream(cur)
         with torch.cuda.stream(self.stream):
             self._barrier()                             # all send slots of this step are complete
+            import os
+            self_on_main = os.environ.get("UDB_P2P_SELFCOPY", "dma") == "main"      # experiment: own part copied by a kernel
             for step in range(self.world):
                 r = (self.rank - step) % self.world     # start with the local slot, then walk the ring
+                if r == self.rank and self_on_main:
+                    continue
                 for k in self.keys:
                     n = full[k][0].numel() * b * 4
                     dst = full[k].data_ptr() + r * n
@@ -174,6 +178,9 @@ class PeerGather:
             self._barrier()                             # all pulls done: the slot may be reused
             ev = torch.cuda.Event()
             ev.record(self.stream)
+        if self_on_main:
+            for k in self.keys:
+                full[k][self.rank * b:(self.rank + 1) * b].copy_(views[k])
         self.last[slot] = ev
         return PendingOutputs(None, full, None, None, event=ev)
 

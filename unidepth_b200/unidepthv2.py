@@ -853,7 +853,8 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
                 self._graphs.popitem(last=False)
         else:
             self._graphs.move_to_end(key)
-        entry["inp"].copy_(rgb, non_blocking=True)
+        if os.environ.get("UDB_SKIP_INPUT_COPY") != "1":      # (experiment switch: isolates copy-engine contention)
+            entry["inp"].copy_(rgb, non_blocking=True)
         entry["graph"].replay()
         bufs = self.output_buffers
         if bufs is not None:       # caller-provided destinations (e.g. the send slot of parallel.PeerGather): one copy, no clone

@@ -299,6 +299,28 @@ def _launches():
     return _cabi.launch_count()
 
 
+def test_first_call_graph_survives_allocator_churn(shallow):
+    """Regression: a graph captured by the model's very FIRST infer (the call that also packs the weights) must stay valid
+    when memory is allocated, filled and freed afterwards and a larger graph is captured.  Every address a captured kernel
+    reads has to be owned by something that outlives the graph (the ray-frequency table once was not)."""
+    cfg, sd = shallow
+    m = _model(cfg, sd)
+    rgb = _rgb((3, 240, 320), 21)
+    first = m.infer(rgb[:1])                                   # first call: pack + engine + capture of the B=1 graph
+    junk = [torch.full((n,), float("nan"), device="cuda:0") for n in (64, 128, 256, 256, 256, 512, 1024, 4096) for _ in range(64)]
+    del junk
+    big = m.infer(rgb)                                         # larger capture (new workspace, new static outputs)
+    junk = [torch.full((256,), float("nan"), device="cuda:0") for _ in range(512)]
+    again = m.infer(rgb[:1])                                   # replay of the first graph
+    del junk
+    m.use_cuda_graph = False
+    eager = m.infer(rgb[:1])
+    for k in first:
+        assert torch.equal(first[k], eager[k]), k
+        assert torch.equal(again[k], eager[k]), k
+        assert torch.equal(big[k][:1], eager[k]), k
+
+
 def test_high_res_1024x1536_long_sequence():
     """BASELINE config 5 shape: 3x1024x1536 is resized by infer to 644x952 -> 3129 tokens (long-sequence
     attention, 25 key tiles).  ViT-L widths with a 4-block encoder so the CPU oracle stays fast."""

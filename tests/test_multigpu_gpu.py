@@ -41,8 +41,10 @@ def same(got, tag):
               f"per-image max {[round(x, 6) for x in d.flatten(1).max(1).values.tolist()]}", flush=True)
     return not bad
 
-single = m.infer(rgb)
+# order matters: the FIRST call of the model captures the small (B=2) graph, then a gather, then the larger (B=4) graph --
+# the sequence that exposed the use-after-free of the ray-frequency table (unidepthv2.py::_run_on_device)
 full = infer_sharded(m, rgb)
+single = m.infer(rgb)
 ok = same(full, "first synchronous gather")
 # pipelined form: three gathers in flight one after the other, replays of the older (B=2) graph after the
 # capture of the larger (B=4) one

@@ -105,6 +105,7 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
         self._packed_key = None
         self._graphs: "OrderedDict[tuple, dict]" = OrderedDict()
         self._posembed_cache: Dict[tuple, torch.Tensor] = {}
+        self._scales_cache: Dict[tuple, torch.Tensor] = {}      # ray-embedding frequency tables: shape constants, never dropped
         self._engine_shapes: set = set()
 
     # ------------------------------------------------------------------ reference-compatible API
@@ -803,11 +804,17 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
         nh, nw = geom["net_hw"]
         gh, gw = nh // PATCH, nw // PATCH
         bands = self.spec.hidden // 2
-        skey = ("scales", gh, gw)
-        if skey not in self._posembed_cache:
-            # positional_embedding.py:231-233 -- computed with the same torch expression (host, once)
-            self._posembed_cache[skey] = (2.0 ** torch.linspace(0.0, math.log2(max(gh, gw) // 2), steps=bands)).to(dev)
-        geom["scales"] = self._posembed_cache[skey]
+        # Weights first: packing drops the engine and every cache that depends on it.  (Round-1/2 bug: the frequency table
+        # below used to live in _posembed_cache and be created BEFORE this call; the first infer then packed, cleared the
+        # cache, captured the graph with the table's pointer and let the tensor die with `geom` -- later allocations reused
+        # its memory and replays of that first graph computed the ray embedding from garbage.  It surfaced only when the
+        # freed block happened to be reused, e.g. by the peer-memory gather's output tensors.)
+        self._weights()
+        skey = (gh, gw, bands, dev.index)
+        if skey not in self._scales_cache:
+            # positional_embedding.py:231-233 -- computed with the same torch expression (host, once per grid)
+            self._scales_cache[skey] = (2.0 ** torch.linspace(0.0, math.log2(max(gh, gw) // 2), steps=bands)).to(dev)
+        geom["scales"] = self._scales_cache[skey]
 
         gt_intr4, camera_k = None, None
         if camera is not None and not isinstance(camera, torch.Tensor):
@@ -847,7 +854,8 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 static_out = run(static_in)
-            entry = dict(graph=graph, inp=static_in, out=static_out, ws=getattr(self, "_last_ws", None))
+            # the entry owns everything whose address the captured kernels read
+            entry = dict(graph=graph, inp=static_in, out=static_out, ws=getattr(self, "_last_ws", None), scales=geom["scales"])
             self._graphs[key] = entry
             while len(self._graphs) > self.max_cached_graphs:
                 self._graphs.popitem(last=False)

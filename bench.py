@@ -292,6 +292,7 @@ def main():
     pending = {"dev": None, "e2e": None}
     from unidepth_b200 import parallel
     pipelined = world > 1 and parallel.gather_mode() != "nccl"
+    no_gather = os.environ.get("UDB_BENCH_NOGATHER") == "1"     # diagnosis only: N independent replicas, max over ranks
 
     last_out = {"v": None}
 
@@ -305,6 +306,8 @@ def main():
 
     def step_device():
         out = infer_into_slot(rgb_dev)
+        if no_gather:
+            return out
         if world > 1 and pipelined:
             nxt = gather_outputs(out, world, async_op=True)
             if pending["dev"] is not None:
@@ -334,6 +337,9 @@ def main():
         def step_e2e():
             x = rgb_host.to(dev, non_blocking=True)
             out = infer_into_slot(x)
+            if no_gather:
+                _d2h({k: v for k, v in out.items()} if world == 1 else {k: torch.cat([v] * 1) for k, v in out.items()}, full) if world == 1 else None
+                return out
             if world > 1 and pipelined:
                 nxt = gather_outputs(out, world, async_op=True)
                 if pending["e2e"] is not None:
@@ -494,7 +500,8 @@ def main():
                        "l2": "per-step working set (f16 weights 0.4-0.7 GB + activations > 4 GB) exceeds the 126 MB L2",
                        "fused_layernorm": (not is_v1) and bool(args.fuse_ln),
                        "cuda_graph": True, "engine": ("udb_infer_v1" if is_v1 else "udb_infer_v2") + " (one C call per infer)",
-                       **({"collective": parallel.gather_description()} if world > 1 else {})},
+                       **({"collective": "NONE (UDB_BENCH_NOGATHER=1 diagnosis run: independent replicas)" if no_gather
+                           else parallel.gather_description()} if world > 1 else {})},
             "e2e": {"value": total_images / (ms_e2e / 1000.0), "unit": "images/s",
                     "h2d_bytes_per_step": rgb_host.numel(), "d2h_bytes_per_step": depth_host.numel() * 4 + k_host.numel() * 4,
                     "d2h": "depth + intrinsics of this rank's images (the reference returns device tensors; these two are "

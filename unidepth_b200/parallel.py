@@ -98,6 +98,16 @@ class PeerGather:
         self.keys = _keys(out_like)
         self.shapes = {k: tuple(out_like[k].shape) for k in self.keys}
         self.batch = self.shapes[self.keys[0]][0]
+        # Physical layout per key: a permuted view of a contiguous tensor (UniDepthV2's depth_features is [B,h,w,C] memory
+        # viewed as [B,C,h,w]) keeps its memory order in the slot and in the gathered tensor, so filling the slot is a
+        # plain copy instead of a transposing one.  order = dims by decreasing stride (batch first), inv = its inverse.
+        self.order, self.inv = {}, {}
+        for k in self.keys:
+            t = out_like[k]
+            order = sorted(range(t.ndim), key=lambda d: (-t.stride(d), d))
+            if order[0] != 0 or t.permute(order).is_contiguous() is False:
+                order = list(range(t.ndim))
+            self.order[k], self.inv[k] = order, [order.index(d) for d in range(t.ndim)]
         self.offs, off = {}, 0
         for k in self.keys:
             self.offs[k] = off
@@ -131,8 +141,10 @@ class PeerGather:
         self.last = [None] * depth                      # event after which slot i may be overwritten
         self.i = 0
         self.epoch = 0
-        self._views = [{k: torch.as_tensor(_DevView(self.base + s * self.slot_bytes + self.offs[k], self.shapes[k]), device=self.device)
-                        for k in self.keys} for s in range(depth)]
+        phys = lambda k, b: [b] + [self.shapes[k][d] for d in self.order[k][1:]]
+        self._phys = phys
+        self._views = [{k: torch.as_tensor(_DevView(self.base + s * self.slot_bytes + self.offs[k], phys(k, self.batch)),
+                                           device=self.device).permute(self.inv[k]) for k in self.keys} for s in range(depth)]
         dist.barrier(group=self.group)                  # every rank has mapped every peer before the first device barrier
 
     def views(self) -> Dict[str, torch.Tensor]:
@@ -159,7 +171,8 @@ class PeerGather:
             if out[k].data_ptr() != views[k].data_ptr():
                 views[k].copy_(out[k])                  # outputs were not produced in place: one staging copy
         b = self.batch
-        full = {k: torch.empty((self.world * b,) + self.shapes[k][1:], device=self.device, dtype=torch.float32) for k in self.keys}
+        full = {k: torch.empty(self._phys(k, self.world * b), device=self.device, dtype=torch.float32).permute(self.inv[k])
+                for k in self.keys}
         C, lib = self.C, self.cabi.lib()
         self.stream.wait_stream(cur)
         with torch.cuda.stream(self.stream):
@@ -171,7 +184,7 @@ class PeerGather:
                 if r == self.rank and self_on_main:
                     continue
                 for k in self.keys:
-                    n = full[k][0].numel() * b * 4
+                    n = full[k][0].numel() * b * 4          # batch is the outermost physical dim: rank r's rows are contiguous
                     dst = full[k].data_ptr() + r * n
                     self.cabi.check(lib.udb_p2p_copy(C.c_void_p(dst), C.c_void_p(self.peer[r] + slot * self.slot_bytes + self.offs[k]), n,
                                                      C.c_void_p(self.stream.cuda_stream)), "udb_p2p_copy")
@@ -181,6 +194,7 @@ class PeerGather:
         if self_on_main:
             for k in self.keys:
                 full[k][self.rank * b:(self.rank + 1) * b].copy_(views[k])
+        # (results keep each key's memory order: depth_features comes back as the same kind of permuted view infer returns)
         self.last[slot] = ev
         return PendingOutputs(None, full, None, None, event=ev)
 

@@ -321,8 +321,8 @@ def main():
     k_host = torch.empty((B, 3, 3), dtype=torch.float32).pin_memory()
     full_host = {}
 
-    def _d2h(out, full=False):
-        lo = rank * B if world > 1 else 0
+    def _d2h(out, full=False, local=False):
+        lo = rank * B if (world > 1 and not local) else 0
         depth_host.copy_(out["depth"][lo:lo + B], non_blocking=True)
         k_host.copy_(out["intrinsics"][lo:lo + B], non_blocking=True)
         if full:
@@ -338,7 +338,7 @@ def main():
             x = rgb_host.to(dev, non_blocking=True)
             out = infer_into_slot(x)
             if no_gather:
-                _d2h({k: v for k, v in out.items()} if world == 1 else {k: torch.cat([v] * 1) for k, v in out.items()}, full) if world == 1 else None
+                _d2h(out, full, local=True)
                 return out
             if world > 1 and pipelined:
                 nxt = gather_outputs(out, world, async_op=True)

@@ -77,3 +77,23 @@ def test_gather_outputs_gloo_world2():
     for p in ps:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_shard_camera_and_v1_output_subset():
+    """Per-image camera arguments are sliced like the images (a single camera is shared); the gather packs whatever subset of
+    the output keys a model returns (UniDepthV1: intrinsics, depth, points)."""
+    import pytest
+    from unidepth_b200.parallel import pack_outputs, shard_camera, unpack_outputs
+    K = torch.arange(6 * 9, dtype=torch.float32).reshape(6, 3, 3)
+    assert torch.equal(shard_camera(K, 6, 2, 4), K[2:4])
+    assert shard_camera(K[:1], 6, 2, 4) is not None and shard_camera(K[:1], 6, 2, 4).shape[0] == 1
+    with pytest.raises(ValueError):
+        shard_camera(K[:5], 6, 2, 4)
+
+    class Cams(list):
+        pass
+    cams = Cams(range(6))
+    assert shard_camera(cams, 6, 1, 3) == [1, 2]
+    v1 = {"intrinsics": torch.randn(3, 3, 3), "depth": torch.randn(3, 1, 4, 5), "points": torch.randn(3, 3, 4, 5)}
+    back = unpack_outputs(pack_outputs(v1), v1)
+    assert set(back) == set(v1) and all(torch.equal(back[k], v1[k]) for k in v1)

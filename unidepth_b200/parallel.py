@@ -302,9 +302,9 @@ def infer_sharded(model, rgb: torch.Tensor, async_op: bool = False, **kw):
     lo, hi = shard_bounds(n, rank, world)
     counts = [shard_bounds(n, r, world)[1] - shard_bounds(n, r, world)[0] for r in range(world)]
     kw = dict(kw)
-    cam = kw.get("camera", None)
-    if cam is not None:
-        kw["camera"] = shard_camera(cam, n, lo, hi)
+    for name in ("camera", "intrinsics"):          # UniDepthV2.infer(camera=...), UniDepthV1.infer(intrinsics=...)
+        if kw.get(name, None) is not None:
+            kw[name] = shard_camera(kw[name], n, lo, hi)
     return gather_outputs(model.infer(rgb[lo:hi], **kw), world, async_op=async_op, counts=counts)
 
 

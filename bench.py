@@ -501,7 +501,8 @@ def main():
                        "fused_layernorm": (not is_v1) and bool(args.fuse_ln),
                        "cuda_graph": True, "engine": ("udb_infer_v1" if is_v1 else "udb_infer_v2") + " (one C call per infer)",
                        **({"collective": "NONE (UDB_BENCH_NOGATHER=1 diagnosis run: independent replicas)" if no_gather
-                           else parallel.gather_description()} if world > 1 else {})},
+                           else parallel.gather_description()} if world > 1 else {}),
+                       **({"peer_memory_unavailable": parallel._p2p_failed[0]} if parallel._p2p_failed[0] else {})},
             "e2e": {"value": total_images / (ms_e2e / 1000.0), "unit": "images/s",
                     "h2d_bytes_per_step": rgb_host.numel(), "d2h_bytes_per_step": depth_host.numel() * 4 + k_host.numel() * 4,
                     "d2h": "depth + intrinsics of this rank's images (the reference returns device tensors; these two are "

@@ -55,6 +55,30 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+// Experiment (build with -DUDB_ATTN_POLY=n, n = 4 / 8; 0 = off, the default): every n-th PAIR of scores takes exp2 on the
+// FMA / ALU pipes instead of the MUFU -- x = k + f, k = round(x), 2^f by a degree-3 minimax polynomial (relative error 7.6e-5,
+// below the f16 rounding of P), 2^k added into the exponent field; inputs clamped to >= -100 (exp2 = 0 in f16 anyway).
+#ifndef UDB_ATTN_POLY
+#define UDB_ATTN_POLY 0
+#endif
+__device__ __forceinline__ void exp2_poly_pair(const uint64_t x2, float& e0, float& e1) {
+  float x0, x1;
+  unpack2(x2, x0, x1);
+  const uint64_t xc = pack2(fmaxf(x0, -100.f), fmaxf(x1, -100.f));
+  const uint64_t magic = pack2(12582912.f, 12582912.f);        // 1.5 * 2^23: x + magic rounds to an integer in the mantissa
+  const uint64_t t2 = add2(xc, magic);
+  const uint64_t n2 = add2(t2, pack2(-12582912.f, -12582912.f));
+  const uint64_t f2 = fma2(n2, pack2(-1.f, -1.f), xc);
+  uint64_t q = fma2(pack2(0.05520550534129143f, 0.05520550534129143f), f2, pack2(0.24261397123336792f, 0.24261397123336792f));
+  q = fma2(q, f2, pack2(0.6932547688484192f, 0.6932547688484192f));
+  q = fma2(q, f2, pack2(0.9999276995658875f, 0.9999276995658875f));
+  float p0, p1, t0, t1;
+  unpack2(q, p0, p1);
+  unpack2(t2, t0, t1);
+  e0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23));
+  e1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
+}
+
 // exp2(s*scale - m) for the 64 scores of one half row; returns their sum; P (f16 pairs) into pk[0..31].
 // MASK: only the first kv_left entries are valid keys (last tile; kv_left may be <= 0).
 template <bool MASK>
@@ -64,9 +88,15 @@ __device__ __forceinline__ float softmax_half(const uint32_t (&sv)[AT_HK], uint3
   uint64_t ps[4] = {0ull, 0ull, 0ull, 0ull};   // independent partial sums: no serial FADD chain behind the MUFUs
 #pragma unroll
   for (int i = 0; i < AT_HK; i += 2) {
-    float t0, t1;
-    unpack2(fma2(pack2u(sv[i], sv[i + 1]), sc2, nm2), t0, t1);
-    float e0 = ex2(t0), e1 = ex2(t1);
+    float e0, e1;
+    if (UDB_ATTN_POLY && ((i >> 1) % (UDB_ATTN_POLY ? UDB_ATTN_POLY : 1)) == (UDB_ATTN_POLY ? UDB_ATTN_POLY - 1 : 1)) {
+      exp2_poly_pair(fma2(pack2u(sv[i], sv[i + 1]), sc2, nm2), e0, e1);
+    } else {
+      float t0, t1;
+      unpack2(fma2(pack2u(sv[i], sv[i + 1]), sc2, nm2), t0, t1);
+      e0 = ex2(t0);
+      e1 = ex2(t1);
+    }
     if (MASK) {
       e0 = (i < kv_left) ? e0 : 0.f;
       e1 = (i + 1 < kv_left) ? e1 : 0.f;
@@ -93,9 +123,15 @@ __device__ __forceinline__ float softmax_half_spec(const uint32_t (&sv)[AT_HK], 
 #pragma unroll
   for (int i = 0; i < AT_HK; i += 2) {
     const float s0 = __uint_as_float(sv[i]), s1 = __uint_as_float(sv[i + 1]);
-    float t0, t1;
-    unpack2(fma2(pack2(s0, s1), sc2, nm2), t0, t1);
-    float e0 = ex2(t0), e1 = ex2(t1);
+    float e0, e1;
+    if (UDB_ATTN_POLY && ((i >> 1) % (UDB_ATTN_POLY ? UDB_ATTN_POLY : 1)) == (UDB_ATTN_POLY ? UDB_ATTN_POLY - 1 : 1)) {
+      exp2_poly_pair(fma2(pack2(s0, s1), sc2, nm2), e0, e1);
+    } else {
+      float t0, t1;
+      unpack2(fma2(pack2(s0, s1), sc2, nm2), t0, t1);
+      e0 = ex2(t0);
+      e1 = ex2(t1);
+    }
     if (MASK) {
       e0 = (i < kv_left) ? e0 : 0.f;
       e1 = (i + 1 < kv_left) ? e1 : 0.f;

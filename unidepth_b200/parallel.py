@@ -120,13 +120,25 @@ class PeerGather:
         self.flags_off = depth * self.slot_bytes
         total = self.flags_off + 1024                   # [world] uint32 flags + a timeout word at +512
         lib = cabi.lib()
+        flag_dev = self.device
+
+        def agree(ok: bool, what: str):
+            """Every fallible LOCAL step is followed by a collective vote, so that either all ranks continue or all give up
+            (a rank that raised alone would leave its peers waiting in the next collective)."""
+            t = torch.tensor([1 if ok else 0], device=flag_dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
+            if int(t.item()) == 0:
+                raise RuntimeError(f"peer-memory gather unavailable: {what} failed on at least one rank"
+                                   + ("" if ok else f" (here: {lib.udb_last_error().decode()})"))
+
         base, handle = C.c_void_p(), (C.c_char * 64)()
         with torch.cuda.device(self.device):
-            cabi.check(lib.udb_p2p_alloc(total, C.byref(base), handle), "udb_p2p_alloc")
+            rc = lib.udb_p2p_alloc(total, C.byref(base), handle)
+        agree(rc == 0, "udb_p2p_alloc")
         self.base = base.value
         handles = [None] * self.world
         dist.all_gather_object(handles, bytes(handle.raw), group=self.group)
-        self.peer = []
+        self.peer, ok = [], True
         for r, h in enumerate(handles):
             if r == self.rank:
                 self.peer.append(self.base)
@@ -134,8 +146,9 @@ class PeerGather:
             p = C.c_void_p()
             buf = (C.c_char * 64).from_buffer_copy(h)
             with torch.cuda.device(self.device):
-                cabi.check(lib.udb_p2p_open(buf, C.byref(p)), f"udb_p2p_open(rank {r})")
-            self.peer.append(p.value)
+                ok = ok and lib.udb_p2p_open(buf, C.byref(p)) == 0
+            self.peer.append(p.value or 0)
+        agree(ok, "udb_p2p_open")
         self.peer_flags = torch.tensor([p + self.flags_off for p in self.peer], dtype=torch.int64, device=self.device)
         self.stream = torch.cuda.Stream(device=self.device)
         self.last = [None] * depth                      # event after which slot i may be overwritten
@@ -198,6 +211,18 @@ class PeerGather:
         self.last[slot] = ev
         return PendingOutputs(None, full, None, None, event=ev)
 
+    def close(self):
+        """Unmap the peers' buffers and free this rank's (after a synchronise; collective order is the caller's business)."""
+        if getattr(self, "base", None) is None:
+            return
+        torch.cuda.synchronize(self.device)
+        lib = self.cabi.lib()
+        for r, p in enumerate(self.peer):
+            if r != self.rank and p:
+                lib.udb_p2p_close(self.C.c_void_p(p))
+        lib.udb_p2p_free(self.C.c_void_p(self.base))
+        self.base, self._views = None, []
+
     def timed_out(self) -> bool:
         """True if a device barrier gave up waiting for a peer (synchronises)."""
         torch.cuda.synchronize(self.device)
@@ -232,19 +257,11 @@ def p2p_gather_for(out: Dict[str, torch.Tensor], group=None):
         return None
     key = tuple((k, tuple(out[k].shape)) for k in _keys(out)) + (out["depth"].device.index,)
     if key not in _p2p_cache:
-        ok = 1
         try:
-            pg = PeerGather(out, out["depth"].device, group)
-        except Exception as e:      # no peer access / IPC unavailable: keep working over NCCL
+            _p2p_cache[key] = PeerGather(out, out["depth"].device, group)
+        except Exception as e:      # agreed on by all ranks (PeerGather votes after every local step): fall back to NCCL
             _p2p_failed[0] = f"{type(e).__name__}: {e}"
-            ok, pg = 0, None
-        # all ranks must agree, or some would wait in a device barrier the others never enter
-        flag = torch.tensor([ok], device=out["depth"].device)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
-        if int(flag.item()) == 0:
-            _p2p_failed[0] = _p2p_failed[0] or "a peer could not set up peer memory"
             return None
-        _p2p_cache[key] = pg
     return _p2p_cache[key]
 
 

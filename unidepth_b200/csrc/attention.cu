@@ -55,11 +55,13 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-// Experiment (build with -DUDB_ATTN_POLY=n, n = 4 / 8; 0 = off, the default): every n-th PAIR of scores takes exp2 on the
-// FMA / ALU pipes instead of the MUFU -- x = k + f, k = round(x), 2^f by a degree-3 minimax polynomial (relative error 7.6e-5,
-// below the f16 rounding of P), 2^k added into the exponent field; inputs clamped to >= -100 (exp2 = 0 in f16 anyway).
+// The MUFU unit (16 ex2 / clk / SM) is the binding pipe of d = 64 attention, so every UDB_ATTN_POLY-th PAIR of scores takes
+// its exp2 on the FMA / ALU pipes instead: x = k + f, k = round(x), 2^f by a degree-3 minimax polynomial (relative error
+// 7.6e-5, below the f16 rounding of P), 2^k added into the exponent field; inputs clamped to >= -100 (exp2 = 0 in f16 anyway).
+// Same-box A/B on the B200 (profiles/r02_attn_poly_ab.txt): share 1/4 -> 4.12 ms of attention per step instead of 4.44
+// (1/3 and 1/5: 4.22; 1/2: 4.53, slower -- the FMA issue slots become the limit; 1/8: 4.30).  -DUDB_ATTN_POLY=0 turns it off.
 #ifndef UDB_ATTN_POLY
-#define UDB_ATTN_POLY 0
+#define UDB_ATTN_POLY 4
 #endif
 __device__ __forceinline__ void exp2_poly_pair(const uint64_t x2, float& e0, float& e1) {
   float x0, x1;

@@ -779,18 +779,38 @@ extern "C" int udb_gemm_f16(const udb_gemm_t* g, void* stream) {
     const char* e = getenv("UDB_GEMM_PAIR");
     return e ? atoi(e) : 1;
   }();
+  // UDB_GEMM_BN_CAP (experiments): upper bound on the tile width
+  static const int bn_cap = [] {
+    const char* e = getenv("UDB_GEMM_BN_CAP");
+    return e ? atoi(e) : 256;
+  }();
   // tile width: widest that divides the work sensibly
   int bn;
   if (g->store_mode == UDB_STORE_HEAD) {
     if (g->N != 32) { set_error("udb_gemm_f16: HEAD store needs N == 32"); return 1; }
     bn = 32;
-  } else if (g->N % 256 == 0) bn = 256;
-  else if (g->N % 192 == 0 && pair_env != 0) bn = 192;      // ConvNeXt widths 192 / 384: 3 (or 6) times fewer passes over A than 64 / 128
+  } else if (g->N % 256 == 0 && bn_cap >= 256) bn = 256;
+  else if (g->N % 192 == 0 && pair_env != 0 && bn_cap >= 192) bn = 192;      // ConvNeXt widths 192 / 384: 3 (or 6) times fewer passes over A than 64 / 128
   else if (g->N % 128 == 0) bn = 128;
   else if (g->N % 64 == 0) bn = 64;
   else bn = 32;
   if (g->store_mode == UDB_STORE_CONVT && (g->ct_cout % 32) != 0) {
     set_error("udb_gemm_f16: CONVT needs Cout %% 32 == 0"); return 1;
+  }
+  // Wave quantisation: the persistent grid has num_sms/2 CTA pairs and a static round-robin tile list, so a launch takes
+  // ceil(tiles / pairs) tile times.  When 128-wide tiles need fewer column-units of time than 256-wide ones (e.g. the
+  // 12888 x 3072 qkv GEMM: 9 waves x 256 vs 17 waves x 128), take the narrower tile.  UDB_GEMM_BN_AUTO=0 disables.
+  static const int bn_auto = [] {
+    const char* e = getenv("UDB_GEMM_BN_AUTO");
+    return e ? atoi(e) : 1;
+  }();
+  if (bn_auto && bn == 256 && pair_env != 0 && g->store_mode != UDB_STORE_HEAD && !g->ln_stats_out) {
+    const long long pairs = num_sms() / 2;
+    const long long tm2 = ((g->a_mode == UDB_A_CONV3X3 ? 0 : (g->M + BM - 1) / BM) + 1) / 2;
+    if (tm2 > 0) {
+      const long long w256 = (tm2 * (g->N / 256) + pairs - 1) / pairs, w128 = (tm2 * (g->N / 128) + pairs - 1) / pairs;
+      if (w128 * 128 * 100 < w256 * 256 * 97) bn = 128;
+    }
   }
   a.tiles_n = (g->N + bn - 1) / bn;
   if (g->ln_stats_out) {

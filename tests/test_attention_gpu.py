@@ -12,7 +12,11 @@ def _ref(q, k, v):
 
 
 @pytest.mark.parametrize("B,H,Sq,Sk", [(1, 1, 128, 128), (1, 2, 128, 256), (2, 3, 200, 200), (2, 16, 1611, 1611),
-                                       (1, 8, 1610, 1610), (1, 4, 77, 300)])
+                                       (1, 8, 1610, 1610), (1, 4, 77, 300),
+                                       # key counts around the 32-key chunk / 64-key half / 128-key tile edges: the second
+                                       # softmax stream of the kernel has no valid key at all when Sk <= 64
+                                       (1, 2, 100, 40), (1, 1, 128, 64), (2, 2, 130, 65), (1, 2, 64, 97), (1, 1, 50, 129),
+                                       (1, 1, 256, 192), (1, 2, 300, 3129)])
 def test_attention_fused_qkv_layout(B, H, Sq, Sk):
     if not torch.cuda.is_available():
         pytest.skip("needs a GPU")

@@ -7,18 +7,6 @@
 #include "../unidepth_b200/csrc/ptx.cuh"
 using namespace udb;
 
-__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
-                                            uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
-      "}\n" ::"r"(tmem_d),
-      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
 struct Res { long long issue, total; };
 
 // mode 0: SS, B K-major; 1: SS, B MN-major; 2: TS (A in TMEM), B K-major; 3: TS, B MN-major
@@ -89,6 +77,11 @@ void run(const char* name, int grid, int R) {
 }
 
 int main() {
+  for (int R : {1, 2, 4, 6, 8, 16}) {   // issue cost of short bursts (the attention kernels issue 4-8 MMAs per event)
+    run<32, 2>("TS 128x32x16  B K-major", 1, R);
+    run<64, 3>("TS 128x64x16  B MN-major", 1, R);
+    run<64, 0>("SS 128x64x16  B K-major", 1, R);
+  }
   for (int grid : {1, 148, 296}) {
     for (int R : {8, 64}) {
       if (grid <= 148) run<256, 0>("SS 128x256x16 B K-major", grid, R);

@@ -136,12 +136,13 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
               for (int k = 0; k < 4; ++k) umma_f16_ss(d, da + 2 * k, dw + 2 * k, idesc, (s | tap | k) != 0 ? 1u : 0u);
             }
           }
-          if (elected) umma_commit(&a_empty[stage]);
+          if (elected) {
+            if (s == p.slabs - 1) umma_commit(&t_full[as]);   // before the slab release: one thread's commits land in turn
+            umma_commit(&a_empty[stage]);
+          }
           __syncwarp();
           if (++stage == p.a_stages) { stage = 0; phase ^= 1; }
         }
-        if (elected) umma_commit(&t_full[as]);
-        __syncwarp();
       }
     }
   } else if (warp >= 4) {

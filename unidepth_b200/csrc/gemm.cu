@@ -465,6 +465,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               // advance 16 elements (32 B) along K inside the 128 B swizzle atom: +2 in 16-byte units
               umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
             }
+            if (kb == p.num_kb - 1) umma_commit(&tmem_full[as]);   // before the stage release: see gemm2_f16_kernel
             umma_commit(&empty_bar[stage]);
           }
           __syncwarp();
@@ -473,8 +474,6 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             phase ^= 1;
           }
         }
-        if (elected) umma_commit(&tmem_full[as]);
-        __syncwarp();
       }
     }
   } else if (warp >= 4) {
@@ -665,6 +664,9 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k)
               umma_f16_ss_2cta(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            // one thread's commits reach their barriers one after the other (~130 clk apart, tools/issue_probe.cu): the
+            // accumulator hand-over the epilogue is waiting for goes before the release of the last operand stage
+            if (kb == p.num_kb - 1) umma_commit_2cta(&tmem_full[as]);
             umma_commit_2cta(&empty_bar[stage]);
           }
           __syncwarp();
@@ -673,8 +675,6 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             phase ^= 1;
           }
         }
-        if (elected) umma_commit_2cta(&tmem_full[as]);
-        __syncwarp();
       }
     }
   } else if (warp >= 4) {
@@ -797,12 +797,15 @@ extern "C" int udb_gemm_f16(const udb_gemm_t* g, void* stream) {
   if (g->store_mode == UDB_STORE_CONVT && (g->ct_cout % 32) != 0) {
     set_error("udb_gemm_f16: CONVT needs Cout %% 32 == 0"); return 1;
   }
-  // Wave quantisation: the persistent grid has num_sms/2 CTA pairs and a static round-robin tile list, so a launch takes
-  // ceil(tiles / pairs) tile times.  When 128-wide tiles need fewer column-units of time than 256-wide ones (e.g. the
-  // 12888 x 3072 qkv GEMM: 9 waves x 256 vs 17 waves x 128), take the narrower tile.  UDB_GEMM_BN_AUTO=0 disables.
+  // Experiment (UDB_GEMM_BN_AUTO=1, off by default).  Wave quantisation: the persistent grid has num_sms/2 CTA pairs and a
+  // static round-robin tile list, so a launch takes ceil(tiles / pairs) tile times; when 128-wide tiles need fewer
+  // column-units of time than 256-wide ones (the 12888 x 3072 qkv GEMM: 9 waves x 256 vs 17 waves x 128) take the narrower
+  // tile.  Measured on the B200 (profiles/r02_gemm_bn_auto_ab.txt): ViT-L GEMM time 10.99 ms instead of 10.19 -- the
+  // 128-wide tile's main loop (A re-streamed twice as often, half the MMA N) loses more than the shorter tail gains;
+  // ConvNeXt-L: 13.41 vs 13.52 ms.
   static const int bn_auto = [] {
     const char* e = getenv("UDB_GEMM_BN_AUTO");
-    return e ? atoi(e) : 1;
+    return e ? atoi(e) : 0;
   }();
   if (bn_auto && bn == 256 && pair_env != 0 && g->store_mode != UDB_STORE_HEAD && !g->ln_stats_out) {
     const long long pairs = num_sms() / 2;

@@ -1,5 +1,5 @@
 """Event timeline of one attention CTA (needs a -DUDB_ATTN_TRACE variant build, see tools/build_variant.sh).
-Times are clock64 deltas relative to the first softmax event; sm = softmax warp 2, mma = the MMA warp."""
+Times are clock64 deltas relative to the first softmax event."""
 import ctypes
 import os
 import sys
@@ -20,23 +20,9 @@ buf = (ctypes.c_longlong * (32 * 16))()
 lib.udb_attn_trace_read(buf)
 ev = [[buf[j * 16 + k] for k in range(16)] for j in range(13)]
 t0 = ev[0][0]
-if os.environ.get("UDB_ATTN_V", "3") == "3":   # third-generation kernel: row r = the r-th chunk of each stream (32 keys)
-    names = {0: "g0:s_full", 1: "g0:exp", 2: "g0:arrived", 4: "g1:s_full", 5: "g1:exp", 6: "g1:arrived",
-             8: "mma:p(g0)", 9: "mma:iss(g0)", 10: "mma:p(g1)", 11: "mma:iss(g1)"}
-    ev = [[buf[j * 16 + k] for k in range(16)] for j in range(26)]
-    for j in range(4, 16):
-        items = sorted((ev[j][k] - t0, names[k]) for k in names if ev[j][k])
-        print(f"chunk pair {j:2d}: " + "  ".join(f"{n}@{t}" for t, n in items))
-    sys.exit(0)
-if os.environ.get("UDB_ATTN_V", "3") == "2":   # second-generation kernel: g0 / g1 = softmax warps 2 / 6, mma = the issuer
-    names = {0: "g0:s_full", 1: "g0:c0", 2: "g0:c1", 3: "g0:arrived", 4: "g1:s_full", 5: "g1:c0", 6: "g1:c1", 7: "g1:arrived",
-             8: "mma:p0", 9: "mma:iss0", 10: "mma:p1", 11: "mma:iss1"}
-    for j in range(13):
-        items = sorted((ev[j][k] - t0, names[k]) for k in names if ev[j][k])
-        print(f"tile {j:2d}: " + "  ".join(f"{n}@{t}" for t, n in items))
-    sys.exit(0)
-names = {0: "sm:sA_full", 1: "sm:A_done", 2: "sm:sB_full", 3: "sm:B_done", 4: "sm:p_free", 5: "sm:p_full!",
-         8: "mma:sA_free", 9: "mma:qkA_iss", 10: "mma:sB_free", 11: "mma:qkB_iss", 12: "mma:p_full", 13: "mma:pv_iss"}
+# g0 / g1 = softmax warps 2 / 6 (first warp of each stream), mma = the issuer; c0 / c1 = 32-key chunks of the stream's half
+names = {0: "g0:s_full", 1: "g0:c0", 2: "g0:c1", 3: "g0:arrived", 4: "g1:s_full", 5: "g1:c0", 6: "g1:c1", 7: "g1:arrived",
+         8: "mma:p0", 9: "mma:iss0", 10: "mma:p1", 11: "mma:iss1"}
 for j in range(13):
     items = sorted((ev[j][k] - t0, names[k]) for k in names if ev[j][k])
     print(f"tile {j:2d}: " + "  ".join(f"{n}@{t}" for t, n in items))

@@ -1,27 +1,6 @@
-// Fused attention forward for sm_100a:  O = softmax(Q K^T * scale) V   (no mask, no dropout)
-//
-// One CTA = one (batch, head, 128-query tile); two CTAs are resident per SM (TMEM 2 x 256 columns,
-// <= 113 KB shared memory each).  Keys are processed in tiles of 128, each as two 64-key HALVES with
-// their own score buffer and barriers:
-//   warp 0      : TMA producer (Q once; K_j / V_j tiles through two independent 2-stage rings)
-//   warp 1      : TMEM allocator + MMA issuer (whole warp in the control flow, one elected lane issues).
-//                 S_j^h = Q (K_j^h)^T (M128 N64 K64) into TMEM columns [64h, 64h+64); as soon as the
-//                 softmax warps release half h of tile j the same half of tile j+1 is issued, so the
-//                 QK^T latency (4 MMAs + commit round trip, ~500 clk) hides behind the softmax of the
-//                 other half.  O += P_j V_j (M128 N64 K128, V is the MN-major B operand) accumulates
-//                 in TMEM columns [128, 192).
-//   warps 2..5  : softmax, one query row per thread, 64 scores at a time in registers.  SPECULATIVE
-//                 single pass: exp2(s*scale - m_ref) against the current reference maximum and the
-//                 half's row maximum in the same loop (MUFU and ALU pipes overlap); only if some row's
-//                 maximum outgrew the reference by more than 2^8 (rare after the first tile) the half is
-//                 redone from the scores still in TMEM and O / l / the already packed half are rescaled
-//                 (lazy rescale).  fp32 max / sum with packed f32x2 math; P_j as f16 through
-//                 128B-swizzled shared memory.
-// Measured structure (tools/attn_trace.py, tools/mma_probe.cu, B200): a single softmax warp needs
-// ~12 clk per MUFU.EX2 (in-order issue, two such warps share a sub-partition's MUFU), a tcgen05.mma
-// burst has ~280 clk of fixed issue-to-mbarrier latency, SS-mode M128 N64 K16 takes 53 clk.
-// Replaces F.scaled_dot_product_attention (reference: metadinov2/attention.py:58,
-// layers/attention.py:136).
+// Fused attention forward for sm_100a:  O = softmax(Q K^T * scale) V   (no mask, no dropout), head dim 64.
+// One kernel, attn_fwd2_kernel (design notes in front of it); a split-f16 fp32 variant for the parity mode at the end.
+// Replaces F.scaled_dot_product_attention (reference: metadinov2/attention.py:58, layers/attention.py:136).
 #include "common.h"
 #include "ptx.cuh"
 
@@ -31,8 +10,6 @@ constexpr int AT_BQ = 128;       // queries per CTA
 constexpr int AT_BK = 128;       // keys per tile
 constexpr int AT_HK = 64;        // keys per half tile (softmax / QK^T granularity)
 constexpr int AT_CTAS_PER_SM = 2;
-constexpr int AT_KV_STAGES = 2;  // per ring
-constexpr int AT_THREADS = 192;  // TMA warp, MMA warp, 4 softmax warps
 
 #ifdef UDB_ATTN_TRACE   // variant build only: event timeline of CTA (1,0,0): softmax warp 2 + the MMA warp
 __device__ long long g_attn_trace[32 * 16];
@@ -57,10 +34,11 @@ __device__ __forceinline__ float ex2(float x) {
 
 // The MUFU unit (16 ex2 / clk / SM) is the binding pipe of d = 64 attention, so every UDB_ATTN_POLY-th PAIR of scores takes
 // its exp2 on the FMA / ALU pipes instead: x = k + f, k = round(x), 2^f by a degree-4 minimax polynomial on [-0.5, 0.5]
-// (relative error 2.7e-6, two orders below the f16 rounding of P; the A/B below was measured with degree 3, 7.5e-5),
-// 2^k added into the exponent field; inputs clamped to >= -100 (exp2 = 0 in f16 anyway).
-// Same-box A/B on the B200 (profiles/r02_attn_poly_ab.txt): share 1/4 -> 4.12 ms of attention per step instead of 4.44
-// (1/3 and 1/5: 4.22; 1/2: 4.53, slower -- the FMA issue slots become the limit; 1/8: 4.30).  -DUDB_ATTN_POLY=0 turns it off.
+// (relative error 2.7e-6, two orders below the f16 rounding of P), 2^k added into the exponent field; inputs clamped to
+// >= -100 (exp2 = 0 in f16 anyway).  Same-box A/B on the B200 (profiles/r02_attn_poly_ab.txt, round-1 kernel, degree 3):
+// share 1/4 -> 4.12 ms of attention per step instead of 4.44 (1/3 and 1/5: 4.22; 1/2: 4.53, slower -- the FMA issue slots
+// become the limit; 1/8: 4.30); on the present kernel 1/3 .. 1/6 are within noise of each other, none: +4 %
+// (profiles/r02_attn_kernels_ab.txt).  -DUDB_ATTN_POLY=0 turns it off.
 #ifndef UDB_ATTN_POLY
 #define UDB_ATTN_POLY 4
 #endif
@@ -113,48 +91,6 @@ __device__ __forceinline__ float softmax_half(const uint32_t (&sv)[W], uint32_t*
   return ps0 + ps1;
 }
 
-// Speculative variant: probabilities against the CURRENT reference m_used AND the half's row maximum
-// in one pass, so the max (ALU pipe, FMNMX3) overlaps the exp2 (MUFU pipe) instead of preceding it.
-// The caller checks afterwards that the maximum did not outgrow the reference by more than the
-// lazy-rescale threshold; if it did (rare) the results -- possibly overflowed -- are discarded and
-// the half is redone from the scores still held in TMEM.
-template <bool MASK, int W>
-__device__ __forceinline__ float softmax_half_spec(const uint32_t (&sv)[W], uint32_t* pk, const float sc,
-                                                   const float m_used, const int kv_left, float& mx_out) {
-  const uint64_t sc2 = pack2(sc, sc), nm2 = pack2(-m_used, -m_used);
-  uint64_t ps[4] = {0ull, 0ull, 0ull, 0ull};
-  float m0 = -INFINITY, m1 = -INFINITY;
-#pragma unroll
-  for (int i = 0; i < W; i += 2) {
-    const float s0 = __uint_as_float(sv[i]), s1 = __uint_as_float(sv[i + 1]);
-    float e0, e1;
-    if (UDB_ATTN_POLY && ((i >> 1) % (UDB_ATTN_POLY ? UDB_ATTN_POLY : 1)) == (UDB_ATTN_POLY ? UDB_ATTN_POLY - 1 : 1)) {
-      exp2_poly_pair(fma2(pack2(s0, s1), sc2, nm2), e0, e1);
-    } else {
-      float t0, t1;
-      unpack2(fma2(pack2(s0, s1), sc2, nm2), t0, t1);
-      e0 = ex2(t0);
-      e1 = ex2(t1);
-    }
-    if (MASK) {
-      e0 = (i < kv_left) ? e0 : 0.f;
-      e1 = (i + 1 < kv_left) ? e1 : 0.f;
-      m0 = (i < kv_left) ? fmaxf(m0, s0) : m0;
-      m1 = (i + 1 < kv_left) ? fmaxf(m1, s1) : m1;
-    } else if ((i >> 1) & 1) {
-      m1 = max3(m1, s0, s1);
-    } else {
-      m0 = max3(m0, s0, s1);
-    }
-    ps[(i >> 1) & 3] = add2(ps[(i >> 1) & 3], pack2(e0, e1));
-    pk[i >> 1] = pack_half2(e0, e1);
-  }
-  mx_out = fmaxf(m0, m1);
-  float ps0, ps1;
-  unpack2(add2(add2(ps[0], ps[1]), add2(ps[2], ps[3])), ps0, ps1);
-  return ps0 + ps1;
-}
-
 template <bool MASK, int W>
 __device__ __forceinline__ float half_max(const uint32_t (&sv)[W], const int kv_left) {
   float m0 = -INFINITY, m1 = -INFINITY;    // two chains for ILP
@@ -171,296 +107,13 @@ __device__ __forceinline__ float half_max(const uint32_t (&sv)[W], const int kv_
   return fmaxf(m0, m1);
 }
 
-template <int HD>
-__global__ void __launch_bounds__(AT_THREADS, AT_CTAS_PER_SM)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                const __grid_constant__ CUtensorMap tmV, const AttnArgs p) {
-  static_assert(HD == 64, "head_dim 64 only");
-  constexpr int kQBytes = AT_BQ * HD * 2;      // 16 KB
-  constexpr int kKBytes = AT_BK * HD * 2;      // 16 KB
-  constexpr int kPBytes = AT_BQ * AT_BK * 2;   // 32 KB (two 64-key sub-tiles of 16 KB)
-  constexpr uint32_t kTmemCols = 256;          // S halves: [0,64) [64,128)   O: [128,192)
-  constexpr int NS = AT_KV_STAGES;
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + kQBytes;                  // NS stages
-  uint8_t* sV = sK + NS * kKBytes;             // NS stages
-  uint8_t* sP = sV + NS * kKBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + kPBytes);
-  uint64_t* q_full = bars;
-  uint64_t* k_full = bars + 1;             // [NS]
-  uint64_t* v_full = k_full + NS;          // [NS]
-  uint64_t* k_empty = v_full + NS;         // [NS]  K stage free once both QK half MMAs have completed
-  uint64_t* v_empty = k_empty + NS;        // [NS]  V stage free once its PV MMA has completed
-  uint64_t* s_full = v_empty + NS;         // [2]   S_j^h complete in TMEM
-  uint64_t* s_free = s_full + 2;           // [2]   S_j^h consumed by all softmax warps
-  uint64_t* p_full = s_free + 2;           // P_j written to smem
-  uint64_t* p_free = p_full + 1;           // PV_j MMA done (one phase per tile)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(p_free + 1);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * AT_BQ;
-  const int head = blockIdx.y;
-  const int b = blockIdx.z;
-  const int n_tiles = p.n_kv_tiles;
-  pdl_launch_dependents();
-
-  if (threadIdx.x == 0) {
-    if (smem_u32(smem) & 1023) __trap();
-    prefetch_tmap(&tmQ);
-    prefetch_tmap(&tmK);
-    prefetch_tmap(&tmV);
-    mbar_init(q_full, 1);
-    for (int i = 0; i < NS; ++i) {
-      mbar_init(&k_full[i], 1);
-      mbar_init(&v_full[i], 1);
-      mbar_init(&k_empty[i], 1);
-      mbar_init(&v_empty[i], 1);
-    }
-    for (int h = 0; h < 2; ++h) {
-      mbar_init(&s_full[h], 1);
-      mbar_init(&s_free[h], 4);
-    }
-    mbar_init(p_full, 4);
-    mbar_init(p_free, 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc<kTmemCols>(tmem_ptr);
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_ptr;
-  const uint32_t tmem_O = tmem_base + AT_BK;
-  pdl_wait();   // everything above overlapped the previous kernel's tail
-#ifdef UDB_ATTN_TRACE
-  const bool trace_on = blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && (warp == 1 || warp == 2) && lane == 0;
-#endif
-
-  if (warp == 0) {
-    const bool leader = elect_one();   // whole warp in the control flow, one lane issues (see the MMA warp)
-    if (leader) {
-      mbar_arrive_expect_tx(q_full, kQBytes);
-      tma_load_3d(sQ, &tmQ, q_full, p.q_col0 + head * HD, q0, b);
-    }
-    __syncwarp();
-    for (int j = 0; j < n_tiles; ++j) {
-      const int st = j % NS;
-      const uint32_t ph = ((j / NS) & 1) ^ 1;
-      mbar_wait(&k_empty[st], ph);
-      if (leader) {
-        mbar_arrive_expect_tx(&k_full[st], kKBytes);
-        tma_load_3d(sK + st * kKBytes, &tmK, &k_full[st], p.k_col0 + head * HD, j * AT_BK, b);
-      }
-      __syncwarp();
-      mbar_wait(&v_empty[st], ph);
-      if (leader) {
-        mbar_arrive_expect_tx(&v_full[st], kKBytes);
-        tma_load_3d(sV + st * kKBytes, &tmV, &v_full[st], p.v_col0 + head * HD, j * AT_BK, b);
-      }
-      __syncwarp();
-    }
-  } else if (warp == 1) {
-    // The whole warp runs the control flow so that descriptors and addresses stay in uniform registers
-    // (under a lane-0 branch ptxas wraps every tcgen05.mma in an ELECT / R2UR waterfall loop);
-    // one elected lane issues the MMAs and commits.
-    const bool leader = elect_one();
-    constexpr uint32_t idesc_qk = umma_idesc_f16(AT_BQ, AT_HK, false, false);
-    constexpr uint32_t idesc_pv = umma_idesc_f16(AT_BQ, HD, false, true);   // B = V is MN-major
-    const uint64_t dq = umma_desc_sw128(smem_u32(sQ), 16, 1024);
-    auto issue_qk = [&](int j, int h) {   // S^h = Q (K_j rows [64h, 64h+64))^T
-      const int st = j % NS;
-      if (h == 0) {
-        mbar_wait(&k_full[st], (j / NS) & 1);
-        tc_fence_after_sync();
-      }
-      const uint64_t dk = umma_desc_sw128(smem_u32(sK + st * kKBytes + h * (AT_HK * 128)), 16, 1024);
-      if (leader) {
-#pragma unroll
-        for (int k = 0; k < HD / 16; ++k) umma_f16_ss(tmem_base + h * AT_HK, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0);
-        if (h == 1) umma_commit(&k_empty[st]);
-        umma_commit(&s_full[h]);
-      }
-      __syncwarp();
-    };
-    mbar_wait(q_full, 0);
-    issue_qk(0, 0);
-    issue_qk(0, 1);
-    for (int j = 0; j < n_tiles; ++j) {
-      const int st = j % NS;
-      if (j + 1 < n_tiles) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          mbar_wait(&s_free[h], j & 1);            // half h of tile j consumed: its columns may be overwritten
-          tc_fence_after_sync();
-          AT_EV(j, 8 + 2 * h);
-          issue_qk(j + 1, h);
-          AT_EV(j, 9 + 2 * h);
-        }
-      }
-      mbar_wait(p_full, j & 1);                    // P_j written
-      AT_EV(j, 12);
-      mbar_wait(&v_full[st], (j / NS) & 1);
-      tc_fence_after_sync();
-      const uint64_t dv = umma_desc_sw128(smem_u32(sV + st * kKBytes), 1024, 1024);
-      const uint64_t dp0 = umma_desc_sw128(smem_u32(sP), 16, 1024);
-      if (leader) {
-#pragma unroll
-        for (int ks = 0; ks < AT_BK / 16; ++ks) {
-          // A = P: sub-tile (ks/4) of 16 KB, 32 B per 16-key step inside the swizzle atom; B = V: 2 KB per step
-          const uint64_t dp = dp0 + (uint64_t)((ks >> 2) * (AT_BQ * 128) >> 4) + 2 * (ks & 3);
-          umma_f16_ss(tmem_O, dp, dv + (uint64_t)(ks * 2048 >> 4), idesc_pv, (j | ks) != 0);
-        }
-        umma_commit(&v_empty[st]);
-        umma_commit(p_free);
-      }
-      __syncwarp();
-      AT_EV(j, 13);
-    }
-  } else {
-    // ------------------------------------------------------------------ softmax warps
-    const int quad = warp & 3;                  // TMEM lane quadrant of this warp
-    const int row = quad * 32 + lane;           // query row inside the tile == TMEM lane
-    const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
-    float m_used = -INFINITY, l_run = 0.f;
-    const int sw = row & 7;
-    const float sc = p.scale_log2;
-    constexpr float kRescaleThreshold = 8.0f;   // log2 domain
-    uint32_t pk[AT_BK / 2];                     // P row of the current tile, f16 pairs
-
-    for (int j = 0; j < n_tiles; ++j) {
-      const int kv_left = p.seq_k - j * AT_BK;   // valid keys in this tile (>= 1)
-      bool pv_done = false;                      // PV_{j-1} known complete (needed before O / sP are touched)
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        mbar_wait(&s_full[h], j & 1);
-        tc_fence_after_sync();
-        AT_EV(j, 2 * h);
-        const int kvl = kv_left - h * AT_HK;     // valid keys in this half (may be <= 0 in the last tile)
-        const bool full = kvl >= AT_HK;
-        uint32_t sv[AT_HK];
-        auto load_scores = [&]() {
-#pragma unroll
-          for (int c = 0; c < AT_HK; c += 32)
-            tmem_ld_32x32b_x32(tmem_base + lane_addr + h * AT_HK + c, *reinterpret_cast<uint32_t(*)[32]>(&sv[c]));
-          tmem_ld_wait();
-        };
-        load_scores();
-        bool careful = (j | h) == 0;             // very first half: no reference yet
-        if (!careful) {
-          // common case: exp2 against the current reference and the row max in the same pass
-          float mx;
-          const float psum = full ? softmax_half_spec<false>(sv, pk + 32 * h, sc, m_used, kvl, mx)
-                                  : softmax_half_spec<true>(sv, pk + 32 * h, sc, m_used, kvl, mx);
-          careful = __any_sync(0xffffffffu, mx * sc > m_used + kRescaleThreshold);
-          if (careful) load_scores();            // rare: the speculative results are discarded
-          else l_run += psum;
-        }
-        if (careful) {
-          const float m_half = (full ? half_max<false>(sv, kvl) : half_max<true>(sv, kvl)) * sc;
-          const bool need = m_half > m_used + kRescaleThreshold;   // always true on the very first half
-          float alpha = 1.0f;
-          if (need) {
-            alpha = ex2(m_used - m_half);          // 0 on the very first half
-            m_used = m_half;
-          }
-          if ((j | h) != 0 && __any_sync(0xffffffffu, need)) {
-            if (j > 0) {
-              // rescale this warp's 32 rows of O (rows that do not need it multiply by 1)
-              if (!pv_done) {
-                mbar_wait(p_free, (j - 1) & 1);
-                tc_fence_after_sync();
-                pv_done = true;
-              }
-              const uint64_t a2 = pack2(alpha, alpha);
-#pragma unroll 1
-              for (int c = 0; c < HD; c += 16) {
-                uint32_t r[16];
-                tmem_ld_32x32b_x16(tmem_O + lane_addr + c, r);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 16; i += 2) {
-                  float lo, hi;
-                  unpack2(mul2(pack2u(r[i], r[i + 1]), a2), lo, hi);
-                  r[i] = __float_as_uint(lo);
-                  r[i + 1] = __float_as_uint(hi);
-                }
-                tmem_st_32x32b_x16(tmem_O + lane_addr + c, r);
-              }
-              tmem_st_wait();
-            }
-            if (h == 1) {
-              // the first half of this tile was packed against the old reference
-              const __half2 ah = __float2half2_rn(alpha);
-#pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                __half2 v = __hmul2(*reinterpret_cast<__half2*>(&pk[i]), ah);
-                pk[i] = *reinterpret_cast<uint32_t*>(&v);
-              }
-            }
-          }
-          const float psum = full ? softmax_half<false>(sv, pk + 32 * h, sc, m_used, kvl)
-                                  : softmax_half<true>(sv, pk + 32 * h, sc, m_used, kvl);
-          l_run = fmaf(l_run, alpha, psum);
-        }
-        // release this half of the score buffer: the same half of the next tile is computed while the
-        // other half / the P store are being worked on
-        tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_free[h]);
-        AT_EV(j, 2 * h + 1);
-      }
-      // the PV MMA of tile j-1 must have finished reading sP (the next completion of p_free needs
-      // this thread's own arrival on p_full, so the parity is unambiguous)
-      if (j > 0 && !pv_done) mbar_wait(p_free, (j - 1) & 1);
-      AT_EV(j, 4);
-      uint8_t* p_row = sP + row * 128;
-#pragma unroll
-      for (int q = 0; q < AT_BK / 8; ++q)      // chunks of 8 halves (16 B); 64-key sub-tiles of 16 KB
-        *reinterpret_cast<uint4*>(p_row + (q >> 3) * (AT_BQ * 128) + (((q & 7) ^ sw) << 4)) =
-            make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-      fence_proxy_async_smem();
-      tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
-      AT_EV(j, 5);
-    }
-    // epilogue: O / l
-    mbar_wait(p_free, (n_tiles - 1) & 1);   // last PV done => all done
-    tc_fence_after_sync();
-    const float inv = 1.0f / l_run;
-    const int q = q0 + row;
-    __half* op = p.out + ((long long)b * p.seq_q + (q < p.seq_q ? q : 0)) * p.ldo + p.o_col0 + head * HD;
-#pragma unroll
-    for (int c = 0; c < HD; c += 32) {
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(tmem_O + lane_addr + c, r);
-      tmem_ld_wait();
-      if (q < p.seq_q) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          *reinterpret_cast<uint4*>(op + c + i) = make_uint4(
-              pack_half2(__uint_as_float(r[i]) * inv, __uint_as_float(r[i + 1]) * inv),
-              pack_half2(__uint_as_float(r[i + 2]) * inv, __uint_as_float(r[i + 3]) * inv),
-              pack_half2(__uint_as_float(r[i + 4]) * inv, __uint_as_float(r[i + 5]) * inv),
-              pack_half2(__uint_as_float(r[i + 6]) * inv, __uint_as_float(r[i + 7]) * inv));
-        }
-      }
-    }
-  }
-
-  tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after_sync();
-    tmem_dealloc<kTmemCols>(tmem_base);
-  }
-}
-
-
 // ---------------------------------------------------------------------------------------------
-// Second-generation kernel (the default): same tiling (128 queries per CTA, two CTAs per SM, keys in tiles of 128 = two
-// 64-key halves) but the two halves are INDEPENDENT online-softmax streams, each with its own group of four softmax warps,
+// One CTA = one (batch, head, 128-query tile); two CTAs per SM (TMEM 2 x 256 columns, 113 KB of shared memory each); keys in
+// tiles of 128 = two 64-key halves.  Warps: 0 = TMA producer (Q once, K / V tiles through 3-stage rings), 1 = TMEM allocator
+// and MMA issuer (whole warp in the control flow, one elected lane issues), 2..9 = two groups of four softmax warps, one
+// query row per thread.  The round-1 kernel had ONE softmax group working through both halves with P staged in shared
+// memory; it ran at 0.34 of the tensor peak with no unit above 53 % -- every warp waiting on a chain.  Here the two halves are
+// INDEPENDENT online-softmax streams, each with its own group of four softmax warps,
 // its own reference maximum / row sum and its own output accumulator in tensor memory; the streams are merged once, in the
 // epilogue (O = (a0 O0 + a1 O1) / (a0 l0 + a1 l1), a_g = 2^(m_g - max m)).  What that buys:
 //   * four softmax warps per sub-partition instead of two, each with half the dependent chain per tile -- the MUFU pipe
@@ -473,11 +126,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 // TMEM (256 columns): S_g / P_g at [64g, 64g+64), O_g at [128+64g, 128+64g+64).  Because P_g aliases S_g the issuer puts
 // PV(j,g) and QK(j+1,g) back to back (the tensor pipe executes one thread's MMAs in order), and the commit that publishes
 // S_g(j+1) also tells the softmax group that O_g is quiescent.
-// Measured on the B200 (tools/tmem_probe.cu, tools/attn_trace.py, profiles/r02_attn2_*): tcgen05.ld.x32 + wait costs a
-// lone warp ~120 clk (16 warps reach 356 B/clk per SM, so TMEM reads are latency, not bandwidth); MUFU.EX2 saturates at
-// 15.4 / clk / SM; one tile takes a CTA ~2650 clk: ~1350 of softmax per stream and ~1300 until its next scores arrive
-// (P published -> the 8 MMAs get through the FIFO the SM's four streams share -> commit), which the other stream and the
-// other CTA fill.  ONE issuer warp serving the streams in turn keeps them in anti-phase; a second issuer (one per stream)
+// Measured on the B200 (tools/tmem_probe.cu, issue_probe.cu, attn_trace.py; profiles/r02_attn2_trace.txt, r02_*_probe.txt):
+// tcgen05.ld.x32 + wait costs a lone warp ~120 clk (16 warps reach 356 B/clk per SM, so TMEM reads are latency, not
+// bandwidth); MUFU.EX2 saturates at 15.4 / clk / SM; issuing a tcgen05.mma costs ~27 clk, but one thread's tcgen05.commit
+// arrivals reach their mbarriers ~130 clk apart -- so the commit a softmax group waits for (s_full) is issued first in every
+// event.  One tile takes a CTA ~2350 clk: ~1350 of softmax per stream and ~1000 until its next scores arrive (P published ->
+// the issuer wakes -> 8 MMAs through the FIFO the SM's four streams share -> commit -> wake-up), which the other stream and
+// the other CTA fill.  ONE issuer warp serving the streams in turn keeps them in anti-phase; a second issuer (one per stream)
 // let them drift into phase and was 6 % slower.
 // ---------------------------------------------------------------------------------------------
 constexpr int AT2_THREADS = 320;   // TMA warp, MMA warp, 2 groups x 4 softmax warps
@@ -968,26 +623,15 @@ extern "C" int udb_attention_f16(const udb_attn_t* a, void* stream) {
   p.scale_log2 = a->scale * 1.4426950408889634f;
   dim3 grid((a->seq_q + AT_BQ - 1) / AT_BQ, a->heads, a->B);
   note_work(4.0 * a->B * a->heads * (double)a->seq_q * a->seq_k * HD, 2.0 * a->B * a->heads * HD * (2.0 * a->seq_q + 2.0 * a->seq_k));
-  static const int version = [] { const char* e = getenv("UDB_ATTN_V"); return e ? atoi(e) : 2; }();   // 1: first-generation kernel
-  cudaError_t e;
-  if (version == 1) {
-    constexpr int smem_bytes = 16384 + 2 * AT_KV_STAGES * (AT_BK * 128) + AT_BQ * AT_BK * 2 + 256;
-    static std::atomic<uint64_t> attr_mask{0};
-    if (first_on_device(attr_mask)) {
-      e = cudaFuncSetAttribute(attn_fwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-      if (e != cudaSuccess) { set_error("attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1; }
-    }
-    e = launch_ex(attn_fwd_kernel<HD>, grid, dim3(AT_THREADS), smem_bytes, reinterpret_cast<cudaStream_t>(stream), 1, tq, tk, tv, p);
-  } else {
-    constexpr int smem_bytes = 16384 + 2 * AT2_STAGES * (AT_BK * 128) + 256;
-    static_assert(2 * (smem_bytes + 1024) <= 228 * 1024, "two CTAs per SM");
-    static std::atomic<uint64_t> attr_mask{0};
-    if (first_on_device(attr_mask)) {
-      e = cudaFuncSetAttribute(attn_fwd2_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-      if (e != cudaSuccess) { set_error("attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1; }
-    }
-    e = launch_ex(attn_fwd2_kernel<HD>, grid, dim3(AT2_THREADS), smem_bytes, reinterpret_cast<cudaStream_t>(stream), 1, tq, tk, tv, p);
+  constexpr int smem_bytes = 16384 + 2 * AT2_STAGES * (AT_BK * 128) + 256;
+  static_assert(2 * (smem_bytes + 1024) <= 228 * 1024, "two CTAs per SM");
+  static std::atomic<uint64_t> attr_mask{0};
+  if (first_on_device(attr_mask)) {
+    cudaError_t ea = cudaFuncSetAttribute(attn_fwd2_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (ea != cudaSuccess) { set_error("attention: cudaFuncSetAttribute: %s", cudaGetErrorString(ea)); return 1; }
   }
+  cudaError_t e = launch_ex(attn_fwd2_kernel<HD>, grid, dim3(AT2_THREADS), smem_bytes, reinterpret_cast<cudaStream_t>(stream), 1,
+                            tq, tk, tv, p);
   if (e != cudaSuccess) { set_error("attn_fwd_kernel launch: %s", cudaGetErrorString(e)); return 1; }
   return check_launch("attn_fwd_kernel");
 }

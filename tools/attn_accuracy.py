@@ -1,5 +1,5 @@
 """Mean / max error of the attention kernel against a float64 reference on the same f16 inputs (run once per kernel version:
-UDB_ATTN_V=1 / 2).  Inputs: N(0,1) q/k/v and a 'peaky' set (q scaled by 3) closer to trained attention maps."""
+UDB_LIB=<variant library>).  Inputs: N(0,1) q/k/v and a 'peaky' set (q scaled by 3) closer to trained attention maps."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -19,5 +19,5 @@ for name, gain in (("normal", 1.0), ("peaky", 3.0), ("very peaky", 6.0)):
     ref = (torch.softmax(q @ k.transpose(-1, -2) * d ** -0.5, -1) @ v).permute(0, 2, 1, 3).reshape(B * S, D)
     e = (out.double() - ref).abs()
     r16 = (ref.half().double() - ref).abs()          # the output rounding alone
-    print(f"v{os.environ.get('UDB_ATTN_V', '2')} {name:10s}: mean abs err {e.mean().item():.4e}  max {e.max().item():.3e}  rms {e.pow(2).mean().sqrt().item():.4e}"
+    print(f"{name:10s}: mean abs err {e.mean().item():.4e}  max {e.max().item():.3e}  rms {e.pow(2).mean().sqrt().item():.4e}"
           f"   (f16 rounding of the exact result alone: mean {r16.mean().item():.4e})  ref rms {ref.pow(2).mean().sqrt().item():.3e}")

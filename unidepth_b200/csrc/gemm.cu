@@ -173,12 +173,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, const EpiWarp& 
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float4 b4 = __ldg(bp + j);
-#ifdef UDB_EPI_PACK
-              unpack2(add2(pack2(v[4 * j], v[4 * j + 1]), pack2(b4.x, b4.y)), v[4 * j], v[4 * j + 1]);
-              unpack2(add2(pack2(v[4 * j + 2], v[4 * j + 3]), pack2(b4.z, b4.w)), v[4 * j + 2], v[4 * j + 3]);
-#else
               v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
-#endif
             }
           }
           if (p.act == UDB_ACT_GELU) {
@@ -201,12 +196,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, const EpiWarp& 
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float4 g4 = __ldg(gp + j);
-#ifdef UDB_EPI_PACK
-              unpack2(mul2(pack2(v[4 * j], v[4 * j + 1]), pack2(g4.x, g4.y)), v[4 * j], v[4 * j + 1]);
-              unpack2(mul2(pack2(v[4 * j + 2], v[4 * j + 3]), pack2(g4.z, g4.w)), v[4 * j + 2], v[4 * j + 3]);
-#else
               v[4 * j] *= g4.x; v[4 * j + 1] *= g4.y; v[4 * j + 2] *= g4.z; v[4 * j + 3] *= g4.w;
-#endif
             }
           }
           long long coff = n0;
@@ -279,20 +269,6 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, const EpiWarp& 
               st_s2 = fmaf(dlt, dlt, st_s2);
             }
           }
-#ifdef UDB_EPI_DIRECT16
-          // f16-only outputs (qkv, fc1, ...): the thread's 32 columns are 64 contiguous bytes of its own row -- store them
-          // straight from registers (4 x 16 B) instead of transposing through shared memory
-          if (p.out && !p.out_f32 && !p.out2 && p.out_split == 0) {
-            if (valid) {
-              uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + out_off + coff);
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                op[j] = make_uint4(pack_half2(v[8 * j], v[8 * j + 1]), pack_half2(v[8 * j + 2], v[8 * j + 3]),
-                                   pack_half2(v[8 * j + 4], v[8 * j + 5]), pack_half2(v[8 * j + 6], v[8 * j + 7]));
-            }
-            continue;
-          }
-#endif
           if (p.out) {
             stage_rows(v);
             __syncwarp();

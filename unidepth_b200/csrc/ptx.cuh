@@ -395,17 +395,9 @@ __device__ __forceinline__ void gelu_erf_pair(float& x0, float& x1) {
   unpack2(q, p0, p1);
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(p0));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(p1));
-#ifdef UDB_EPI_PACK
-  // Phi(|x|) = 1 - r/2, Phi(-|x|) = r/2:  gelu = x * (x >= 0 ? 1 - r/2 : r/2)   (one packed FMA + two selects + one packed mul)
-  float a0, a1;
-  unpack2(fma2(pack2(r0, r1), pack2(-0.5f, -0.5f), pack2(1.0f, 1.0f)), a0, a1);
-  const float s0 = x0 >= 0.f ? a0 : 1.0f - a0, s1 = x1 >= 0.f ? a1 : 1.0f - a1;
-  unpack2(mul2(pack2(x0, x1), pack2(s0, s1)), x0, x1);
-#else
   const float h0 = 0.5f * x0, h1 = 0.5f * x1;
   x0 = fmaf(copysignf(1.0f - r0, x0), h0, h0);
   x1 = fmaf(copysignf(1.0f - r1, x1), h1, h1);
-#endif
 }
 __device__ __forceinline__ float leaky(float x) { return x > 0.f ? x : 0.01f * x; }
 

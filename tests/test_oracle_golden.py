@@ -188,3 +188,33 @@ def test_nystrom_restatement_properties():
     x = torch.arange(300.0).reshape(1, 1, 300, 1)
     lm = O1._avg_landmarks(x, 128)[0, 0, :, 0]
     assert lm[0] == 0.5 and lm[83] == 166.5 and lm[84] == 169.0 and lm[-1] == 298.0
+
+
+def test_nystrom_restatement_matches_independent_implementation():
+    """Second anchor for the one "parity unpinned" function: HuggingFace transformers ships the Nystromformer authors'
+    own implementation of the same published algorithm (segment-mean landmarks, three softmax kernels, 6 Newton-Schulz
+    iterations).  With its skip-connection convolution zeroed and the exact 1/||K||_1 initialisation (xformers'
+    default `pinverse_original_init=False`) it must agree with `nystrom_attention` to fp32 rounding wherever the
+    sequence length is a multiple of the landmark count (HF supports nothing else).  xformers' own arithmetic stays
+    unpinned only for the ragged pooling (checked by hand in the test above) and the s == landmarks shortcut."""
+    pytest.importorskip("transformers")
+    from transformers import NystromformerConfig
+    from transformers.models.nystromformer.modeling_nystromformer import NystromformerSelfAttention
+    import unidepth_v1_oracle as O1
+    torch.manual_seed(0)
+    # (heads, head_dim, tokens, landmarks, input scale): the V1 decoder's 1/8-scale block shape, a long peaky one, a small one
+    for heads, d, s, m, scale in ((4, 64, 1024, 128, 1.0), (8, 64, 2304, 128, 3.0), (2, 32, 640, 64, 2.0)):
+        cfg = NystromformerConfig(hidden_size=heads * d, num_attention_heads=heads, num_landmarks=m,
+                                  segment_means_seq_len=s, conv_kernel_size=3, attention_probs_dropout_prob=0.0)
+        att = NystromformerSelfAttention(cfg).eval()
+        att.init_option = "exact"            # any value but "original": per-matrix 1/||K||_1, as in xformers
+        att.conv.weight.data.zero_()         # xformers' NystromAttention default: no convolutional skip connection
+        x = torch.randn(2, s, heads * d) * scale
+        with torch.no_grad():
+            want = att(x)[0]
+            split = lambda t: t.view(2, s, heads, d).transpose(1, 2)
+            got = O1.nystrom_attention(split(att.query(x)), split(att.key(x)), split(att.value(x)), m)
+        got = got.transpose(1, 2).reshape(2, s, heads * d)
+        err = (got - want).abs().max().item()
+        print(f"nystrom vs HF Nystromformer heads={heads} d={d} s={s} m={m}: max abs {err:.2e} (mean |out| {want.abs().mean():.3f})")
+        assert err < 5e-6, err

@@ -401,8 +401,10 @@ def pinhole_rays(kmat: torch.Tensor, hh: int, ww: int):
 @torch.no_grad()
 def infer_v2(sd: Dict[str, torch.Tensor], config: dict, rgb: torch.Tensor,
              resolution_level: Optional[int] = None, normalize: bool = True,
-             interpolation_mode: str = "bilinear", taps_out: Optional[dict] = None):
-    """UniDepthV2.infer (unidepthv2.py:239-339) + encode_decode (:341-379), fp32 on CPU."""
+             interpolation_mode: str = "bilinear", taps_out: Optional[dict] = None, camera=None):
+    """UniDepthV2.infer (unidepthv2.py:239-339) + encode_decode (:341-379), fp32 on CPU.  `camera` (GT-camera branch,
+    :267-303,:361-362; decoder.py:400): a (...,3,3) pinhole K, or a camera object with the reference's
+    crop / resize / get_rays methods; its rays replace the predicted ones, the intrinsics output stays the predicted one."""
     spec = ModelSpec(config)
     if rgb.ndim == 3:
         rgb = rgb.unsqueeze(0)
@@ -417,7 +419,21 @@ def infer_v2(sd: Dict[str, torch.Tensor], config: dict, rgb: torch.Tensor,
     if taps_out is not None:
         taps_out["feat3"] = feats[-1].clone()
         taps_out["cls3"] = clss[-1].clone()
-    out = decoder(sd, spec, feats, clss, (nh, nw), taps_out=taps_out)
+    rays_gt = None
+    if isinstance(camera, torch.Tensor):
+        kn = camera.reshape(-1, 3, 3).float().clone()      # Camera.crop(-pads) then resize(factor): camera.py:78-81,115-120
+        kn[:, 0, 2] += paddings[0]
+        kn[:, 1, 2] += paddings[2]
+        kn[:, :2, :] *= factor
+        rays_gt = pinhole_rays(kn.expand(b, 3, 3) if kn.shape[0] == 1 else kn, nh, nw)
+    elif camera is not None:
+        import copy as _copy
+        cam = _copy.deepcopy(camera)
+        cam = cam.crop(left=-paddings[0], top=-paddings[2], right=-paddings[1], bottom=-paddings[3])
+        cam = cam.resize(factor)
+        r = cam.get_rays(shapes=(b, nh, nw))
+        rays_gt = r.expand(b, 3, nh, nw).flatten(2).transpose(1, 2)
+    out = decoder(sd, spec, feats, clss, (nh, nw), rays_gt=rays_gt, taps_out=taps_out)
     rays_map = out["rays"].transpose(1, 2).reshape(b, 3, nh, nw)
     points = rays_map * out["radius"]
     res = {}

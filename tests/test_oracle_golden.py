@@ -63,6 +63,38 @@ def test_oracle_matches_reference_golden(name, golden_dir):
         assert ((kk[:, i, j] - kr[:, i, j]).abs() / kr[:, i, j].abs()).max().item() < 1e-5
 
 
+CAMERA_CASES = ["vits_camK_120x160", "vits_campinhole_pad_96x288_rl3", "vits_cameucm_pad_200x70_rl0"]
+
+
+@pytest.mark.parametrize("name", CAMERA_CASES)
+def test_oracle_gt_camera_branch_matches_reference_golden(name, golden_dir):
+    """infer(rgb, camera=...) of the unmodified reference (oracle/make_golden_camera_infer.py): K tensor, Pinhole object with
+    padding + resolution level, a non-pinhole (EUCM) object on a portrait image.  The camera objects handed to the oracle
+    are this repo's own classes (unidepth_b200/camera.py), so this also checks them inside the whole forward."""
+    from unidepth_b200 import camera as C
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    meta = json.loads(str(z["__meta__"]))
+    cfg = json.load(open(os.path.join(golden_dir, meta["config"])))
+    sd = make_state_dict(cfg, meta["seed"])
+    kind, params = meta["camera"]["kind"], meta["camera"]["params"]
+    if kind == "K":
+        cam = torch.tensor([[[params[0], 0.0, params[2]], [0.0, params[1], params[3]], [0.0, 0.0, 1.0]]])
+    else:
+        cam = getattr(C, kind)(params=torch.tensor([params], dtype=torch.float32))
+    out = O.infer_v2(sd, cfg, _rgb(meta["shape"], meta["seed"]), resolution_level=meta["resolution_level"], camera=cam)
+    out = subsample_like_golden(out, meta)
+    for k, v in out.items():
+        ref = torch.from_numpy(z[k])
+        assert v.shape == ref.shape, (k, v.shape, ref.shape)
+        floor = 0.1 * ref.abs().mean().item()
+        err = ((v - ref).abs() / ref.abs().clamp(min=floor)).max().item()
+        print(name, k, "max rel err", err)
+        assert err < 3e-4, (k, err)
+    assert (out["rays"] - torch.from_numpy(z["rays"])).abs().max().item() < 2e-6       # the GT rays themselves
+    if kind != "K":      # the oracle works on a copy, like the product (the reference mutates the caller's object)
+        assert torch.equal(cam.params, torch.tensor([params], dtype=torch.float32))
+
+
 def test_shape_arithmetic_examples():
     # SURVEY.md section 8 a1 (values produced by the reference functions)
     assert O.get_resize_factor((480, 640), (2e5, 6e5))[1] == (490, 644)

@@ -382,22 +382,26 @@ static const ShapeTables* prepare(udb_engine* e, const udb_geometry_t& g) {
   if (pw == e->w.end()) { set_error("engine: 'pos' must be registered before udb_workspace_bytes"); return nullptr; }
   const int D = e->cfg.embed_dim, m = e->cfg.pos_grid, N = g.gh * g.gw;
   ShapeTables tb;
-  if (cudaMalloc(&tb.pos, static_cast<size_t>(N + 1) * D * 4) != cudaSuccess ||
-      cudaMalloc(&tb.scales, static_cast<size_t>(e->cfg.hidden / 2) * 4) != cudaSuccess) {
-    set_error("engine: cudaMalloc of the per-shape tables failed");
+  auto fail = [&tb](const char* why) -> const ShapeTables* {      // nothing half-built stays allocated
+    if (why) set_error("%s", why);
+    cudaFree(tb.pos);
+    cudaFree(tb.scales);
     return nullptr;
-  }
+  };
+  if (cudaMalloc(&tb.pos, static_cast<size_t>(N + 1) * D * 4) != cudaSuccess ||
+      cudaMalloc(&tb.scales, static_cast<size_t>(e->cfg.hidden / 2) * 4) != cudaSuccess)
+    return fail("engine: cudaMalloc of the per-shape tables failed");
   const float* pos = static_cast<const float*>(pw->second.p);
   cudaMemcpy(tb.pos, pos, static_cast<size_t>(D) * 4, cudaMemcpyDeviceToDevice);   // cls position
   if (g.gh == m && g.gw == m) {
     cudaMemcpy(tb.pos + D, pos + D, static_cast<size_t>(N) * D * 4, cudaMemcpyDeviceToDevice);
   } else if (udb_posembed_bicubic(pos + D, m, D, tb.pos + D, g.gh, g.gw, nullptr)) {
-    return nullptr;
+    return fail(nullptr);                                          // the operator has set the error text
   }
   std::vector<float> sc;
   ray_scale_table(g.gh, g.gw, e->cfg.hidden / 2, sc);
   cudaMemcpy(tb.scales, sc.data(), sc.size() * 4, cudaMemcpyHostToDevice);
-  if (cudaDeviceSynchronize() != cudaSuccess) { set_error("engine: preparing the per-shape tables failed"); return nullptr; }
+  if (cudaDeviceSynchronize() != cudaSuccess) return fail("engine: preparing the per-shape tables failed");
   return &(e->tables[key] = tb);
 }
 

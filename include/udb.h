@@ -564,6 +564,15 @@ void udb_v1_destroy(udb_engine_v1* e);
 int udb_v1_set_weight(udb_engine_v1* e, const char* name, const void* dev_ptr, const int64_t* shape, int32_t ndim,
                       int32_t dtype);
 int udb_v1_set_scalar(udb_engine_v1* e, const char* name, double value);
+/* Shape arithmetic of one V1 call, the engine's own copy of `_shapes` / `_paddings` (unidepthv1.py:30-46): the image is resized
+ * by `ratio` to (resized_h, resized_w) -- the larger side-ratio that still fits the fixed network input -- and zero-padded
+ * (pad_* >= 0 here; Python floor division kept for the general case) to net_h x net_w. */
+typedef struct udb_v1_geometry_t {
+  int32_t resized_h, resized_w;
+  int32_t pad_l, pad_r, pad_t, pad_b;
+  double ratio;
+} udb_v1_geometry_t;
+int udb_v1_geometry(int32_t H, int32_t W, int32_t net_h, int32_t net_w, udb_v1_geometry_t* out);
 /* bytes of workspace udb_infer_v1 needs for this shape (0 + udb_last_error on failure); must be called once per
  * (B, H, W) after the weights are registered and outside stream capture */
 size_t udb_v1_workspace_bytes(udb_engine_v1* e, int32_t B, int32_t H, int32_t W);

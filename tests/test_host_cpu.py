@@ -42,12 +42,12 @@ def test_ctypes_structs_match_c_layout():
                "udb_config_t": _cabi.Config, "udb_geometry_t": _cabi.Geometry, "udb_infer_args_t": _cabi.InferArgs,
                "udb_v1_preprocess_t": _cabi.V1Preprocess, "udb_layernorm_any_t": _cabi.LayerNormAny, "udb_v1_rays_t": _cabi.V1Rays,
                "udb_v1_postprocess_t": _cabi.V1Postprocess, "udb_v1_config_t": _cabi.V1Config, "udb_infer_v1_args_t": _cabi.InferV1Args,
-               "udb_profile_entry_t": _cabi.ProfileEntry}
+               "udb_v1_geometry_t": _cabi.V1Geometry, "udb_profile_entry_t": _cabi.ProfileEntry}
     last = {"udb_gemm_t": "ln_eps", "udb_conv_halo_t": "head_out", "udb_attn_t": "lo_off_o", "udb_layernorm_t": "out_split", "udb_preprocess_t": "split",
             "udb_small_linear_t": "ldr", "udb_ray_embed_t": "out_f32", "udb_postprocess_t": "out_rays",
             "udb_config_t": "pixels_max", "udb_geometry_t": "factor", "udb_infer_args_t": "depth_features",
             "udb_v1_preprocess_t": "patches", "udb_layernorm_any_t": "s2d_w", "udb_v1_rays_t": "sh_k", "udb_v1_postprocess_t": "out_points",
-            "udb_v1_config_t": "net_w", "udb_infer_v1_args_t": "out_depth", "udb_profile_entry_t": "bytes"}
+            "udb_v1_config_t": "net_w", "udb_infer_v1_args_t": "out_depth", "udb_v1_geometry_t": "ratio", "udb_profile_entry_t": "bytes"}
     src = '#include <stdio.h>\n#include <stddef.h>\n#include "udb.h"\nint main(){\n'
     for n in structs:
         src += f'printf("{n} %zu %zu\\n", sizeof({n}), offsetof({n}, {last[n]}));\n'
@@ -246,6 +246,22 @@ def test_v1_geometry_and_fail_loudly():
         (rh, rw), ratio = v1_shapes((int(h), int(w)), (462, 616))
         assert [rh, rw, *v1_paddings((rh, rw), (462, 616))] == z[f"shape{i}"].tolist()
         assert abs(ratio - float(z[f"ratio{i}"])) < 1e-12
+    # the C engine's own copy of that arithmetic (engine_v1.cu v1_geometry, exported as udb_v1_geometry) against the Python
+    # functions -- themselves checked against the reference just above -- on the golden cases and 400 random shapes
+    import ctypes as C
+    from unidepth_b200 import _cabi
+    lib, g = _cabi.lib(), _cabi.V1Geometry()
+    gen = torch.Generator().manual_seed(2)
+    shapes = [tuple(int(v) for v in c) for c in z["cases"]] + [(462, 616), (1, 1), (3000, 17), (17, 3000)]
+    shapes += [(int(torch.randint(8, 2600, (1,), generator=gen)), int(torch.randint(8, 2600, (1,), generator=gen))) for _ in range(400)]
+    for net in ((462, 616), (42, 56), (616, 462)):
+        for (h, w) in shapes:
+            (rh, rw), ratio = v1_shapes((h, w), net)
+            pl, pr, pt, pb = v1_paddings((rh, rw), net)
+            assert lib.udb_v1_geometry(h, w, net[0], net[1], C.byref(g)) == 0
+            assert (g.resized_h, g.resized_w, g.pad_l, g.pad_r, g.pad_t, g.pad_b) == (rh, rw, pl, pr, pt, pb), (h, w, net)
+            assert g.ratio == ratio, (h, w, net)
+    assert lib.udb_v1_geometry(0, 5, 462, 616, C.byref(g)) != 0
     cfg = json.load(open(os.path.join(ROOT, "tests", "golden", "config_v1_cnvnxtl.json")))
     cfg["model"]["pixel_encoder"]["arch"] = {"depths": [1, 1, 1, 1], "dims": [64, 64, 64, 64]}
     m = UniDepthV1(cfg)

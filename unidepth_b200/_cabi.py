@@ -109,6 +109,13 @@ class Geometry(C.Structure):
     ]
 
 
+class V1Geometry(C.Structure):
+    _fields_ = [
+        ("resized_h", i32), ("resized_w", i32), ("pad_l", i32), ("pad_r", i32), ("pad_t", i32), ("pad_b", i32),
+        ("ratio", C.c_double),
+    ]
+
+
 class InferArgs(C.Structure):
     _fields_ = [
         ("rgb", vp), ("rgb_is_u8", i32), ("normalize", i32), ("B", i32), ("H", i32), ("W", i32),
@@ -223,6 +230,7 @@ EXPORTS = {
     "udb_v1_destroy": (None, [vp]),
     "udb_v1_set_weight": (i32, [vp, C.c_char_p, vp, C.POINTER(i64), i32, i32]),
     "udb_v1_set_scalar": (i32, [vp, C.c_char_p, C.c_double]),
+    "udb_v1_geometry": (i32, [i32, i32, i32, i32, C.POINTER(V1Geometry)]),
     "udb_v1_workspace_bytes": (C.c_size_t, [vp, i32, i32, i32]),
     "udb_infer_v1": (i32, [vp, C.POINTER(InferV1Args), vp]),
     # peer-memory plumbing (multi-GPU gather)

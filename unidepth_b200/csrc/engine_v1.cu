@@ -512,6 +512,15 @@ int udb_v1_create(const udb_v1_config_t* cfg, udb_engine_v1** out) {
 
 void udb_v1_destroy(udb_engine_v1* e) { delete e; }
 
+int udb_v1_geometry(int32_t H, int32_t W, int32_t net_h, int32_t net_w, udb_v1_geometry_t* out) {
+  if (!out || H <= 0 || W <= 0 || net_h <= 0 || net_w <= 0) { set_error("udb_v1_geometry: bad argument"); return 1; }
+  const V1Geom g = v1_geometry(H, W, net_h, net_w);      // the function run_v1 uses
+  out->resized_h = g.rh; out->resized_w = g.rw;
+  out->pad_l = g.pad_l; out->pad_r = g.pad_r; out->pad_t = g.pad_t; out->pad_b = g.pad_b;
+  out->ratio = g.ratio;
+  return 0;
+}
+
 int udb_v1_set_weight(udb_engine_v1* e, const char* name, const void* dev_ptr, const int64_t* shape, int32_t ndim, int32_t dtype) {
   if (!e || !name || !dev_ptr || ndim < 0 || ndim > 4) { set_error("udb_v1_set_weight: bad argument"); return 1; }
   if (reinterpret_cast<uintptr_t>(dev_ptr) & 15) { set_error("udb_v1_set_weight(%s): pointer must be 16-byte aligned", name); return 1; }

@@ -515,6 +515,10 @@ int udb_geometry(const udb_engine* e, int32_t H, int32_t W, int32_t resolution_l
 /* Bytes of scratch udb_infer_v2 needs for this shape; also prepares the per-shape tables (may
  * allocate and launch on the default stream: call it outside graph capture). 0 = error. */
 size_t udb_workspace_bytes(udb_engine* e, int32_t B, int32_t H, int32_t W, int32_t resolution_level);
+/* The same number from a dry run of the schedule alone: walks every stage with the registered operands, checks their
+ * names and shapes, sizes the bump allocator -- and touches no device (no table is prepared, nothing is recorded), so it
+ * also works on a machine without a GPU.  udb_infer_v2 still requires udb_workspace_bytes.  0 = error. */
+size_t udb_schedule_bytes(udb_engine* e, int32_t B, int32_t H, int32_t W, int32_t resolution_level);
 
 typedef struct udb_infer_args_t {
   const void* rgb;            /* [B,3,H,W] uint8 or float32 (0..255 when normalize) */

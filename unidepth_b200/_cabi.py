@@ -206,6 +206,7 @@ EXPORTS = {
     "udb_set_scalar": (i32, [vp, C.c_char_p, C.c_double]),
     "udb_geometry": (i32, [vp, i32, i32, i32, C.POINTER(Geometry)]),
     "udb_workspace_bytes": (C.c_size_t, [vp, i32, i32, i32, i32]),
+    "udb_schedule_bytes": (C.c_size_t, [vp, i32, i32, i32, i32]),
     "udb_infer_v2": (i32, [vp, C.POINTER(InferArgs), vp]),
     # UniDepthV1 operators + engine
     "udb_v1_preprocess": (i32, [C.POINTER(V1Preprocess), vp]),

@@ -116,7 +116,7 @@ static int run(udb_engine* e, const udb_infer_args_t& a, const udb_geometry_t& g
     q.lda = 640 * sx; q.a_split_k = sp ? 640 : 0;
     q.bias = c.F("patch_b"); q.resid = tb.pos; q.resid_f32 = 1; q.ldr = D; q.out = x; q.out_f32 = 1;
     q.rows_per_group = N; q.group_stride = T; q.row_offset = 1; q.resid_mod = N; q.resid_row_offset = 1;
-    if (sp) c.expect2("patch_w", D, 3 * 640);
+    c.expect2("patch_w", D, sp ? 3 * 640 : 640);
     if (fuse) { q.out2 = x16; q.out2_leaky = 0; q.ln_stats_out = stats; q.ln_parts = ln_parts; q.ln_part_cols = ln_pc; }
     c.gemm(q);
     if (!c.dry && !c.rc)
@@ -139,8 +139,11 @@ static int run(udb_engine* e, const udb_infer_args_t& a, const udb_geometry_t& g
     int tap = 0;
     for (int i = 0; i < cf.depth; ++i) {
       const std::string b = idx("blocks.%d.", i);
-      if (sp) { c.expect2(b + "qkv_w", 3 * D, 3 * D); c.expect2(b + "proj_w", D, 3 * D); c.expect2(b + "fc1_w", 4 * D, 3 * D);
-                c.expect2(b + "fc2_w", D, 12 * D); }
+      // a weight packed for another mode (or transposed) must be refused, not read with the wrong leading dimension
+      c.expect2(b + (fuse ? "qkv_wf" : "qkv_w"), 3 * D, D * kx);
+      c.expect2(b + (fuse ? "fc1_wf" : "fc1_w"), 4 * D, D * kx);
+      c.expect2(b + "proj_w", D, D * kx);
+      c.expect2(b + "fc2_w", D, 4 * D * kx);
       if (fuse) {
         Ctx::G q{x16, c.H(b + "qkv_wf"), static_cast<int>(BT), 3 * D, D};
         q.bias = c.F(b + "qkv_c2"); q.ln_stats_in = stats; q.ln_c1 = c.F(b + "qkv_c1"); q.ln_parts = ln_parts; q.ln_part_cols = ln_pc;
@@ -469,6 +472,20 @@ int udb_geometry(const udb_engine* e, int32_t H, int32_t W, int32_t level, udb_g
   }
   paddings(H, W, e->cfg.ratio_min, e->cfg.ratio_max, out);
   return resize(e->cfg, level, out);
+}
+
+size_t udb_schedule_bytes(udb_engine* e, int32_t B, int32_t H, int32_t W, int32_t level) {
+  if (!e || B <= 0) { set_error("udb_schedule_bytes: bad argument"); return 0; }
+  udb_geometry_t g;
+  if (udb_geometry(e, H, W, level, &g)) return 0;
+  udb_infer_args_t a;
+  memset(&a, 0, sizeof(a));
+  a.B = B; a.H = H; a.W = W; a.resolution_level = level;
+  a.camera_k = reinterpret_cast<const float*>(16);   // the larger (GT-camera) variant, as udb_workspace_bytes sizes it
+  const ShapeTables none;                            // a dry run only hands the table pointers on
+  Arena ar(nullptr, 0);
+  if (run(e, a, g, none, ar, nullptr)) return 0;
+  return ar.peak + 256;
 }
 
 size_t udb_workspace_bytes(udb_engine* e, int32_t B, int32_t H, int32_t W, int32_t level) {

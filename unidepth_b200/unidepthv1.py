@@ -108,6 +108,15 @@ class UniDepthV1(nn.Module, PyTorchModelHubMixin,
             raise RuntimeError("unidepth_b200.UniDepthV1.infer needs the model on a CUDA device (model.to('cuda')); "
                                "there is no CPU fallback")
         torch.cuda.set_device(dev)
+        T, S = self._pack_tensors(dev)
+        self._packed = dict(T=T, S=S)
+        self._packed_key = self._fingerprint()
+        self._drop_engine()
+
+    def _pack_tensors(self, dev):
+        """({engine tensor name: tensor on `dev`}, {scalar name: float}): plain torch layout work.  `_pack` is the only
+        product caller (CUDA device); tests/test_engine_schedule_cpu.py runs it on the CPU to check, through the engine's
+        dry run, that the packer registers exactly the operands the C schedule asks for."""
         s = self.spec
         sd = {k: v.detach() for k, v in self.state_dict().items()}
         h16 = lambda t: t.to(f16).contiguous()
@@ -245,9 +254,7 @@ class UniDepthV1(nn.Module, PyTorchModelHubMixin,
             w = sd[f"{dl}{name}.weight"]                                             # [1, C, 3, 3] -> [9, C]
             T[f"{name}.w"] = c32(w.permute(0, 2, 3, 1).reshape(9, w.shape[1]))
             S[f"{name}.b"] = float(sd[f"{dl}{name}.bias"].item())
-        self._packed = dict(T=T, S=S)
-        self._packed_key = self._fingerprint()
-        self._drop_engine()
+        return T, S
 
     def _weights(self):
         if self._packed is None or self._packed_key != self._fingerprint():
@@ -269,10 +276,8 @@ class UniDepthV1(nn.Module, PyTorchModelHubMixin,
         except Exception:
             pass
 
-    def _get_engine(self):
-        P = self._weights()
-        if self._engine is not None:
-            return self._engine
+    def _engine_config(self) -> "cabi.V1Config":
+        """udb_v1_config_t of this model (include/udb.h)."""
         s = self.spec
         cfg = cabi.V1Config()
         for i in range(4):
@@ -281,16 +286,29 @@ class UniDepthV1(nn.Module, PyTorchModelHubMixin,
         for i in range(3):
             cfg.dec_depths[i] = s.dec_depths[i]
         cfg.net_h, cfg.net_w = self.image_shape
-        handle = C.c_void_p()
+        return cfg
+
+    @staticmethod
+    def _register(handle, tensors: dict, scalars: dict):
+        """udb_v1_set_weight / udb_v1_set_scalar for every packed operand (the engine borrows the pointers)."""
         lib = cabi.lib()
-        cabi.check(lib.udb_v1_create(C.byref(cfg), C.byref(handle)), "udb_v1_create")
-        for name, t in P["T"].items():
-            assert t.is_cuda and t.is_contiguous() and t.dtype in (f16, f32), name
+        for name, t in tensors.items():
+            assert t.is_contiguous() and t.dtype in (f16, f32), name
             shape = (C.c_int64 * max(t.ndim, 1))(*t.shape)
             cabi.check(lib.udb_v1_set_weight(handle, name.encode(), C.c_void_p(t.data_ptr()), shape, t.ndim,
                                              cabi.DT_F32 if t.dtype == f32 else cabi.DT_F16), f"udb_v1_set_weight({name})")
-        for name, v in P["S"].items():
+        for name, v in scalars.items():
             cabi.check(lib.udb_v1_set_scalar(handle, name.encode(), float(v)), f"udb_v1_set_scalar({name})")
+
+    def _get_engine(self):
+        P = self._weights()
+        if self._engine is not None:
+            return self._engine
+        handle = C.c_void_p()
+        cabi.check(cabi.lib().udb_v1_create(C.byref(self._engine_config()), C.byref(handle)), "udb_v1_create")
+        for name, t in P["T"].items():
+            assert t.is_cuda, name
+        self._register(handle, P["T"], P["S"])
         self._engine, self._engine_device = handle, self.device
         return handle
 

@@ -149,11 +149,19 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
         if dev.type != "cuda":
             raise RuntimeError("unidepth_b200.UniDepthV2.infer needs the model on a CUDA device "
                                "(model.to('cuda')); there is no CPU fallback")
+        torch.cuda.set_device(dev)      # callers hold `with torch.cuda.device(self.device)`
+        self._packed = self._pack_tensors(dev)
+        self._packed_key = self._fingerprint()
+        self._drop_engine()
+
+    def _pack_tensors(self, dev) -> dict:
+        """The packed operands as tensors on `dev` (plain torch layout work, no kernel involved).  `_pack` is the only
+        product caller (CUDA device); tests/test_engine_schedule_cpu.py runs it on the CPU to check, through the engine's
+        dry run, that every packing mode registers exactly the operands the C schedule asks for."""
         s = self.spec
         if s.kernel_size != 3:
             raise NotImplementedError(f"pixel_decoder.kernel_size={s.kernel_size}: the residual conv units run as 3x3 "
                                       "convolutions (every shipped UniDepthV2 config sets 3)")
-        torch.cuda.set_device(dev)      # callers hold `with torch.cuda.device(self.device)`
         sd = {k: v.detach() for k, v in self.state_dict().items()}
         h16 = lambda t: t.to(f16).contiguous()
         c32 = lambda t: t.to(f32).contiguous()
@@ -332,9 +340,7 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
         ones[:c_hr_real] = 1.0               # padded channels: weight 0 -> normalised value 0
         P["ln_ones"] = ones
         P["ln_zeros"] = torch.zeros(c_hr, device=dev, dtype=f32)
-        self._packed = P
-        self._packed_key = self._fingerprint()
-        self._drop_engine()
+        return P
 
     # ------------------------------------------------------------------ C engine (udb_create / udb_infer_v2)
     def _drop_engine(self):
@@ -400,14 +406,9 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
             S[f"heads.{i}.add"] = hd["add"]
         return T, S
 
-    def _get_engine(self):
-        P = self._weights()
-        sc = self.shape_constraints
-        key = (tuple(sc["ratio_bounds"]), sc["pixels_min"], sc["pixels_max"])
-        if self._engine is not None and self._engine_key == key:
-            return self._engine
-        self._drop_engine()
-        s = self.spec
+    def _engine_config(self, P: dict) -> "cabi.Config":
+        """udb_config_t of this model (include/udb.h)."""
+        s, sc = self.spec, self.shape_constraints
         cfg = cabi.Config()
         cfg.embed_dim, cfg.depth, cfg.enc_heads = s.embed_dim, s.depth, s.enc_heads
         for i, t in enumerate(s.taps):
@@ -419,16 +420,32 @@ class UniDepthV2(nn.Module, PyTorchModelHubMixin,
             cfg.dec_depths[i] = dd
         cfg.ratio_min, cfg.ratio_max = sc["ratio_bounds"]
         cfg.pixels_min, cfg.pixels_max = sc["pixels_min"], sc["pixels_max"]
-        handle = C.c_void_p()
-        cabi.check(cabi.lib().udb_create(C.byref(cfg), C.byref(handle)), "udb_create")
-        tensors, scalars = self._flatten_packed(P)
+        return cfg
+
+    @staticmethod
+    def _register(handle, tensors: dict, scalars: dict):
+        """udb_set_weight / udb_set_scalar for every packed operand (the engine borrows the pointers)."""
         for name, t in tensors.items():
-            assert t.is_cuda and t.is_contiguous() and t.dtype in (f16, f32), name
+            assert t.is_contiguous() and t.dtype in (f16, f32), name
             shape = (C.c_int64 * max(t.ndim, 1))(*t.shape)
             cabi.check(cabi.lib().udb_set_weight(handle, name.encode(), C.c_void_p(t.data_ptr()), shape, t.ndim,
                                                  cabi.DT_F32 if t.dtype == f32 else cabi.DT_F16), f"udb_set_weight({name})")
         for name, v in scalars.items():
             cabi.check(cabi.lib().udb_set_scalar(handle, name.encode(), float(v)), f"udb_set_scalar({name})")
+
+    def _get_engine(self):
+        P = self._weights()
+        sc = self.shape_constraints
+        key = (tuple(sc["ratio_bounds"]), sc["pixels_min"], sc["pixels_max"])
+        if self._engine is not None and self._engine_key == key:
+            return self._engine
+        self._drop_engine()
+        handle = C.c_void_p()
+        cabi.check(cabi.lib().udb_create(C.byref(self._engine_config(P)), C.byref(handle)), "udb_create")
+        tensors, scalars = self._flatten_packed(P)
+        for name, t in tensors.items():
+            assert t.is_cuda, name
+        self._register(handle, tensors, scalars)
         self._engine, self._engine_key = handle, key
         self._engine_device = self.device
         self._engine_tensors = tensors          # the engine borrows these pointers

@@ -70,3 +70,70 @@ def test_gelu_erf_approximation_of_the_gemm_epilogue():
     gelu = 0.5 * x * (1.0 + np.copysign(1.0 - r, x))
     ref = 0.5 * x * (1.0 + erf(x / np.sqrt(2.0)))
     assert np.abs(gelu - ref).max() < 2e-6      # absolute; the epilogue's output is rounded to f16 (2^-11 relative) afterwards
+
+
+def _infer_with_f16_operands(sd, cfg, rgb, level):
+    """The fp32 oracle with ONE change: every operand of a Linear / convolution / attention product is rounded to f16 before
+    the (fp32) product, and attention probabilities and outputs are rounded to f16 -- i.e. what the tcgen05 kernels are fed
+     -- while the camera head stays fp32 as on the GPU.  No kernel is involved: this is the arithmetic
+    model of the default precision mode."""
+    import torch
+    import torch.nn.functional as F
+    import unidepth_oracle as O
+    q16 = lambda t: t.to(torch.float16).to(torch.float32)
+    lin, sdpa, conv, convt, cam = O._lin, O._sdpa, F.conv2d, F.conv_transpose2d, O.camera_head
+
+    def lin16(x, s, prefix, bias=True):
+        return F.linear(q16(x), q16(s[prefix + ".weight"]), s.get(prefix + ".bias") if bias else None)
+
+    def sdpa16(q, k, v):
+        q, k, v = q16(q), q16(k), q16(v)
+        s = (q @ k.transpose(-1, -2)) / (q.shape[-1] ** 0.5)
+        p = torch.exp(s - s.max(-1, keepdim=True).values)
+        return q16((q16(p) @ v) / p.sum(-1, keepdim=True))
+
+    def cam32(*a, **k):
+        O._lin, O._sdpa = lin, sdpa
+        try:
+            return cam(*a, **k)
+        finally:
+            O._lin, O._sdpa = lin16, sdpa16
+
+    O._lin, O._sdpa, O.camera_head = lin16, sdpa16, cam32
+    O.F.conv2d = lambda x, w, b=None, *a, **k: conv(q16(x), q16(w), b, *a, **k)
+    O.F.conv_transpose2d = lambda x, w, b=None, *a, **k: convt(q16(x), q16(w), b, *a, **k)
+    try:
+        return O.infer_v2(sd, cfg, rgb, resolution_level=level)
+    finally:
+        O._lin, O._sdpa, O.camera_head = lin, sdpa, cam
+        O.F.conv2d, O.F.conv_transpose2d = conv, convt
+
+
+def test_f16_operand_rounding_explains_the_measured_gpu_error():
+    """DESIGN.md section 4 / 6 claim: the default mode's residual against the reference is f16 OPERAND ROUNDING, not logic.
+    GPU-side proof: the split-precision mode removes it (intrinsics 1.8e-6).  CPU-side, shown here: rounding the operands in
+    the fp32 oracle -- nothing else -- reproduces the errors MEASURED on the B200 (tests/test_infer_parity_gpu.py::MEASURED,
+    profiles/r02_parity_gpu.log) to within a factor of two, case by case, for depth ARel, depth max-rel and the intrinsics."""
+    import json
+    import os
+    import torch
+    from fixture import make_state_dict
+    from test_infer_parity_gpu import MEASURED
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    for name in ("vits_120x160", "vits_pad_96x288_rl3", "vitb_112x160"):
+        z = np.load(os.path.join(gold, name + ".npz"))
+        meta = json.loads(str(z["__meta__"]))
+        cfg = json.load(open(os.path.join(gold, meta["config"])))
+        sd = make_state_dict(cfg, meta["seed"])
+        b, h, w = meta["shape"]
+        rgb = torch.randint(0, 256, (b, 3, h, w), dtype=torch.uint8, generator=torch.Generator().manual_seed(1234 + meta["seed"]))
+        out = _infer_with_f16_operands(sd, cfg, rgb, meta["resolution_level"])
+        k, kr = out["intrinsics"], torch.from_numpy(z["intrinsics"])
+        kerr = max(((k[:, i, j] - kr[:, i, j]).abs() / kr[:, i, j].abs()).max().item() for i, j in ((0, 0), (1, 1), (0, 2), (1, 2)))
+        rel = (out["depth"] - torch.from_numpy(z["depth"])).abs() / torch.from_numpy(z["depth"])
+        arel, dmax = rel.mean().item(), rel.max().item()
+        m_arel, m_dmax, m_k = MEASURED["golden_" + name]
+        print(f"{name}: emulated f16 operands: depth ARel {arel:.2e} max {dmax:.2e} K {kerr:.2e} | measured on the B200: "
+              f"{m_arel:.2e} {m_dmax:.2e} {m_k:.2e} | ratio {arel / m_arel:.2f} {dmax / m_dmax:.2f} {kerr / m_k:.2f}")
+        for got, meas in ((arel, m_arel), (dmax, m_dmax), (kerr, m_k)):
+            assert 0.5 < got / meas < 2.0, (name, got, meas)
